@@ -1,0 +1,245 @@
+// One GaussianFit.fit() for one spot, written once for two executors:
+//   * WarpExec (fit_kernels.cu): 32 lanes of the warp that owns the spot; voxels are strided
+//     over the lanes, sums are combined with shuffles, the 10x10 algebra runs on lane 0 with
+//     its state in shared memory;
+//   * SerialExec (tests/hostsim): one "lane" on the CPU, used to debug the numerics in a
+//     container without a GPU.  It is test infrastructure, never a product fallback.
+// Follows GaussianFit.__init__ / fit / to_natural_paramaters of External/Fitting_v4.py:166-393
+// (and Fitting_v3.py:51-254).
+#pragma once
+#include "gauss_model.h"
+#include "lm_core.h"
+
+namespace ia3 {
+
+// Per-spot scratch that must be visible to every lane (shared memory on the device).
+template <typename T>
+struct SpotShared {
+  LMState st;
+  VoxConsts<T> vc;
+  double A[NTRI];
+  double g[NP];
+  double x0[NP];
+  double small10[10], large10[10];
+  double bcast[4];
+  int ibcast[4];
+};
+
+// ---- initial guess (GaussianFit.__init__, Fitting_v4.py:174-185) ---------------------------
+// dv[0..m) holds the float64 voxel values in voxel order; tmp[0..m) is scratch of the same size.
+template <typename Exec>
+IA3_HD void select10(Exec& ex, const double* dv, double* tmp, int m, bool largest, double* out10) {
+  for (int k = ex.lane(); k < m; k += Exec::W) tmp[k] = largest ? -dv[k] : dv[k];
+  ex.sync();
+  for (int r = 0; r < 10; ++r) {
+    double best = INFINITY;
+    int bk = 0x7fffffff;
+    for (int k = ex.lane(); k < m; k += Exec::W) {
+      double v = tmp[k];
+      if (v < best) { best = v; bk = k; }   // ascending k inside a lane: first minimum kept
+    }
+    ex.argmin(best, bk);
+    if (ex.lane() == 0) { out10[r] = largest ? -best : best; if (bk != 0x7fffffff) tmp[bk] = INFINITY; }
+    ex.sync();
+  }
+}
+
+// numpy's float64 pairwise sum for n = 10 (8-wide unrolled block, then the tail), / 10
+IA3_HD double mean10_numpy(const double* a) {
+  double res = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  res += a[8];
+  res += a[9];
+  return res / 10.0;
+}
+
+// Builds x0 (as float32-rounded values, :185).  init_w_raw[3]: v4 -> the three entries are the
+// same scalar init_w; v3 -> per-axis init_w.  Also fills fp.init_wt for v3.
+IA3_HD void initial_guess(FitParams& fp, const double* small10_asc, const double* large10_desc,
+                          const double* init_w_raw, double* x0) {
+  const double eps = exp(-10.0);
+  double asc[10];
+  for (int i = 0; i < 10; ++i) asc[i] = large10_desc[9 - i];
+  double mb = mean10_numpy(small10_asc), mh = mean10_numpy(asc);
+  double bk = log(mb > eps ? mb : eps), hh = log(mh > eps ? mh : eps);   // np.max([mean, eps])
+  if (mb != mb) bk = mb;  // np.max propagates NaN
+  if (mh != mh) hh = mh;
+  double wg[3];
+  if (fp.personality == 4) {
+    for (int i = 0; i < 3; ++i) {
+      double wsq = init_w_raw[i] * init_w_raw[i];
+      wg[i] = log((fp.max_w2 - wsq) / (wsq - fp.min_w2));
+    }
+  } else {
+    // Fitting_v3.py:70-75 -- the guard compares w^2 with the *unsquared* bounds and the
+    // replacement value is 1.5**2 (which is then squared again)
+    const double max_w = sqrt(fp.max_w2), min_w = sqrt(fp.min_w2);
+    for (int i = 0; i < 3; ++i) {
+      double iw = init_w_raw[i];
+      if (iw * iw > max_w || iw * iw < min_w) iw = 1.5 * 1.5;
+      wg[i] = log((fp.max_w2 - iw * iw) / (iw * iw - fp.min_w2));
+      fp.init_wt[i] = wg[i];
+    }
+  }
+  const double raw[NP] = {bk, hh, 0, 0, 0, wg[0], wg[1], wg[2], 0, 0};
+  for (int i = 0; i < NP; ++i) x0[i] = (double)(float)raw[i];
+}
+
+// ---- voxel passes --------------------------------------------------------------------------
+// Vox provides: int m; void get(int k, T& X0, T& X1, T& X2, T& data) with coordinates relative
+// to the spot's integer origin.
+
+// |f| with MINPACK enorm's semantics.  enorm keeps three accumulators (large / mid / small
+// components) so that it neither overflows nor underflows; what matters for parity is how it
+// behaves when the model blows up (v3 has no overflow guards and regularly proposes bk ~ 1e6):
+//   * one +-inf residual           -> inf          (x1max = inf, s1 = 1)
+//   * two or more inf residuals    -> NaN          ((inf/inf)^2)
+//   * finite but > rgiant/m        -> finite norm, where a plain sum of squares gives inf
+// lmder's step-bound update then takes different branches for inf / NaN / finite (the test
+// "0.1*fnorm1 >= fnorm" is false for NaN), so the trust region shrinks by 0.1 or by ~0.25.
+// Mid-range components use the plain sum of squares; the (very rare) large ones need a second
+// sweep once the largest magnitude is known.
+template <typename T, typename Exec, typename Vox>
+IA3_HD double pass_residual(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* sum_abs) {
+  const double agiant = 1.304e19 / (double)vox.m;
+  double s2 = 0.0, sa = 0.0, big = 0.0;
+  int ninf = 0, nlarge = 0, nnan = 0;
+  for (int k = ex.lane(); k < vox.m; k += Exec::W) {
+    T X0, X1, X2, d;
+    vox.get(k, X0, X1, X2, d);
+    const double r = (double)eval_res<T>(vc, X0, X1, X2, d);
+    const double a = fabs(r);
+    sa += a;
+    if (a < agiant) s2 += r * r;
+    else if (a != a) nnan += 1;
+    else { nlarge += 1; if (a > DBL_MAX) ninf += 1; else big = fmax(big, a); }
+  }
+  s2 = ex.allsum(s2);
+  if (sum_abs) *sum_abs = ex.allsum(sa);
+  nlarge = ex.allsum_int(nlarge);
+  nnan = ex.allsum_int(nnan);
+  if (nlarge == 0) return nnan ? NAN : sqrt(s2);   // sqrt taken here so callers get the norm
+  ninf = ex.allsum_int(ninf);
+  if (ninf == 1) return INFINITY;
+  if (ninf >= 2) return NAN;
+  big = ex.allmax(big);
+  double s1 = 0.0;
+  for (int k = ex.lane(); k < vox.m; k += Exec::W) {
+    T X0, X1, X2, d;
+    vox.get(k, X0, X1, X2, d);
+    const double a = fabs((double)eval_res<T>(vc, X0, X1, X2, d));
+    if (a >= agiant) { const double q = a / big; s1 += q * q; }
+  }
+  s1 = ex.allsum(s1);
+  return big * sqrt(s1 + (s2 / big) / big);
+}
+
+template <typename T, typename Exec, typename Vox>
+IA3_HD void pass_jacobian(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* A_out, double* g_out) {
+  double A[NTRI], g[NP];
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) A[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) g[i] = 0.0;
+  for (int k = ex.lane(); k < vox.m; k += Exec::W) {
+    T X0, X1, X2, d, res;
+    float J[NP];
+    vox.get(k, X0, X1, X2, d);
+    eval_jac<T>(vc, X0, X1, X2, d, res, J);
+    const double r = (double)res;
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const double ji = (double)J[i];
+      g[i] += ji * r;
+#pragma unroll
+      for (int j = i; j < NP; ++j) { A[idx] += ji * (double)J[j]; ++idx; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) { double s = ex.allsum(A[i]); if (ex.lane() == 0) A_out[i] = s; }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { double s = ex.allsum(g[i]); if (ex.lane() == 0) g_out[i] = s; }
+}
+
+struct FitResult {
+  double p_raw[NP];
+  float ps[NOUT];
+  int nfev, njev, info;
+};
+
+// Runs leastsq from sh.x0.  Every lane must call this; results are valid on lane 0 after return
+// (and in sh.st.x for everybody after the final sync).
+template <typename T, typename Exec, typename Vox>
+IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen_est,
+                   const double* origin, const Vox& vox, SpotShared<T>& sh) {
+  LMState& st = sh.st;
+  // f(x0)
+  if (ex.lane() == 0) {
+    ModelConsts mc;
+    model_consts(fp, cen_est, sh.x0, false, mc);
+    narrow_consts<T>(mc, origin, false, sh.vc);
+  }
+  ex.sync();
+  double fn0 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
+  if (ex.lane() == 0) lm_init(st, sh.x0, fn0);
+  ex.sync();
+  for (;;) {
+    // Jacobian at st.x
+    if (ex.lane() == 0) {
+      ModelConsts mc;
+      model_consts(fp, cen_est, st.x, true, mc);
+      narrow_consts<T>(mc, origin, true, sh.vc);
+    }
+    ex.sync();
+    pass_jacobian<T>(ex, sh.vc, vox, sh.A, sh.g);
+    ex.sync();
+    if (ex.lane() == 0) sh.ibcast[0] = lm_outer(st, cfg, sh.A, sh.g) ? 1 : 0;
+    ex.sync();
+    if (!sh.ibcast[0]) break;
+    int action;
+    for (;;) {
+      if (ex.lane() == 0) {
+        lm_propose(st);
+        ModelConsts mc;
+        model_consts(fp, cen_est, st.xt, false, mc);
+        narrow_consts<T>(mc, origin, false, sh.vc);
+      }
+      ex.sync();
+      double fn1 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
+      if (ex.lane() == 0) sh.ibcast[1] = lm_judge(st, cfg, fn1);
+      ex.sync();
+      action = sh.ibcast[1];
+      if (action != LM_RETRY) break;
+    }
+    if (action == LM_DONE) break;
+  }
+  ex.sync();
+}
+
+// to_natural_paramaters() with the final parameters (Fitting_v4.py:244-258): ps[0..9] natural
+// parameters, ps[10] = mean |residual| over the fitted voxels; all cast to float32.
+template <typename T, typename Exec, typename Vox>
+IA3_HD void finish_fit(Exec& ex, const FitParams& fp, const double* cen_est, const double* origin,
+                       const Vox& vox, SpotShared<T>& sh, FitResult* out /*lane 0 writes*/) {
+  if (ex.lane() == 0) {
+    ModelConsts mc;
+    model_consts(fp, cen_est, sh.st.x, false, mc);
+    narrow_consts<T>(mc, origin, false, sh.vc);
+  }
+  ex.sync();
+  double sa = 0.0;
+  pass_residual<T>(ex, sh.vc, vox, &sa);
+  if (ex.lane() == 0) {
+    double nat[10];
+    natural_params(fp, cen_est, sh.st.x, nat);
+    for (int i = 0; i < 10; ++i) out->ps[i] = (float)nat[i];
+    out->ps[10] = (float)(sa / (double)vox.m);
+    for (int i = 0; i < NP; ++i) out->p_raw[i] = sh.st.x[i];
+    out->nfev = sh.st.nfev;
+    out->njev = sh.st.njev;
+    out->info = sh.st.info;
+  }
+  ex.sync();
+}
+
+}  // namespace ia3

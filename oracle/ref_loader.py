@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *real* reference modules under import shims.
+
+This file is part of ``oracle/`` and must never be imported by the product package
+(``imageanalysis3_b200``).  It only works where ``/root/reference`` exists (the build
+container); the GPU box does not have it.  It is used to
+  * pin the restated oracle (``oracle/seed_oracle.py``, ``oracle/fit_oracle.py``) against the
+    reference's own code, and
+  * generate the committed fixtures under ``tests/golden/`` (``oracle/make_golden.py``).
+
+Shims: the reference was written against numpy 1.x / old scipy and
+imports GUI / FFT packages that are not installed here:
+  np.int / np.float aliases               spot_tools/fitting.py:60,63,150
+  scipy.signal.gaussian                   External/Fitting_v4.py:13
+  pyfftw.interfaces.numpy_fft             External/Fitting_v4.py:5-6
+  matplotlib.pyplot                       External/Fitting_v4.py:753
+  parent package constants                __init__.py:4-19, spot_tools/__init__.py:4-8
+"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+REF_ROOT = os.environ.get("IA3_REFERENCE_ROOT", "/root/reference")
+_PKG = "IA3REF"
+_cache = {}
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, "spot_tools", "fitting.py"))
+
+
+def _install_shims():
+    import scipy.fft
+    import scipy.signal
+    import scipy.signal.windows
+
+    if not hasattr(np, "int"):
+        np.int = int
+    if not hasattr(np, "float"):
+        np.float = float
+    if not hasattr(scipy.signal, "gaussian"):
+        scipy.signal.gaussian = scipy.signal.windows.gaussian
+    if "pyfftw" not in sys.modules:
+        m0 = types.ModuleType("pyfftw")
+        m1 = types.ModuleType("pyfftw.interfaces")
+        m2 = types.ModuleType("pyfftw.interfaces.numpy_fft")
+        m2.rfftn = scipy.fft.rfftn
+        m2.irfftn = scipy.fft.irfftn
+        m0.interfaces = m1
+        m1.numpy_fft = m2
+        sys.modules.update({"pyfftw": m0, "pyfftw.interfaces": m1, "pyfftw.interfaces.numpy_fft": m2})
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except Exception:
+            mm = types.ModuleType("matplotlib")
+            mp = types.ModuleType("matplotlib.pyplot")
+            mm.pyplot = mp
+            sys.modules.update({"matplotlib": mm, "matplotlib.pyplot": mp})
+
+
+def _load(name, relpath):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def load():
+    """Return a namespace with .Fitting_v3, .Fitting_v4, .fitting, .visual (lifted functions)."""
+    if "ns" in _cache:
+        return _cache["ns"]
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    _install_shims()
+    sigma_zxy = [1.35, 1.9, 1.9]
+    root = types.ModuleType(_PKG)
+    root.__path__ = []
+    root._correction_folder = ""
+    root._temp_folder = ""
+    root._distance_zxy = [200, 108, 108]
+    root._sigma_zxy = sigma_zxy
+    root._allowed_colors = ["750", "647", "561", "488", "405"]
+    root._image_size = [30, 2048, 2048]
+    sys.modules[_PKG] = root
+
+    ext = types.ModuleType(_PKG + ".External")
+    ext.__path__ = [os.path.join(REF_ROOT, "External")]
+    ext._sigma_zxy = sigma_zxy
+    sys.modules[_PKG + ".External"] = ext
+    root.External = ext
+
+    st = types.ModuleType(_PKG + ".spot_tools")
+    st.__path__ = []
+    st._seed_th = {"750": 400, "647": 600, "561": 400}
+    sys.modules[_PKG + ".spot_tools"] = st
+    root.spot_tools = st
+
+    vt = types.ModuleType(_PKG + ".visual_tools")
+    vt.get_seed_points_base = lambda *a, **k: None  # imported but unused by spot_tools/fitting.py:12
+    sys.modules[_PKG + ".visual_tools"] = vt
+    root.visual_tools = vt
+
+    v3 = _load(_PKG + ".External.Fitting_v3", "External/Fitting_v3.py")
+    v4 = _load(_PKG + ".External.Fitting_v4", "External/Fitting_v4.py")
+    ext.Fitting_v3 = v3
+    ext.Fitting_v4 = v4
+    fitting = _load(_PKG + ".spot_tools.fitting", "spot_tools/fitting.py")
+
+    ns = types.SimpleNamespace(Fitting_v3=v3, Fitting_v4=v4, fitting=fitting, visual=_lift_visual(v3, sigma_zxy))
+    _cache["ns"] = ns
+    return ns
+
+
+def _lift_visual(v3, sigma_zxy):
+    """visual_tools.py does not import here (matplotlib/skimage/...); lift the four seeding
+    functions (visual_tools.py:260-381, 1775-1870, 3081-3139) out of the file by AST."""
+    from scipy.ndimage import gaussian_filter, maximum_filter, minimum_filter, median_filter
+
+    wanted = {"get_STD_centers", "get_seed_points_base", "get_seed_in_distance", "find_matched_seeds",
+              "select_sparse_centers"}
+    with open(os.path.join(REF_ROOT, "visual_tools.py"), "r", encoding="utf-8", errors="replace") as fh:
+        tree = ast.parse(fh.read())
+    nodes = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    env = dict(np=np, gaussian_filter=gaussian_filter, maximum_filter=maximum_filter,
+               minimum_filter=minimum_filter, median_filter=median_filter,
+               Fitting_v3=v3, _sigma_zxy=sigma_zxy, os=os, sys=sys)
+    code = compile(ast.Module(body=nodes, type_ignores=[]), "<reference visual_tools.py (lifted)>", "exec")
+    exec(code, env)
+    return types.SimpleNamespace(**{k: env[k] for k in wanted if k in env})
