@@ -1,0 +1,318 @@
+"""ctypes binding of libia3b200.so (C ABI in include/ia3b200.h).
+
+There is deliberately no CPU fallback: if the library is missing or no B200 is visible the
+calls raise.  CUDA is initialised lazily on first use inside the calling process, so the module
+can be imported (and forked, e.g. by multiprocessing.Pool as the reference's callers do,
+classes/field_of_view.py:1129) before any GPU work happens.
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libia3b200.so")
+
+DTYPE_U16, DTYPE_F32, DTYPE_F64 = 0, 1, 2
+_NP2DT = {np.dtype(np.uint16): DTYPE_U16, np.dtype(np.float32): DTYPE_F32, np.dtype(np.float64): DTYPE_F64}
+
+
+class IA3Error(RuntimeError):
+    pass
+
+
+class SeedCfg(C.Structure):
+    _fields_ = [("w_fg", C.POINTER(C.c_double)), ("r_fg", C.c_int),
+                ("w_bg", C.POINTER(C.c_double)), ("r_bg", C.c_int),
+                ("filt_size", C.c_int), ("variant", C.c_int),
+                ("edge", C.c_double), ("h_min", C.c_double)]
+
+
+class SeedTiming(C.Structure):
+    _fields_ = [("ms_gauss_fg", C.c_float), ("ms_gauss_bg", C.c_float), ("ms_rank", C.c_float),
+                ("ms_compact", C.c_float), ("ms_total", C.c_float)]
+
+
+class FitCfg(C.Structure):
+    _fields_ = [("personality", C.c_int), ("radius", C.c_int),
+                ("min_w", C.c_double), ("max_w", C.c_double),
+                ("init_w", C.c_double * 3), ("weight_sigma", C.c_double),
+                ("maxfev", C.c_int), ("eval_fp32", C.c_int)]
+
+
+EXPORTS = [
+    "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count",
+    "ia3_timer_start", "ia3_timer_stop",
+    "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy",
+    "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume",
+    "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
+    "ia3_fit_first_resolve", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_get_volume",
+    "ia3_fit_get_rec", "ia3_fit_num_levels", "ia3_fit_last_ms", "ia3_gaussfit_batch", "ia3_gauss_eval",
+]
+
+_lib = None
+# bytes this process copied through the C ABI (host->device, device->host); bench.py's e2e record
+COPIED = {"h2d": 0, "d2h": 0}
+
+
+def load():
+    """Load the shared library (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IA3Error(f"{LIB_PATH} not found: build it with `python -m imageanalysis3_b200.build` "
+                       "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    P = C.POINTER
+    lib.ia3_last_error.restype = C.c_char_p
+    lib.ia3_launch_count.restype = i64
+    lib.ia3_fit_last_ms.restype = C.c_float
+    lib.ia3_init.argtypes = [i32]
+    lib.ia3_stack_create.argtypes = [vp, i32, i32, i32, i32, P(vp)]
+    lib.ia3_stack_wrap_device.argtypes = [vp, i32, i32, i32, i32, P(vp)]
+    lib.ia3_stack_destroy.argtypes = [vp]
+    lib.ia3_seed_run.argtypes = [vp, P(SeedCfg), P(i64), P(SeedTiming)]
+    lib.ia3_seed_fetch.argtypes = [vp, vp, vp, i64]
+    lib.ia3_seed_fetch_volume.argtypes = [vp, i32, vp]
+    lib.ia3_fit_create.argtypes = [vp, vp, i64, P(FitCfg), P(vp)]
+    lib.ia3_fit_destroy.argtypes = [vp]
+    lib.ia3_fit_first_prepare.argtypes = [vp, P(i64)]
+    lib.ia3_fit_first_ties.argtypes = [vp, vp, vp, i64]
+    lib.ia3_fit_first_resolve.argtypes = [vp, vp, i64]
+    lib.ia3_fit_first_run.argtypes = [vp, dbl, vp, vp, vp, vp, vp]
+    lib.ia3_fit_repeat_sweep.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
+    lib.ia3_fit_get_volume.argtypes = [vp, i32, vp]
+    lib.ia3_fit_get_rec.argtypes = [vp, i64, vp, vp, P(i32)]
+    lib.ia3_fit_num_levels.argtypes = [vp]
+    lib.ia3_fit_last_ms.argtypes = [vp]
+    lib.ia3_gaussfit_batch.argtypes = [P(FitCfg), dbl, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ia3_gauss_eval.argtypes = [P(FitCfg), dbl, vp, vp, vp, i64, vp]
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise IA3Error(load().ia3_last_error().decode("utf-8", "replace"))
+
+
+def init(device=-1):
+    _check(load().ia3_init(int(device)))
+
+
+def timer_start():
+    _check(load().ia3_timer_start())
+
+
+def timer_stop():
+    ms = C.c_float(0)
+    _check(load().ia3_timer_stop(C.byref(ms)))
+    return float(ms.value)
+
+
+def launch_count():
+    return int(load().ia3_launch_count())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Stack:
+    """An image stack resident in HBM (one H2D copy shared by the seed and fit stages)."""
+
+    def __init__(self, im=None, device_ptr=None, shape=None, dtype=None):
+        lib = load()
+        self._h = C.c_void_p()
+        self._keep = None
+        if device_ptr is not None:
+            self.shape = tuple(int(s) for s in shape)
+            self.dtype = np.dtype(dtype)
+            _check(lib.ia3_stack_wrap_device(C.c_void_p(int(device_ptr)), _NP2DT[self.dtype], *self.shape, C.byref(self._h)))
+        else:
+            if not isinstance(im, np.ndarray):
+                raise TypeError(f"image given should be a numpy.ndarray, but {type(im)} is given.")
+            if im.ndim != 3:
+                raise ValueError("the device path needs a 3D (Z, X, Y) stack")
+            if im.dtype not in _NP2DT:
+                if im.dtype.kind in "ui" and im.size and im.min() >= 0 and im.max() <= 65535:
+                    im = im.astype(np.uint16)
+                elif im.dtype.kind in "uib":
+                    im = im.astype(np.float64)
+                else:
+                    im = im.astype(np.float64)
+            im = np.ascontiguousarray(im)
+            self.shape = im.shape
+            self.dtype = im.dtype
+            self._keep = im
+            _check(lib.ia3_stack_create(_ptr(im), _NP2DT[im.dtype], *im.shape, C.byref(self._h)))
+            COPIED["h2d"] += im.nbytes
+            self._keep = None
+        self._fin = weakref.finalize(self, lib.ia3_stack_destroy, self._h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        self._fin()
+
+    # ---- seed stage --------------------------------------------------------------------------
+    def seed_candidates(self, w_fg, w_bg, filt_size, variant, edge, h_min):
+        """Runs the device seed stage; returns (zxy int32 (n,3) in C order, h float32 (n,), timing)."""
+        lib = load()
+        cfg = SeedCfg()
+        keep = []
+
+        def half(w):
+            if w is None:
+                return None, -1
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            keep.append(w)
+            return w.ctypes.data_as(C.POINTER(C.c_double)), len(w) - 1
+
+        cfg.w_fg, cfg.r_fg = half(w_fg)
+        cfg.w_bg, cfg.r_bg = half(w_bg)
+        cfg.filt_size = int(filt_size)
+        cfg.variant = int(variant)
+        cfg.edge = float(edge)
+        cfg.h_min = float(h_min)
+        n = C.c_int64(0)
+        t = SeedTiming()
+        _check(lib.ia3_seed_run(self._h, C.byref(cfg), C.byref(n), C.byref(t)))
+        n = n.value
+        zxy = np.empty((n, 3), dtype=np.int32)
+        h = np.empty((n,), dtype=np.float32)
+        if n:
+            _check(lib.ia3_seed_fetch(self._h, _ptr(zxy), _ptr(h), n))
+        COPIED["d2h"] += zxy.nbytes + h.nbytes + 8
+        return zxy, h, t
+
+    def seed_volume(self, which):
+        out = np.empty(self.shape, dtype=self.dtype)
+        _check(load().ia3_seed_fetch_volume(self._h, int(which), _ptr(out)))
+        return out
+
+
+def make_fit_cfg(personality, radius, min_w, max_w, init_w, weight_sigma=0.0, maxfev=0, eval_fp32=False):
+    cfg = FitCfg()
+    cfg.personality = int(personality)
+    cfg.radius = int(radius)
+    cfg.min_w = float(min_w)
+    cfg.max_w = float(max_w)
+    iw = np.broadcast_to(np.asarray(init_w, dtype=np.float64).ravel()[:3] if np.ndim(init_w) else float(init_w), (3,))
+    for i in range(3):
+        cfg.init_w[i] = float(iw[i])
+    cfg.weight_sigma = float(weight_sigma)
+    cfg.maxfev = int(maxfev)
+    cfg.eval_fp32 = int(bool(eval_fp32))
+    return cfg
+
+
+class FitHandle:
+    """Device state of one iter_fit_seed_points object."""
+
+    def __init__(self, stack, centers_nx3, cfg):
+        lib = load()
+        self.stack = stack
+        self.centers = np.ascontiguousarray(centers_nx3, dtype=np.float64).reshape(-1, 3)
+        self.n = len(self.centers)
+        self._h = C.c_void_p()
+        _check(lib.ia3_fit_create(stack.handle, _ptr(self.centers), self.n, C.byref(cfg), C.byref(self._h)))
+        self._fin = weakref.finalize(self, lib.ia3_fit_destroy, self._h)
+        COPIED["h2d"] += self.centers.nbytes * 2
+        self.ps = np.full((self.n, 11), np.nan, dtype=np.float32)
+        self.p_raw = np.full((self.n, 10), np.nan, dtype=np.float64)
+        self.success = np.zeros(self.n, dtype=np.uint8)
+        self.nfev = np.zeros(self.n, dtype=np.int32)
+        self.info = np.zeros(self.n, dtype=np.int32)
+
+    def close(self):
+        self._fin()
+
+    def first_prepare(self):
+        n = C.c_int64(0)
+        _check(load().ia3_fit_first_prepare(self._h, C.byref(n)))
+        return n.value
+
+    def first_ties(self, n):
+        spot = np.empty(n, dtype=np.int32)
+        zxy = np.empty((n, 3), dtype=np.int32)
+        if n:
+            _check(load().ia3_fit_first_ties(self._h, _ptr(spot), _ptr(zxy), n))
+        return spot, zxy
+
+    def first_resolve(self, keep):
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        _check(load().ia3_fit_first_resolve(self._h, _ptr(keep), len(keep)))
+
+    def first_run(self, delta_center):
+        _check(load().ia3_fit_first_run(self._h, float(delta_center), _ptr(self.ps), _ptr(self.p_raw),
+                                        _ptr(self.success), _ptr(self.nfev), _ptr(self.info)))
+        COPIED["d2h"] += self._result_bytes()
+        COPIED["h2d"] += 4 * self.n
+
+    def repeat_sweep(self, delta_center, active):
+        active = np.ascontiguousarray(active, dtype=np.uint8)
+        _check(load().ia3_fit_repeat_sweep(self._h, float(delta_center), _ptr(active), _ptr(self.ps), _ptr(self.p_raw),
+                                           _ptr(self.success), _ptr(self.nfev), _ptr(self.info)))
+        COPIED["d2h"] += self._result_bytes()
+        COPIED["h2d"] += 4 * int(np.count_nonzero(active))
+
+    def _result_bytes(self):
+        return self.ps.nbytes + self.p_raw.nbytes + self.success.nbytes + self.nfev.nbytes + self.info.nbytes
+
+    def volume(self, which):
+        out = np.empty(self.stack.shape, dtype=np.float64)
+        _check(load().ia3_fit_get_volume(self._h, int(which), _ptr(out)))
+        return out
+
+    def rec(self, i, K=8192):
+        rec = np.empty(K, dtype=np.float64)
+        zxy = np.empty((K, 3), dtype=np.int32)
+        cnt = C.c_int32(0)
+        _check(load().ia3_fit_get_rec(self._h, int(i), _ptr(rec), _ptr(zxy), C.byref(cnt)))
+        return rec[:cnt.value].copy(), zxy[:cnt.value].copy()
+
+    @property
+    def num_levels(self):
+        return int(load().ia3_fit_num_levels(self._h))
+
+    @property
+    def last_ms(self):
+        return float(load().ia3_fit_last_ms(self._h))
+
+
+def gaussfit_batch(cfg, delta_center, values_list, coords_list, centers, want_rec=False):
+    """Batch of independent GaussianFit problems.  values_list[i]: (m_i,) float64; coords_list[i]: (3, m_i)."""
+    lib = load()
+    n = len(values_list)
+    off = np.zeros(n + 1, dtype=np.int64)
+    for i, v in enumerate(values_list):
+        off[i + 1] = off[i] + len(v)
+    values = np.ascontiguousarray(np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in values_list]) if n else np.zeros(0))
+    coords = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32).T.reshape(-1, 3) for c in coords_list]) if n else np.zeros((0, 3), np.float32), dtype=np.float32)
+    centers = np.ascontiguousarray(centers, dtype=np.float64).reshape(-1, 3)
+    ps = np.empty((n, 11), np.float32)
+    praw = np.empty((n, 10), np.float64)
+    succ = np.zeros(n, np.uint8)
+    nfev = np.zeros(n, np.int32)
+    info = np.zeros(n, np.int32)
+    rec = np.empty(len(values), np.float64) if want_rec else None
+    _check(lib.ia3_gaussfit_batch(C.byref(cfg), float(delta_center), n, _ptr(off), _ptr(values), _ptr(coords),
+                                  _ptr(centers), _ptr(ps), _ptr(praw), _ptr(succ), _ptr(nfev), _ptr(info), _ptr(rec)))
+    recs = [rec[off[i]:off[i + 1]] for i in range(n)] if want_rec else None
+    return ps, praw, succ.astype(bool), nfev, info, recs
+
+
+def gauss_eval(cfg, delta_center, p_raw, center, coords_3xm):
+    """GaussianFit.get_im(): Gaussian part of the model on (3, m) coordinates -> (m,) float64."""
+    co = np.ascontiguousarray(np.asarray(coords_3xm, dtype=np.float32).T.reshape(-1, 3))
+    p_raw = np.ascontiguousarray(p_raw, dtype=np.float64)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    out = np.empty(len(co), dtype=np.float64)
+    _check(load().ia3_gauss_eval(C.byref(cfg), float(delta_center), _ptr(p_raw), _ptr(center), _ptr(co), len(co), _ptr(out)))
+    return out

@@ -1,0 +1,692 @@
+// C ABI of libia3b200.so (declared in include/ia3b200.h): handles, host-side orchestration
+// (buffer management, neighbour lists, dependency levels) and kernel launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ia3b200.h"
+#include "fit_kernels.h"
+#include "ia3_device.h"
+#include "seed_kernels.h"
+
+namespace ia3 {
+
+static thread_local std::string g_err;
+int64_t g_launches = 0;
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+static std::mutex g_mu;
+
+void set_error(const std::string& msg) { g_err = msg; }
+
+// ---- caching allocator --------------------------------------------------------------------
+static std::multimap<size_t, void*> g_free;
+static std::unordered_map<void*, size_t> g_sizes;
+static size_t g_cached_bytes = 0;
+static const size_t kCacheLimit = (size_t)48 << 30;
+
+int dev_alloc(void** p, size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  bytes = (bytes + 255) / 256 * 256;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_free.lower_bound(bytes);
+    if (it != g_free.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+      *p = it->second;
+      g_cached_bytes -= it->first;
+      g_free.erase(it);
+      return 0;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    dev_cache_clear();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    return -1;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_sizes[*p] = bytes;
+  return 0;
+}
+
+void dev_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_sizes.find(p);
+  if (it == g_sizes.end()) return;
+  if (g_cached_bytes + it->second > kCacheLimit) {
+    cudaFree(p);
+    g_sizes.erase(it);
+    return;
+  }
+  g_free.emplace(it->second, p);
+  g_cached_bytes += it->second;
+}
+
+void dev_cache_clear() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_free) { cudaFree(kv.second); g_sizes.erase(kv.second); }
+  g_free.clear();
+  g_cached_bytes = 0;
+}
+
+static int ensure_device() {
+  if (g_device >= 0) { IA3_CUDA(cudaSetDevice(g_device)); return 0; }
+  int dev = 0;
+  if (const char* e = getenv("IA3_DEVICE")) dev = atoi(e);
+  int n = 0;
+  IA3_CUDA(cudaGetDeviceCount(&n));
+  if (n <= 0) { set_error("no CUDA device visible: libia3b200 has no CPU fallback"); return -1; }
+  if (dev >= n) dev = dev % n;
+  IA3_CUDA(cudaSetDevice(dev));
+  g_device = dev;
+  return 0;
+}
+
+static size_t dtype_size(int dt) { return dt == IA3_DTYPE_U16 ? 2 : (dt == IA3_DTYPE_F32 ? 4 : 8); }
+
+template <typename T>
+static int upload(T** d, const std::vector<T>& h, cudaStream_t st) {
+  if (dev_alloc((void**)d, h.size() * sizeof(T))) return -1;
+  if (!h.empty()) IA3_CUDA(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+}  // namespace ia3
+
+using namespace ia3;
+
+struct ia3_stack {
+  int dtype = 0, Z = 0, X = 0, Y = 0;
+  size_t nvox = 0;
+  void* d_im = nullptr;
+  bool owns = false;
+  cudaStream_t stream = nullptr;
+  // seed stage buffers
+  void* fg = nullptr; void* bg = nullptr; void* scratch = nullptr;
+  const void* fg_final = nullptr; const void* bg_final = nullptr;
+  uint8_t* bits = nullptr; int* counts = nullptr; long long* offsets = nullptr;
+  int32_t* cand_zxy = nullptr; float* cand_h = nullptr;
+  int64_t n_cand = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct ia3_fit {
+  ia3_stack* s = nullptr;
+  ia3_fit_cfg cfg;
+  FitDev d;
+  int64_t n = 0;
+  std::vector<double> centers;
+  std::vector<int> level;            // per seed, 0-based
+  int n_levels = 0;
+  std::vector<int8_t> offs;
+  bool prepared = false, first_done = false;
+  int64_t n_ties = 0;
+  // device arrays owned here
+  double* d_centers = nullptr; int* d_own = nullptr; int* d_nbr_start = nullptr; int* d_nbr_idx = nullptr;
+  int8_t* d_offs = nullptr; uint32_t* d_mask = nullptr;
+  int* d_tie_count = nullptr; int* d_tie_spot = nullptr; int* d_tie_k = nullptr; int tie_cap = 0;
+  float* d_ps = nullptr; double* d_praw = nullptr; uint8_t* d_succ = nullptr; int* d_nfev = nullptr; int* d_info = nullptr;
+  double* d_rec = nullptr; double* d_snap = nullptr; double* d_vol = nullptr;
+  int* d_work = nullptr; size_t work_cap = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float last_ms = 0.f;
+};
+
+extern "C" {
+
+int ia3_init(int device) {
+  if (device >= 0) {
+    int n = 0;
+    IA3_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) { set_error("no CUDA device visible: libia3b200 has no CPU fallback"); return -1; }
+    g_device = device % n;
+  }
+  return ensure_device();
+}
+const char* ia3_last_error(void) { return g_err.c_str(); }
+int ia3_version(void) { return 100; }
+int ia3_device_sm_count(void) {
+  if (ensure_device()) return -1;
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g_device);
+  return v;
+}
+int64_t ia3_launch_count(void) { return g_launches; }
+
+int ia3_timer_start(void) {
+  if (ensure_device()) return -1;
+  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  if (!g_t0) { IA3_CUDA(cudaEventCreate(&g_t0)); IA3_CUDA(cudaEventCreate(&g_t1)); }
+  IA3_CUDA(cudaDeviceSynchronize());
+  IA3_CUDA(cudaEventRecord(g_t0, g_stream));
+  return 0;
+}
+int ia3_timer_stop(float* ms) {
+  if (ensure_device()) return -1;
+  if (!g_t0) { set_error("timer not started"); return -1; }
+  IA3_CUDA(cudaEventRecord(g_t1, g_stream));
+  IA3_CUDA(cudaEventSynchronize(g_t1));
+  IA3_CUDA(cudaDeviceSynchronize());
+  IA3_CUDA(cudaEventElapsedTime(ms, g_t0, g_t1));
+  return 0;
+}
+
+// ---- stacks ---------------------------------------------------------------------------------
+static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
+  if (dtype < 0 || dtype > 2 || Z <= 0 || X <= 0 || Y <= 0) { set_error("bad stack dtype/shape"); return -1; }
+  s->dtype = dtype; s->Z = Z; s->X = X; s->Y = Y;
+  s->nvox = (size_t)Z * X * Y;
+  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  s->stream = g_stream;   // one stream per process: stage timings bracket everything with events on it
+  for (auto& e : s->ev) IA3_CUDA(cudaEventCreate(&e));
+  return 0;
+}
+
+int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack** out) {
+  if (ensure_device()) return -1;
+  if (!im || !out) { set_error("null argument"); return -1; }
+  ia3_stack* s = new ia3_stack();
+  if (stack_common(s, dtype, Z, X, Y)) { delete s; return -1; }
+  if (dev_alloc(&s->d_im, s->nvox * dtype_size(dtype))) { delete s; return -1; }
+  s->owns = true;
+  IA3_CUDA(cudaMemcpyAsync(s->d_im, im, s->nvox * dtype_size(dtype), cudaMemcpyHostToDevice, s->stream));
+  IA3_CUDA(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return 0;
+}
+
+int ia3_stack_wrap_device(const void* d_im, int dtype, int Z, int X, int Y, ia3_stack** out) {
+  if (ensure_device()) return -1;
+  if (!d_im || !out) { set_error("null argument"); return -1; }
+  ia3_stack* s = new ia3_stack();
+  if (stack_common(s, dtype, Z, X, Y)) { delete s; return -1; }
+  s->d_im = const_cast<void*>(d_im);
+  s->owns = false;
+  *out = s;
+  return 0;
+}
+
+int ia3_stack_destroy(ia3_stack* s) {
+  if (!s) return 0;
+  if (g_device >= 0) cudaSetDevice(g_device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->owns) dev_free(s->d_im);
+  dev_free(s->fg); dev_free(s->bg); dev_free(s->scratch);
+  dev_free(s->bits); dev_free(s->counts); dev_free(s->offsets);
+  dev_free(s->cand_zxy); dev_free(s->cand_h);
+  for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  delete s;
+  return 0;
+}
+
+// ---- seed stage -----------------------------------------------------------------------------
+}  // extern "C"
+
+template <typename Tin>
+static int seed_run_t(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, ia3_seed_timing* t) {
+  cudaStream_t st = s->stream;
+  const size_t bytes = s->nvox * sizeof(Tin);
+  const Tin* im = reinterpret_cast<const Tin*>(s->d_im);
+  if (!s->scratch && dev_alloc(&s->scratch, bytes)) return -1;
+  IA3_CUDA(cudaEventRecord(s->ev[0], st));
+  auto blur = [&](const double* w, int r, void** buf, const void** fin) -> int {
+    if (r < 0) { *fin = im; return 0; }
+    if (r > GaussW::MAXR) { set_error("gaussian radius too large (max 95)"); return -1; }
+    if (!*buf && dev_alloc(buf, bytes)) return -1;
+    GaussW gw;
+    memset(&gw, 0, sizeof(gw));
+    gw.r = r;
+    for (int j = 0; j <= r; ++j) gw.w[j] = w[j];
+    if (gaussian_filter_exact<Tin>(im, reinterpret_cast<Tin*>(*buf), reinterpret_cast<Tin*>(s->scratch), s->Z, s->X, s->Y, gw, st)) return -1;
+    *fin = *buf;
+    return 0;
+  };
+  if (blur(cfg->w_fg, cfg->r_fg, &s->fg, &s->fg_final)) return -1;
+  IA3_CUDA(cudaEventRecord(s->ev[1], st));
+  if (blur(cfg->w_bg, cfg->r_bg, &s->bg, &s->bg_final)) return -1;
+  IA3_CUDA(cudaEventRecord(s->ev[2], st));
+
+  SeedDims d;
+  d.Z = s->Z; d.X = s->X; d.Y = s->Y;
+  d.cpr = (s->Y + 7) / 8;
+  d.n_chunks = (long long)s->Z * s->X * d.cpr;
+  const int T = seed_flag_threads();
+  d.n_blocks = (int)((d.n_chunks + T - 1) / T);
+  d.fs = cfg->filt_size < 1 ? 1 : cfg->filt_size;
+  d.s1 = d.fs / 2; d.s2 = d.fs - d.s1 - 1;
+  d.edge_on = (cfg->variant == 0 && cfg->edge > 0) ? 1 : 0;
+  d.lo = (int)std::ceil(cfg->edge);
+  d.hiZ = (int)std::floor((double)s->Z - cfg->edge);
+  d.hiX = (int)std::floor((double)s->X - cfg->edge);
+  d.hiY = (int)std::floor((double)s->Y - cfg->edge);
+  d.h_min = cfg->h_min;
+  if (!s->bits && dev_alloc((void**)&s->bits, (size_t)d.n_chunks)) return -1;
+  if (!s->counts && dev_alloc((void**)&s->counts, sizeof(int) * (size_t)d.n_blocks)) return -1;
+  if (!s->offsets && dev_alloc((void**)&s->offsets, sizeof(long long) * ((size_t)d.n_blocks + 1))) return -1;
+  const Tin* fg = reinterpret_cast<const Tin*>(s->fg_final);
+  const Tin* bg = reinterpret_cast<const Tin*>(s->bg_final);
+  if (seed_flags<Tin>(fg, bg, d, cfg->variant, s->bits, s->counts, s->offsets, st)) return -1;
+  IA3_CUDA(cudaEventRecord(s->ev[3], st));
+  long long total = 0;
+  IA3_CUDA(cudaMemcpyAsync(&total, s->offsets + d.n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  dev_free(s->cand_zxy); dev_free(s->cand_h);
+  s->cand_zxy = nullptr; s->cand_h = nullptr;
+  if (dev_alloc((void**)&s->cand_zxy, sizeof(int32_t) * 3 * (size_t)std::max<long long>(total, 1))) return -1;
+  if (dev_alloc((void**)&s->cand_h, sizeof(float) * (size_t)std::max<long long>(total, 1))) return -1;
+  if (total > 0 && seed_emit<Tin>(fg, bg, d, cfg->variant, s->bits, s->offsets, s->cand_zxy, s->cand_h, st)) return -1;
+  IA3_CUDA(cudaEventRecord(s->ev[4], st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  s->n_cand = total;
+  if (n_candidates) *n_candidates = total;
+  if (t) {
+    cudaEventElapsedTime(&t->ms_gauss_fg, s->ev[0], s->ev[1]);
+    cudaEventElapsedTime(&t->ms_gauss_bg, s->ev[1], s->ev[2]);
+    cudaEventElapsedTime(&t->ms_rank, s->ev[2], s->ev[3]);
+    cudaEventElapsedTime(&t->ms_compact, s->ev[3], s->ev[4]);
+    cudaEventElapsedTime(&t->ms_total, s->ev[0], s->ev[4]);
+  }
+  return 0;
+}
+
+extern "C" {
+
+int ia3_seed_run(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, ia3_seed_timing* t) {
+  if (ensure_device()) return -1;
+  if (!s || !cfg) { set_error("null argument"); return -1; }
+  if (s->dtype == IA3_DTYPE_U16) return seed_run_t<uint16_t>(s, cfg, n_candidates, t);
+  if (s->dtype == IA3_DTYPE_F32) return seed_run_t<float>(s, cfg, n_candidates, t);
+  set_error("seed stage supports uint16 and float32 stacks");
+  return -1;
+}
+
+int ia3_seed_fetch(ia3_stack* s, int32_t* zxy, float* h, int64_t cap) {
+  if (ensure_device()) return -1;
+  if (!s) { set_error("null argument"); return -1; }
+  const int64_t n = std::min<int64_t>(cap, s->n_cand);
+  if (n > 0) {
+    if (zxy) IA3_CUDA(cudaMemcpyAsync(zxy, s->cand_zxy, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (h) IA3_CUDA(cudaMemcpyAsync(h, s->cand_h, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream));
+    IA3_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  return 0;
+}
+
+int ia3_seed_fetch_volume(ia3_stack* s, int which, void* out) {
+  if (ensure_device()) return -1;
+  const void* src = which == 0 ? s->fg_final : s->bg_final;
+  if (!src) { set_error("seed stage has not run"); return -1; }
+  IA3_CUDA(cudaMemcpyAsync(out, src, s->nvox * dtype_size(s->dtype), cudaMemcpyDeviceToHost, s->stream));
+  IA3_CUDA(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// ---- fit stage ------------------------------------------------------------------------------
+static inline long long cell_key(long long a, long long b, long long c) {
+  return ((a + (1LL << 20)) << 42) | ((b + (1LL << 20)) << 21) | (c + (1LL << 20));
+}
+
+int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_fit_cfg* cfg, ia3_fit** out) {
+  if (ensure_device()) return -1;
+  if (!s || !cfg || !out || (n > 0 && !centers_zxy)) { set_error("null argument"); return -1; }
+  if (cfg->radius < 1 || cfg->radius > 15) { set_error("radius_fit must be in 1..15"); return -1; }
+  if (cfg->personality != 3 && cfg->personality != 4) { set_error("personality must be 3 or 4"); return -1; }
+  for (int64_t i = 0; i < 3 * n; ++i)
+    if (!(std::fabs(centers_zxy[i]) < 1e6)) { set_error("seed coordinates must be finite and |c| < 1e6"); return -1; }
+  ia3_fit* f = new ia3_fit();
+  f->s = s; f->cfg = *cfg; f->n = n;
+  f->centers.assign(centers_zxy, centers_zxy + 3 * n);
+  cudaStream_t st = s->stream;
+  const int r = cfg->radius;
+  // window offsets: np.indices([2r]*3) - r, kept where d^2 <= r^2, C order (Fitting_v4.py:580-583)
+  for (int a = -r; a < r; ++a) for (int b = -r; b < r; ++b) for (int c = -r; c < r; ++c)
+    if (a * a + b * b + c * c <= r * r) { f->offs.push_back((int8_t)a); f->offs.push_back((int8_t)b); f->offs.push_back((int8_t)c); }
+  const int K = (int)(f->offs.size() / 3);
+  const int KW = (K + 31) / 32;
+
+  // neighbour lists (seeds that can own a voxel of this seed's window) and dependency levels
+  const double reach = 2.0 * ((double)r + 1.7320508075688772) + 1e-6;
+  const double cs = std::ceil(reach);
+  std::vector<long long> key(n);
+  std::unordered_map<long long, std::vector<int>> cells;
+  cells.reserve((size_t)n * 2 + 16);
+  auto cellc = [&](double v) { return (long long)std::floor(v / cs); };
+  for (int64_t i = 0; i < n; ++i) {
+    const double* c = &f->centers[3 * i];
+    cells[cell_key(cellc(c[0]), cellc(c[1]), cellc(c[2]))].push_back((int)i);
+  }
+  std::vector<int> nbr_start(n + 1, 0), nbr_idx, own(n);
+  f->level.assign(n, 0);
+  int n_levels = 0;
+  const int lim = 2 * r - 1;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* c = &f->centers[3 * i];
+    const long long a = cellc(c[0]), b = cellc(c[1]), cc = cellc(c[2]);
+    const int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
+    int lvl = 0, ownid = (int)i;
+    const size_t begin = nbr_idx.size();
+    for (long long da = -1; da <= 1; ++da) for (long long db = -1; db <= 1; ++db) for (long long dc = -1; dc <= 1; ++dc) {
+      auto it = cells.find(cell_key(a + da, b + db, cc + dc));
+      if (it == cells.end()) continue;
+      for (int j : it->second) {
+        if (j == (int)i) continue;
+        const double* q = &f->centers[3 * j];
+        const double d0 = q[0] - c[0], d1 = q[1] - c[1], d2 = q[2] - c[2];
+        if (d0 * d0 + d1 * d1 + d2 * d2 <= reach * reach) nbr_idx.push_back(j);
+        if (d0 == 0 && d1 == 0 && d2 == 0 && j < ownid) ownid = j;
+        if (j < (int)i) {
+          const int e0 = std::abs((int)q[0] - ic[0]), e1 = std::abs((int)q[1] - ic[1]), e2 = std::abs((int)q[2] - ic[2]);
+          if (e0 <= lim && e1 <= lim && e2 <= lim && e0 * e0 + e1 * e1 + e2 * e2 <= 4 * r * r)
+            lvl = std::max(lvl, f->level[j] + 1);
+        }
+      }
+    }
+    std::sort(nbr_idx.begin() + begin, nbr_idx.end());
+    nbr_start[i + 1] = (int)nbr_idx.size();
+    own[i] = ownid;
+    f->level[i] = lvl;
+    n_levels = std::max(n_levels, lvl + 1);
+  }
+  f->n_levels = n_levels;
+
+  if (upload(&f->d_centers, f->centers, st) || upload(&f->d_own, own, st) || upload(&f->d_nbr_start, nbr_start, st) ||
+      upload(&f->d_nbr_idx, nbr_idx, st) || upload(&f->d_offs, f->offs, st)) { ia3_fit_destroy(f); return -1; }
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  if (dev_alloc((void**)&f->d_mask, nn * KW * 4) || dev_alloc((void**)&f->d_ps, nn * NOUT * 4) ||
+      dev_alloc((void**)&f->d_praw, nn * NP * 8) || dev_alloc((void**)&f->d_succ, nn) ||
+      dev_alloc((void**)&f->d_nfev, nn * 4) || dev_alloc((void**)&f->d_info, nn * 4) ||
+      dev_alloc((void**)&f->d_rec, nn * K * 8) || dev_alloc((void**)&f->d_snap, nn * K * 8) ||
+      dev_alloc((void**)&f->d_vol, s->nvox * 8) || dev_alloc((void**)&f->d_tie_count, 256)) { ia3_fit_destroy(f); return -1; }
+  IA3_CUDA(cudaMemsetAsync(f->d_succ, 0, nn, st));
+  IA3_CUDA(cudaMemsetAsync(f->d_rec, 0, nn * K * 8, st));
+  IA3_CUDA(cudaEventCreate(&f->e0));
+  IA3_CUDA(cudaEventCreate(&f->e1));
+
+  FitDev& d = f->d;
+  memset(&d, 0, sizeof(d));
+  d.im = s->d_im; d.im_dtype = s->dtype; d.vol = f->d_vol;
+  d.Z = s->Z; d.X = s->X; d.Y = s->Y;
+  d.n = n; d.centers = f->d_centers; d.own_id = f->d_own; d.nbr_start = f->d_nbr_start; d.nbr_idx = f->d_nbr_idx;
+  d.K = K; d.KW = KW; d.offs = f->d_offs; d.mask = f->d_mask;
+  d.tie_count = f->d_tie_count;
+  d.ps = f->d_ps; d.p_raw = f->d_praw; d.success = f->d_succ; d.nfev = f->d_nfev; d.info = f->d_info;
+  d.rec = f->d_rec;
+  d.fp.min_w2 = cfg->min_w * cfg->min_w; d.fp.max_w2 = cfg->max_w * cfg->max_w;
+  d.fp.delta = 1.0; d.fp.weight_sigma = cfg->weight_sigma; d.fp.personality = cfg->personality;
+  d.fp.init_wt[0] = d.fp.init_wt[1] = d.fp.init_wt[2] = 0.0;
+  d.lm.ftol = 1.49012e-8; d.lm.xtol = 1.49012e-8; d.lm.gtol = 0.0; d.lm.factor = 100.0;
+  d.lm.maxfev = cfg->maxfev > 0 ? cfg->maxfev : (cfg->personality == 4 ? 1000 : 1100);
+  for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
+  IA3_CUDA(cudaStreamSynchronize(st));
+  *out = f;
+  return 0;
+}
+
+int ia3_fit_destroy(ia3_fit* f) {
+  if (!f) return 0;
+  if (g_device >= 0) cudaSetDevice(g_device);
+  if (g_stream) cudaStreamSynchronize(g_stream);
+  void* ptrs[] = {f->d_centers, f->d_own, f->d_nbr_start, f->d_nbr_idx, f->d_offs, f->d_mask, f->d_tie_count,
+                  f->d_tie_spot, f->d_tie_k, f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info, f->d_rec,
+                  f->d_snap, f->d_vol, f->d_work};
+  for (void* p : ptrs) dev_free(p);
+  if (f->e0) cudaEventDestroy(f->e0);
+  if (f->e1) cudaEventDestroy(f->e1);
+  delete f;
+  return 0;
+}
+
+int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
+  if (ensure_device()) return -1;
+  if (!f) { set_error("null argument"); return -1; }
+  cudaStream_t st = f->s->stream;
+  int cap = (int)std::min<int64_t>(std::max<int64_t>(f->n * 8, 4096), (int64_t)1 << 24);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (cap > f->tie_cap) {
+      dev_free(f->d_tie_spot); dev_free(f->d_tie_k);
+      f->d_tie_spot = f->d_tie_k = nullptr;
+      if (dev_alloc((void**)&f->d_tie_spot, sizeof(int) * (size_t)cap) || dev_alloc((void**)&f->d_tie_k, sizeof(int) * (size_t)cap)) return -1;
+      f->tie_cap = cap;
+    }
+    f->d.tie_cap = f->tie_cap; f->d.tie_spot = f->d_tie_spot; f->d.tie_k = f->d_tie_k;
+    IA3_CUDA(cudaMemsetAsync(f->d_tie_count, 0, sizeof(int), st));
+    if (launch_voronoi(f->d, st)) return -1;
+    int cnt = 0;
+    IA3_CUDA(cudaMemcpyAsync(&cnt, f->d_tie_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IA3_CUDA(cudaStreamSynchronize(st));
+    f->n_ties = cnt;
+    if (cnt <= f->tie_cap) break;
+    cap = cnt;
+  }
+  f->prepared = true;
+  if (n_ties) *n_ties = f->n_ties;
+  return 0;
+}
+
+int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
+  if (ensure_device()) return -1;
+  if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
+  const int64_t n = std::min<int64_t>(cap, f->n_ties);
+  if (n <= 0) return 0;
+  std::vector<int> sp(n), kk(n);
+  IA3_CUDA(cudaMemcpy(sp.data(), f->d_tie_spot, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  IA3_CUDA(cudaMemcpy(kk.data(), f->d_tie_k, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) {
+    const int sidx = sp[i], k = kk[i];
+    spot[i] = sidx;
+    for (int a = 0; a < 3; ++a) zxy[3 * i + a] = (int)f->centers[3 * (size_t)sidx + a] + f->offs[3 * (size_t)k + a];
+  }
+  return 0;
+}
+
+int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
+  if (ensure_device()) return -1;
+  if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
+  n = std::min<int64_t>(n, f->n_ties);
+  if (n <= 0) return 0;
+  uint8_t* d_keep = nullptr;
+  if (dev_alloc((void**)&d_keep, (size_t)n)) return -1;
+  cudaStream_t st = f->s->stream;
+  IA3_CUDA(cudaMemcpyAsync(d_keep, keep, (size_t)n, cudaMemcpyHostToDevice, st));
+  if (launch_apply_ties(f->d_mask, f->d.KW, f->d_tie_spot, f->d_tie_k, d_keep, (int)n, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  dev_free(d_keep);
+  return 0;
+}
+
+static int fetch_results(ia3_fit* f, float* ps, double* p_raw, uint8_t* success, int32_t* nfev, int32_t* info) {
+  cudaStream_t st = f->s->stream;
+  const size_t n = (size_t)f->n;
+  if (n == 0) return 0;
+  if (ps) IA3_CUDA(cudaMemcpyAsync(ps, f->d_ps, n * NOUT * 4, cudaMemcpyDeviceToHost, st));
+  if (p_raw) IA3_CUDA(cudaMemcpyAsync(p_raw, f->d_praw, n * NP * 8, cudaMemcpyDeviceToHost, st));
+  if (success) IA3_CUDA(cudaMemcpyAsync(success, f->d_succ, n, cudaMemcpyDeviceToHost, st));
+  if (nfev) IA3_CUDA(cudaMemcpyAsync(nfev, f->d_nfev, n * 4, cudaMemcpyDeviceToHost, st));
+  if (info) IA3_CUDA(cudaMemcpyAsync(info, f->d_info, n * 4, cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// builds per-level work lists of the selected seeds; returns level boundaries
+static int build_work(ia3_fit* f, const uint8_t* active, std::vector<int>& bounds) {
+  std::vector<std::vector<int>> per(f->n_levels);
+  for (int64_t i = 0; i < f->n; ++i)
+    if (!active || active[i]) per[f->level[i]].push_back((int)i);
+  std::vector<int> flat;
+  bounds.assign(1, 0);
+  for (auto& v : per) { flat.insert(flat.end(), v.begin(), v.end()); bounds.push_back((int)flat.size()); }
+  if (flat.size() > f->work_cap) {
+    dev_free(f->d_work);
+    f->d_work = nullptr;
+    if (dev_alloc((void**)&f->d_work, sizeof(int) * std::max<size_t>(flat.size(), (size_t)f->n))) return -1;
+    f->work_cap = std::max<size_t>(flat.size(), (size_t)f->n);
+  }
+  if (!flat.empty())
+    IA3_CUDA(cudaMemcpyAsync(f->d_work, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, f->s->stream));
+  IA3_CUDA(cudaStreamSynchronize(f->s->stream));   // flat is a local
+  return 0;
+}
+
+int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw, uint8_t* success, int32_t* nfev,
+                      int32_t* info) {
+  if (ensure_device()) return -1;
+  if (!f) { set_error("null argument"); return -1; }
+  if (!f->prepared && ia3_fit_first_prepare(f, nullptr)) return -1;
+  cudaStream_t st = f->s->stream;
+  f->d.fp.delta = delta_center;
+  std::vector<int> bounds;
+  if (build_work(f, nullptr, bounds)) return -1;
+  IA3_CUDA(cudaEventRecord(f->e0, st));
+  if (launch_init_window(f->d, st)) return -1;
+  if (launch_fit(f->d, 0, nullptr, f->n, f->cfg.eval_fp32 != 0, st)) return -1;
+  for (int l = 0; l < f->n_levels; ++l)
+    if (launch_subtract(f->d, f->d_work + bounds[l], bounds[l + 1] - bounds[l], st)) return -1;
+  if (launch_window_copy(f->d, f->d_snap, nullptr, 0, st)) return -1;
+  IA3_CUDA(cudaEventRecord(f->e1, st));
+  if (fetch_results(f, ps, p_raw, success, nfev, info)) return -1;
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  f->first_done = true;
+  return 0;
+}
+
+int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active, float* ps, double* p_raw,
+                         uint8_t* success, int32_t* nfev, int32_t* info) {
+  if (ensure_device()) return -1;
+  if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
+  cudaStream_t st = f->s->stream;
+  f->d.fp.delta = delta_center;
+  std::vector<int> bounds;
+  if (build_work(f, active, bounds)) return -1;
+  IA3_CUDA(cudaEventRecord(f->e0, st));
+  for (int l = 0; l < f->n_levels; ++l)
+    if (launch_fit(f->d, 1, f->d_work + bounds[l], bounds[l + 1] - bounds[l], f->cfg.eval_fp32 != 0, st)) return -1;
+  IA3_CUDA(cudaEventRecord(f->e1, st));
+  if (fetch_results(f, ps, p_raw, success, nfev, info)) return -1;
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  return 0;
+}
+
+int ia3_fit_get_volume(ia3_fit* f, int which, double* out) {
+  if (ensure_device()) return -1;
+  if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
+  cudaStream_t st = f->s->stream;
+  double* tmp = nullptr;
+  if (dev_alloc((void**)&tmp, f->s->nvox * 8)) return -1;
+  if (launch_to_f64(f->s->d_im, f->s->dtype, tmp, (long long)f->s->nvox, st)) return -1;
+  if (which == 0) {
+    if (launch_window_copy(f->d, f->d_snap, tmp, 1, st)) return -1;
+  } else {
+    // im_add: current work volume on the window voxels
+    double* snap2 = nullptr;
+    if (dev_alloc((void**)&snap2, (size_t)std::max<int64_t>(f->n, 1) * f->d.K * 8)) return -1;
+    if (launch_window_copy(f->d, snap2, nullptr, 0, st)) return -1;
+    if (launch_window_copy(f->d, snap2, tmp, 1, st)) return -1;
+    IA3_CUDA(cudaStreamSynchronize(st));
+    dev_free(snap2);
+  }
+  IA3_CUDA(cudaMemcpyAsync(out, tmp, f->s->nvox * 8, cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  dev_free(tmp);
+  return 0;
+}
+
+int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* count) {
+  if (ensure_device()) return -1;
+  if (!f || i < 0 || i >= f->n) { set_error("bad seed index"); return -1; }
+  const int K = f->d.K;
+  std::vector<double> full(K);
+  IA3_CUDA(cudaMemcpy(full.data(), f->d_rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost));
+  int m = 0;
+  for (int k = 0; k < K; ++k) {
+    int v[3];
+    for (int a = 0; a < 3; ++a) v[a] = (int)f->centers[3 * (size_t)i + a] + f->offs[3 * (size_t)k + a];
+    if (v[0] < 0 || v[0] >= f->s->Z || v[1] < 0 || v[1] >= f->s->X || v[2] < 0 || v[2] >= f->s->Y) continue;
+    if (rec) rec[m] = full[k];
+    if (zxy) { zxy[3 * m] = v[0]; zxy[3 * m + 1] = v[1]; zxy[3 * m + 2] = v[2]; }
+    ++m;
+  }
+  if (count) *count = m;
+  return 0;
+}
+
+int ia3_fit_num_levels(ia3_fit* f) { return f ? f->n_levels : 0; }
+float ia3_fit_last_ms(ia3_fit* f) { return f ? f->last_ms : 0.f; }
+
+// ---- standalone GaussianFit -----------------------------------------------------------------
+int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_problems, const int64_t* off,
+                       const double* values, const float* coords, const double* centers, float* ps, double* p_raw,
+                       uint8_t* success, int32_t* nfev, int32_t* info, double* rec) {
+  if (ensure_device()) return -1;
+  if (!cfg || n_problems < 0 || (n_problems > 0 && (!off || !values || !coords || !centers))) { set_error("null argument"); return -1; }
+  if (n_problems == 0) return 0;
+  const int64_t total = off[n_problems];
+  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaStream_t st = g_stream;
+  GenericFitDev d;
+  memset(&d, 0, sizeof(d));
+  long long* d_off; double* d_val; float* d_co; double* d_cen; double* d_tmp; double* d_rec = nullptr;
+  float* d_ps; double* d_praw; uint8_t* d_s; int* d_nf; int* d_in;
+  const size_t np_ = (size_t)n_problems, tt = (size_t)std::max<int64_t>(total, 1);
+  if (dev_alloc((void**)&d_off, (np_ + 1) * 8) || dev_alloc((void**)&d_val, tt * 8) || dev_alloc((void**)&d_co, tt * 12) ||
+      dev_alloc((void**)&d_cen, np_ * 24) || dev_alloc((void**)&d_tmp, tt * 8) || dev_alloc((void**)&d_ps, np_ * NOUT * 4) ||
+      dev_alloc((void**)&d_praw, np_ * NP * 8) || dev_alloc((void**)&d_s, np_) || dev_alloc((void**)&d_nf, np_ * 4) ||
+      dev_alloc((void**)&d_in, np_ * 4) || (rec && dev_alloc((void**)&d_rec, tt * 8))) return -1;
+  IA3_CUDA(cudaMemcpyAsync(d_off, off, (np_ + 1) * 8, cudaMemcpyHostToDevice, st));
+  IA3_CUDA(cudaMemcpyAsync(d_val, values, (size_t)total * 8, cudaMemcpyHostToDevice, st));
+  IA3_CUDA(cudaMemcpyAsync(d_co, coords, (size_t)total * 12, cudaMemcpyHostToDevice, st));
+  IA3_CUDA(cudaMemcpyAsync(d_cen, centers, np_ * 24, cudaMemcpyHostToDevice, st));
+  d.n = n_problems; d.off = d_off; d.values = d_val; d.coords = d_co; d.centers = d_cen; d.tmp = d_tmp;
+  d.ps = d_ps; d.p_raw = d_praw; d.success = d_s; d.nfev = d_nf; d.info = d_in; d.rec = d_rec;
+  d.fp.min_w2 = cfg->min_w * cfg->min_w; d.fp.max_w2 = cfg->max_w * cfg->max_w; d.fp.delta = delta_center;
+  d.fp.weight_sigma = cfg->weight_sigma; d.fp.personality = cfg->personality;
+  d.lm.ftol = 1.49012e-8; d.lm.xtol = 1.49012e-8; d.lm.gtol = 0.0; d.lm.factor = 100.0;
+  d.lm.maxfev = cfg->maxfev > 0 ? cfg->maxfev : (cfg->personality == 4 ? 1000 : 1100);
+  for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
+  if (launch_generic_fit(d, st)) return -1;
+  if (ps) IA3_CUDA(cudaMemcpyAsync(ps, d_ps, np_ * NOUT * 4, cudaMemcpyDeviceToHost, st));
+  if (p_raw) IA3_CUDA(cudaMemcpyAsync(p_raw, d_praw, np_ * NP * 8, cudaMemcpyDeviceToHost, st));
+  if (success) IA3_CUDA(cudaMemcpyAsync(success, d_s, np_, cudaMemcpyDeviceToHost, st));
+  if (nfev) IA3_CUDA(cudaMemcpyAsync(nfev, d_nf, np_ * 4, cudaMemcpyDeviceToHost, st));
+  if (info) IA3_CUDA(cudaMemcpyAsync(info, d_in, np_ * 4, cudaMemcpyDeviceToHost, st));
+  if (rec) IA3_CUDA(cudaMemcpyAsync(rec, d_rec, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  void* ptrs[] = {d_off, d_val, d_co, d_cen, d_tmp, d_rec, d_ps, d_praw, d_s, d_nf, d_in};
+  for (void* p : ptrs) dev_free(p);
+  return 0;
+}
+
+int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_raw, const double* center,
+                   const float* coords, int64_t m, double* out) {
+  if (ensure_device()) return -1;
+  if (!cfg || !p_raw || !center || (m > 0 && (!coords || !out))) { set_error("null argument"); return -1; }
+  if (m == 0) return 0;
+  FitParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.min_w2 = cfg->min_w * cfg->min_w; fp.max_w2 = cfg->max_w * cfg->max_w; fp.delta = delta_center;
+  fp.weight_sigma = 0.0; fp.personality = cfg->personality;
+  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaStream_t st = g_stream;
+  double* d_p; double* d_c; float* d_co; double* d_out;
+  if (dev_alloc((void**)&d_p, 80) || dev_alloc((void**)&d_c, 24) || dev_alloc((void**)&d_co, (size_t)m * 12) ||
+      dev_alloc((void**)&d_out, (size_t)m * 8)) return -1;
+  IA3_CUDA(cudaMemcpyAsync(d_p, p_raw, 80, cudaMemcpyHostToDevice, st));
+  IA3_CUDA(cudaMemcpyAsync(d_c, center, 24, cudaMemcpyHostToDevice, st));
+  IA3_CUDA(cudaMemcpyAsync(d_co, coords, (size_t)m * 12, cudaMemcpyHostToDevice, st));
+  if (launch_eval_f0(fp, d_p, d_c, d_co, m, d_out, st)) return -1;
+  IA3_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  dev_free(d_p); dev_free(d_c); dev_free(d_co); dev_free(d_out);
+  return 0;
+}
+
+}  // extern "C"

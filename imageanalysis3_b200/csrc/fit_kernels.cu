@@ -1,0 +1,467 @@
+// Fit stage kernels (sm_100a): one warp per spot.
+//
+//   k_init_window  float64 work volume <- image, only for voxels inside some seed's window
+//   k_voronoi      firstfit membership of every window voxel (nearest seed), tie detection
+//   k_fit          GaussianFit.fit() for one spot per warp: window voxels compacted into shared
+//                  memory, initial guess by warp-wide selection, lmder-faithful LM (lm_core.h)
+//                  with the per-voxel model / Jacobian strided over the lanes, J^T J, J^T f and
+//                  |f|^2 combined by xor-shuffle butterflies (so every lane holds bit-identical
+//                  sums), 10x10 algebra in FP64 on lane 0 with its state in shared memory
+//   k_subtract     firstfit's "im_subtr[window] -= reconstruction", one dependency level at a time
+//
+// Sequential semantics of the reference (seed order, in-place im_add updates; Fitting_v4.py:
+// 651-675) are preserved by launching one dependency level at a time: two seeds are in the same
+// level only if their windows are disjoint, and a seed's level is above that of every
+// lower-index seed it overlaps (levels are computed on the host, capi.cu).
+#include <algorithm>
+#include "ia3_device.h"
+#include "fit_kernels.h"
+#include "fit_spot.h"
+
+namespace ia3 {
+
+constexpr int WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct WarpExec {
+  static constexpr int W = 32;
+  __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ double allsum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+  }
+  __device__ __forceinline__ int allsum_int(int v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+  }
+  __device__ __forceinline__ double allmax(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+  }
+  __device__ __forceinline__ void argmin(double& v, int& k) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(FULL, v, o);
+      const int ok = __shfl_xor_sync(FULL, k, o);
+      if (ov < v || (ov == v && ok < k)) { v = ov; k = ok; }
+    }
+  }
+};
+
+__device__ __forceinline__ double load_im(const void* im, int dtype, long long idx) {
+  if (dtype == 0) return (double)reinterpret_cast<const uint16_t*>(im)[idx];
+  if (dtype == 1) return (double)reinterpret_cast<const float*>(im)[idx];
+  return reinterpret_cast<const double*>(im)[idx];
+}
+
+// packed window voxel: offsets (6 bits each, biased by 32) + window index k (14 bits)
+__device__ __forceinline__ uint32_t pack_vox(int dz, int dx, int dy, int k) {
+  return (uint32_t)(dz + 32) | ((uint32_t)(dx + 32) << 6) | ((uint32_t)(dy + 32) << 12) | ((uint32_t)k << 18);
+}
+
+template <typename T>
+struct BallVox {
+  int m;
+  const uint32_t* pk;
+  const float* data;
+  __device__ __forceinline__ void get(int k, T& X0, T& X1, T& X2, T& d) const {
+    const uint32_t p = pk[k];
+    X0 = (T)((int)(p & 63u) - 32);
+    X1 = (T)((int)((p >> 6) & 63u) - 32);
+    X2 = (T)((int)((p >> 12) & 63u) - 32);
+    d = (T)data[k];
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_init_window(FitDev d) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long s = t / d.K;
+  if (s >= d.n) return;
+  const int k = (int)(t % d.K);
+  const int z = (int)d.centers[3 * s] + d.offs[3 * k];
+  const int x = (int)d.centers[3 * s + 1] + d.offs[3 * k + 1];
+  const int y = (int)d.centers[3 * s + 2] + d.offs[3 * k + 2];
+  if (z < 0 || z >= d.Z || x < 0 || x >= d.X || y < 0 || y >= d.Y) return;
+  const long long idx = ((long long)z * d.X + x) * d.Y + y;
+  d.vol[idx] = load_im(d.im, d.im_dtype, idx);   // overlapping windows write the same value
+}
+
+// squared distance exactly as scipy's sqeuclidean_distance_double for 3 components:
+// s = d0*d0; s += d1*d1; s += d2*d2 (no FMA)
+__device__ __forceinline__ double sqdist3(double v0, double v1, double v2, const double* c) {
+  const double d0 = __dsub_rn(v0, c[0]), d1 = __dsub_rn(v1, c[1]), d2 = __dsub_rn(v2, c[2]);
+  double s = __dmul_rn(d0, d0);
+  s = __dadd_rn(s, __dmul_rn(d1, d1));
+  s = __dadd_rn(s, __dmul_rn(d2, d2));
+  return s;
+}
+
+__global__ void __launch_bounds__(WARPS * 32) k_voronoi(FitDev d) {
+  const int lane = threadIdx.x & 31;
+  const long long s = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (s >= d.n) return;
+  const double c[3] = {d.centers[3 * s], d.centers[3 * s + 1], d.centers[3 * s + 2]};
+  const int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
+  const int nb0 = d.nbr_start[s], nb1 = d.nbr_start[s + 1];
+  const bool v4 = (d.fp.personality == 4);
+  const int own = v4 ? (int)s : d.own_id[s];
+  for (int k0 = 0; k0 < d.K; k0 += 32) {
+    const int k = k0 + lane;
+    bool member = false, tie = false;
+    if (k < d.K) {
+      const int z = ic[0] + d.offs[3 * k], x = ic[1] + d.offs[3 * k + 1], y = ic[2] + d.offs[3 * k + 2];
+      if (z >= 0 && z < d.Z && x >= 0 && x < d.X && y >= 0 && y < d.Y) {
+        const double v0 = (double)z, v1 = (double)x, v2 = (double)y;
+        if (v4) {
+          // cKDTree.query(k=1): nearest by squared distance; a strictly closer seed takes the voxel,
+          // an equally close one makes it a tie that the host resolves with the same tree
+          const double dm = sqdist3(v0, v1, v2, c);
+          bool closer = false;
+          for (int e = nb0; e < nb1; ++e) {
+            const int j = d.nbr_idx[e];
+            const double cj[3] = {d.centers[3 * j], d.centers[3 * j + 1], d.centers[3 * j + 2]};
+            const double dj = sqdist3(v0, v1, v2, cj);
+            if (dj < dm) { closer = true; break; }
+            if (dj == dm) tie = true;
+          }
+          member = !closer && !tie;
+          tie = tie && !closer;
+        } else {
+          // cdist (sqrt of the squared distance) + argmin: lowest index wins ties
+          double best = sqrt(sqdist3(v0, v1, v2, c));
+          int bi = (int)s;
+          for (int e = nb0; e < nb1; ++e) {
+            const int j = d.nbr_idx[e];
+            const double cj[3] = {d.centers[3 * j], d.centers[3 * j + 1], d.centers[3 * j + 2]};
+            const double dj = sqrt(sqdist3(v0, v1, v2, cj));
+            if (dj < best || (dj == best && j < bi)) { best = dj; bi = j; }
+          }
+          member = (bi == own);
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(FULL, member);
+    if (lane == 0) d.mask[s * d.KW + (k0 >> 5)] = bal;
+    if (tie) {
+      const int pos = atomicAdd(d.tie_count, 1);
+      if (pos < d.tie_cap) { d.tie_spot[pos] = (int)s; d.tie_k[pos] = k; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wi = (long long)blockIdx.x * WARPS + warp;
+  if (wi >= n_work) return;
+  const long long s = work ? (long long)work[wi] : wi;
+  const int K = d.K;
+  // per-warp shared layout
+  const size_t per_warp = (sizeof(SpotShared<T>) + 15) / 16 * 16 + (size_t)K * (8 + 8 + 4 + 4);
+  unsigned char* base = smem_raw + per_warp * warp;
+  SpotShared<T>& sh = *reinterpret_cast<SpotShared<T>*>(base);
+  double* dv = reinterpret_cast<double*>(base + (sizeof(SpotShared<T>) + 15) / 16 * 16);
+  double* tmp = dv + K;
+  float* data = reinterpret_cast<float*>(tmp + K);
+  uint32_t* pk = reinterpret_cast<uint32_t*>(data + K);
+
+  WarpExec ex;
+  const double c[3] = {d.centers[3 * s], d.centers[3 * s + 1], d.centers[3 * s + 2]};
+  const int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
+  const double origin[3] = {(double)ic[0], (double)ic[1], (double)ic[2]};
+  const bool had_rec = (mode == 1) && d.success[s];
+
+  // gather the window (in-image voxels, firstfit: Voronoi members only) in window order
+  int m = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    bool use = false;
+    long long idx = 0;
+    int dz = 0, dx = 0, dy = 0;
+    if (k < K) {
+      dz = d.offs[3 * k]; dx = d.offs[3 * k + 1]; dy = d.offs[3 * k + 2];
+      const int z = ic[0] + dz, x = ic[1] + dx, y = ic[2] + dy;
+      use = (z >= 0 && z < d.Z && x >= 0 && x < d.X && y >= 0 && y < d.Y);
+      idx = ((long long)z * d.X + x) * d.Y + y;
+      if (mode == 0) use = use && ((d.mask[s * d.KW + (k0 >> 5)] >> lane) & 1u);
+    }
+    const unsigned bal = __ballot_sync(FULL, use);
+    if (use) {
+      const int pos = m + __popc(bal & ((1u << lane) - 1u));
+      double v;
+      if (mode == 0) v = load_im(d.im, d.im_dtype, idx);
+      else { v = d.vol[idx]; if (had_rec) v = d.rec[s * K + k] + v; }   // im_ = im_rec + im_  (:662)
+      dv[pos] = v;
+      data[pos] = (float)v;                                            // self.im = float32(im) (:172)
+      pk[pos] = pack_vox(dz, dx, dy, k);
+    }
+    m += __popc(bal);
+  }
+  __syncwarp();
+
+  if (m < NP) {
+    // len(p_) > len(im): success = False (Fitting_v4.py:382-383); firstfit stores a NaN row
+    if (lane == 0) {
+      d.success[s] = 0;
+      d.nfev[s] = 0; d.info[s] = 0;
+      if (mode == 0) {
+        for (int i = 0; i < NOUT; ++i) d.ps[s * NOUT + i] = NAN;
+        for (int i = 0; i < NP; ++i) d.p_raw[s * NP + i] = NAN;
+      }
+    }
+    return;
+  }
+
+  FitParams fp = d.fp;
+  select10(ex, dv, tmp, m, false, sh.small10);
+  select10(ex, dv, tmp, m, true, sh.large10);
+  if (lane == 0) initial_guess(fp, sh.small10, sh.large10, d.init_w, sh.x0);
+  __syncwarp();
+
+  BallVox<T> vox{m, pk, data};
+  run_lm<T>(ex, fp, d.lm, c, origin, vox, sh);
+  __shared__ FitResult res_s[WARPS];
+  FitResult& res = res_s[warp];
+  finish_fit<T>(ex, fp, c, origin, vox, sh, &res);
+  if (lane < NOUT) d.ps[s * NOUT + lane] = res.ps[lane];
+  if (lane < NP) d.p_raw[s * NP + lane] = res.p_raw[lane];
+  if (lane == 0) { d.success[s] = 1; d.nfev[s] = res.nfev; d.info[s] = res.info; }
+
+  if (mode == 1) {
+    // im_rec = get_im(); ims_rec[ic] = im_rec; im_add[window] = im_ - im_rec   (:671-675)
+    __shared__ VoxConsts<double> vcd_s[WARPS];
+    VoxConsts<double>& vcd = vcd_s[warp];
+    if (lane == 0) {
+      ModelConsts mc;
+      model_consts(fp, c, sh.st.x, false, mc);
+      narrow_consts<double>(mc, origin, false, vcd);
+    }
+    __syncwarp();
+    for (int pos = lane; pos < m; pos += 32) {
+      const uint32_t p = pk[pos];
+      const int dz = (int)(p & 63u) - 32, dx = (int)((p >> 6) & 63u) - 32, dy = (int)((p >> 12) & 63u) - 32;
+      const int k = (int)(p >> 18);
+      const double f0 = eval_f0<double>(vcd, (double)dz, (double)dx, (double)dy);
+      const long long idx = ((long long)(ic[0] + dz) * d.X + (ic[1] + dx)) * d.Y + (ic[2] + dy);
+      d.rec[s * K + k] = f0;
+      d.vol[idx] = dv[pos] - f0;
+    }
+  }
+}
+
+// firstfit: ims_rec[s] = get_im() over the full clipped window; im_subtr[window] -= im_rec (:629-633)
+__global__ void __launch_bounds__(WARPS * 32) k_subtract(FitDev d, const int* __restrict__ work, long long n_work) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long wi = (long long)blockIdx.x * WARPS + warp;
+  if (wi >= n_work) return;
+  const long long s = work[wi];
+  if (!d.success[s]) return;
+  __shared__ VoxConsts<double> vcd_s[WARPS];
+  VoxConsts<double>& vcd = vcd_s[warp];
+  const double c[3] = {d.centers[3 * s], d.centers[3 * s + 1], d.centers[3 * s + 2]};
+  const int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
+  if (lane == 0) {
+    const double origin[3] = {(double)ic[0], (double)ic[1], (double)ic[2]};
+    double x[NP];
+    for (int i = 0; i < NP; ++i) x[i] = d.p_raw[s * NP + i];
+    ModelConsts mc;
+    model_consts(d.fp, c, x, false, mc);
+    narrow_consts<double>(mc, origin, false, vcd);
+  }
+  __syncwarp();
+  for (int k = lane; k < d.K; k += 32) {
+    const int dz = d.offs[3 * k], dx = d.offs[3 * k + 1], dy = d.offs[3 * k + 2];
+    const int z = ic[0] + dz, x = ic[1] + dx, y = ic[2] + dy;
+    if (z < 0 || z >= d.Z || x < 0 || x >= d.X || y < 0 || y >= d.Y) continue;
+    const double f0 = eval_f0<double>(vcd, (double)dz, (double)dx, (double)dy);
+    const long long idx = ((long long)z * d.X + x) * d.Y + y;
+    d.rec[s * d.K + k] = f0;
+    d.vol[idx] -= f0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Standalone GaussianFit on arbitrary voxel lists (values/coords in global memory).
+struct GlobalVox {
+  int m;
+  const double* values;
+  const float* coords;
+  __device__ __forceinline__ void get(int k, double& X0, double& X1, double& X2, double& d) const {
+    X0 = (double)coords[3 * k]; X1 = (double)coords[3 * k + 1]; X2 = (double)coords[3 * k + 2];
+    d = (double)(float)values[k];
+  }
+};
+
+__global__ void __launch_bounds__(WARPS * 32) k_generic_fit(GenericFitDev d) {
+  __shared__ SpotShared<double> sh_s[WARPS];
+  __shared__ FitResult res_s[WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * WARPS + warp;
+  if (b >= d.n) return;
+  SpotShared<double>& sh = sh_s[warp];
+  const long long o0 = d.off[b];
+  const int m = (int)(d.off[b + 1] - o0);
+  if (m < NP) {
+    if (lane == 0) {
+      d.success[b] = 0; d.nfev[b] = 0; d.info[b] = 0;
+      for (int i = 0; i < NOUT; ++i) d.ps[b * NOUT + i] = NAN;
+      for (int i = 0; i < NP; ++i) d.p_raw[b * NP + i] = NAN;
+    }
+    return;
+  }
+  WarpExec ex;
+  FitParams fp = d.fp;
+  const double c[3] = {d.centers[3 * b], d.centers[3 * b + 1], d.centers[3 * b + 2]};
+  const double origin[3] = {0.0, 0.0, 0.0};
+  select10(ex, d.values + o0, d.tmp + o0, m, false, sh.small10);
+  select10(ex, d.values + o0, d.tmp + o0, m, true, sh.large10);
+  if (lane == 0) initial_guess(fp, sh.small10, sh.large10, d.init_w, sh.x0);
+  __syncwarp();
+  GlobalVox vox{m, d.values + o0, d.coords + 3 * o0};
+  run_lm<double>(ex, fp, d.lm, c, origin, vox, sh);
+  FitResult& res = res_s[warp];
+  finish_fit<double>(ex, fp, c, origin, vox, sh, &res);
+  if (lane < NOUT) d.ps[b * NOUT + lane] = res.ps[lane];
+  if (lane < NP) d.p_raw[b * NP + lane] = res.p_raw[lane];
+  if (lane == 0) { d.success[b] = 1; d.nfev[b] = res.nfev; d.info[b] = res.info; }
+  if (d.rec) {
+    // finish_fit left sh.vc = constants of the final parameters
+    for (int k = lane; k < m; k += 32)
+      d.rec[o0 + k] = eval_f0<double>(sh.vc, (double)vox.coords[3 * k], (double)vox.coords[3 * k + 1], (double)vox.coords[3 * k + 2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+int fit_smem_bytes(int K, bool fp32) {
+  const size_t shs = fp32 ? sizeof(SpotShared<float>) : sizeof(SpotShared<double>);
+  const size_t per_warp = (shs + 15) / 16 * 16 + (size_t)K * (8 + 8 + 4 + 4);
+  return (int)(per_warp * WARPS);
+}
+
+int launch_init_window(const FitDev& d, cudaStream_t st) {
+  const long long total = d.n * d.K;
+  if (total == 0) return 0;
+  k_init_window<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_voronoi(const FitDev& d, cudaStream_t st) {
+  if (d.n == 0) return 0;
+  k_voronoi<<<(unsigned)((d.n + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(d);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, bool fp32, cudaStream_t st) {
+  if (n_work == 0) return 0;
+  const int smem = fit_smem_bytes(d.K, fp32);
+  const unsigned grid = (unsigned)((n_work + WARPS - 1) / WARPS);
+  if (fp32) {
+    IA3_CUDA(cudaFuncSetAttribute(k_fit<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_fit<float><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
+  } else {
+    IA3_CUDA(cudaFuncSetAttribute(k_fit<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_fit<double><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
+  }
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_subtract(const FitDev& d, const int* work, long long n_work, cudaStream_t st) {
+  if (n_work == 0) return 0;
+  k_subtract<<<(unsigned)((n_work + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(d, work, n_work);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_generic_fit(const GenericFitDev& d, cudaStream_t st) {
+  if (d.n == 0) return 0;
+  k_generic_fit<<<(unsigned)((d.n + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(d);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia3
+
+// ---- small helper kernels used by the C ABI ---------------------------------------------------
+namespace ia3 {
+
+__global__ void k_apply_ties(uint32_t* mask, int KW, const int* tie_spot, const int* tie_k, const uint8_t* keep, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  atomicOr(&mask[(long long)tie_spot[i] * KW + (tie_k[i] >> 5)], 1u << (tie_k[i] & 31));
+}
+int launch_apply_ties(uint32_t* mask, int KW, const int* tie_spot, const int* tie_k, const uint8_t* keep, int n, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_apply_ties<<<(n + 255) / 256, 256, 0, st>>>(mask, KW, tie_spot, tie_k, keep, n);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+// gather (dir = 0: snap <- vol) or scatter (dir = 1: vol_out <- snap) the window voxels of all seeds
+__global__ void k_window_copy(FitDev d, double* snap, double* vol_out, int dir) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long s = t / d.K;
+  if (s >= d.n) return;
+  const int k = (int)(t % d.K);
+  const int z = (int)d.centers[3 * s] + d.offs[3 * k];
+  const int x = (int)d.centers[3 * s + 1] + d.offs[3 * k + 1];
+  const int y = (int)d.centers[3 * s + 2] + d.offs[3 * k + 2];
+  if (z < 0 || z >= d.Z || x < 0 || x >= d.X || y < 0 || y >= d.Y) return;
+  const long long idx = ((long long)z * d.X + x) * d.Y + y;
+  if (dir == 0) snap[t] = d.vol[idx];
+  else vol_out[idx] = snap[t];
+}
+int launch_window_copy(const FitDev& d, double* snap, double* vol_out, int dir, cudaStream_t st) {
+  const long long total = d.n * d.K;
+  if (total == 0) return 0;
+  k_window_copy<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d, snap, vol_out, dir);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_to_f64(const void* im, int dtype, double* out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = load_im(im, dtype, i);
+}
+// GaussianFit.get_im() on arbitrary coordinates: f0 = exp(h - xsigmax/2)
+__global__ void k_eval_f0(FitParams fp, const double* p_raw, const double* center, const float* coords, long long m, double* out) {
+  __shared__ VoxConsts<double> vc;
+  if (threadIdx.x == 0) {
+    double x[NP], c[3] = {center[0], center[1], center[2]};
+    for (int i = 0; i < NP; ++i) x[i] = p_raw[i];
+    const double origin[3] = {0.0, 0.0, 0.0};
+    ModelConsts mc;
+    model_consts(fp, c, x, false, mc);
+    narrow_consts<double>(mc, origin, false, vc);
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += stride)
+    out[k] = eval_f0<double>(vc, (double)coords[3 * k], (double)coords[3 * k + 1], (double)coords[3 * k + 2]);
+}
+int launch_eval_f0(const FitParams& fp, const double* p_raw, const double* center, const float* coords, long long m,
+                   double* out, cudaStream_t st) {
+  if (m == 0) return 0;
+  const int blocks = (int)std::min<long long>((m + 255) / 256, 1184);
+  k_eval_f0<<<blocks, 256, 0, st>>>(fp, p_raw, center, coords, m, out);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_to_f64(const void* im, int dtype, double* out, long long n, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_to_f64<<<148 * 8, 256, 0, st>>>(im, dtype, out, n);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia3

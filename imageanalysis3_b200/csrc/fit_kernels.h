@@ -1,0 +1,59 @@
+// Host-callable launchers of the fit stage kernels (fit_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gauss_model.h"
+#include "lm_core.h"
+
+namespace ia3 {
+
+struct FitDev {
+  // image / volumes
+  const void* im; int im_dtype;       // original stack (u16 / f32 / f64)
+  double* vol;                        // float64 work volume (im_subtr -> im_add); only window voxels are initialised
+  int Z, X, Y;
+  // seeds
+  long long n;
+  const double* centers;              // n x 3
+  const int* own_id;                  // v3: lowest index among seeds with identical coordinates
+  const int* nbr_start;               // n + 1
+  const int* nbr_idx;
+  // window
+  int K, KW;                          // voxels in the ball; mask words per seed
+  const int8_t* offs;                 // K x 3 offsets
+  uint32_t* mask;                     // n x KW membership bits
+  // ties (v4)
+  int* tie_count; int tie_cap;
+  int* tie_spot; int* tie_k;
+  // results
+  float* ps; double* p_raw; uint8_t* success; int* nfev; int* info;
+  double* rec;                        // n x K reconstructions (ims_rec)
+  // config
+  FitParams fp; LMConfig lm; double init_w[3];
+};
+
+int fit_smem_bytes(int K, bool fp32);
+int launch_init_window(const FitDev& d, cudaStream_t st);
+int launch_voronoi(const FitDev& d, cudaStream_t st);
+// mode 0 = firstfit (image data, Voronoi mask), 1 = repeatfit (vol + own rec, full window, write back)
+int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, bool fp32, cudaStream_t st);
+int launch_subtract(const FitDev& d, const int* work, long long n_work, cudaStream_t st);
+
+struct GenericFitDev {
+  long long n; const long long* off;
+  const double* values; const float* coords; const double* centers;
+  double* tmp;                        // scratch, same size as values
+  float* ps; double* p_raw; uint8_t* success; int* nfev; int* info; double* rec;
+  FitParams fp; LMConfig lm; double init_w[3];
+};
+int launch_generic_fit(const GenericFitDev& d, cudaStream_t st);
+
+}  // namespace ia3
+
+namespace ia3 {
+int launch_apply_ties(uint32_t* mask, int KW, const int* tie_spot, const int* tie_k, const uint8_t* keep, int n, cudaStream_t st);
+int launch_window_copy(const FitDev& d, double* snap, double* vol_out, int dir, cudaStream_t st);
+int launch_to_f64(const void* im, int dtype, double* out, long long n, cudaStream_t st);
+int launch_eval_f0(const FitParams& fp, const double* p_raw, const double* center, const float* coords, long long m,
+                   double* out, cudaStream_t st);
+}  // namespace ia3

@@ -54,7 +54,7 @@ IA3_HD double mean10_numpy(const double* a) {
 
 // Builds x0 (as float32-rounded values, :185).  init_w_raw[3]: v4 -> the three entries are the
 // same scalar init_w; v3 -> per-axis init_w.  Also fills fp.init_wt for v3.
-IA3_HD void initial_guess(FitParams& fp, const double* small10_asc, const double* large10_desc,
+IA3_HDN void initial_guess(FitParams& fp, const double* small10_asc, const double* large10_desc,
                           const double* init_w_raw, double* x0) {
   const double eps = exp(-10.0);
   double asc[10];

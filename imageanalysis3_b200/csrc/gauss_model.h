@@ -65,7 +65,7 @@ IA3_HD double norm_w_fn(double w, double minw, double maxw) {
 }
 
 // want_jac = false skips the Jacobian-only constants.
-IA3_HD void model_consts(const FitParams& fp, const double* cen_est, const double* x, bool want_jac,
+IA3_HDN void model_consts(const FitParams& fp, const double* cen_est, const double* x, bool want_jac,
                          ModelConsts& mc) {
   const double bk = x[0], h = x[1], xp = x[2], yp = x[3], zp = x[4];
   const double w1 = x[5], w2 = x[6], w3 = x[7], pp = x[8], tp = x[9];
@@ -223,7 +223,7 @@ IA3_HD void eval_jac(const VoxConsts<T>& vc, T X0, T X1, T X2, T data, T& res, f
 }
 
 // natural parameters [hf, c0, c1, c2, bkf, w1f, w2f, w3f, t, p] (to_natural_paramaters, :244-258)
-IA3_HD void natural_params(const FitParams& fp, const double* cen_est, const double* x, double* out10) {
+IA3_HDN void natural_params(const FitParams& fp, const double* cen_est, const double* x, double* out10) {
   ModelConsts mc;
   model_consts(fp, cen_est, x, false, mc);
   const bool v4 = (fp.personality == 4);

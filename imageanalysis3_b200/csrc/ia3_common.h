@@ -7,9 +7,11 @@
 
 #if defined(__CUDACC__)
 #define IA3_HD __host__ __device__ __forceinline__
+#define IA3_HDN __host__ __device__ inline       /* big scalar routines: let the compiler decide */
 #define IA3_D __device__ __forceinline__
 #else
 #define IA3_HD inline
+#define IA3_HDN inline
 #define IA3_D inline
 #endif
 

@@ -47,7 +47,7 @@ IA3_HD double enorm_n(const double* v, int n) {
 
 // Pivoted Cholesky of the packed symmetric A (55 entries) with MINPACK qrfac's pivoting.
 // Outputs st.R (upper), st.ipvt, st.acn and st.qtf = R^-T (g permuted).
-IA3_HD void lm_factor(LMState& st, const double* A, const double* g) {
+IA3_HDN void lm_factor(LMState& st, const double* A, const double* g) {
   double M[NP][NP];
   double rd[NP];  // remaining squared norms (Schur complement diagonal)
   double gp[NP];
@@ -98,7 +98,7 @@ IA3_HD void lm_factor(LMState& st, const double* A, const double* g) {
 }
 
 // MINPACK qrsolv: solve min |R P^T x - qtb|^2 + |D x|^2 given d = sqrt(par)*diag.
-IA3_HD void lm_qrsolv(LMState& st, const double* d, double* x /*out, unpermuted*/, double* wa) {
+IA3_HDN void lm_qrsolv(LMState& st, const double* d, double* x /*out, unpermuted*/, double* wa) {
   double (*r)[NP] = st.R;
   double xsave[NP];
   for (int j = 0; j < NP; ++j) {
@@ -153,7 +153,7 @@ IA3_HD void lm_qrsolv(LMState& st, const double* d, double* x /*out, unpermuted*
 }
 
 // MINPACK lmpar: on return st.par is the LM parameter and xout the (positive-sign) step.
-IA3_HD void lm_lmpar(LMState& st, double* xout) {
+IA3_HDN void lm_lmpar(LMState& st, double* xout) {
   const double dwarf = DBL_MIN;
   double* wa1 = st.w1;
   double* wa2 = st.w2;
@@ -245,7 +245,7 @@ IA3_HD void lm_init(LMState& st, const double* x0, double fnorm0) {
 }
 
 // After a Jacobian pass at st.x (A = J^T J, g = J^T f).  Returns false if lmder stops here.
-IA3_HD bool lm_outer(LMState& st, const LMConfig& cfg, const double* A, const double* g) {
+IA3_HDN bool lm_outer(LMState& st, const LMConfig& cfg, const double* A, const double* g) {
   st.njev += 1;
   lm_factor(st, A, g);
   if (st.iter == 1) {
@@ -273,7 +273,7 @@ IA3_HD bool lm_outer(LMState& st, const LMConfig& cfg, const double* A, const do
 }
 
 // Compute the LM step and the trial point st.xt (model must then be evaluated at st.xt).
-IA3_HD void lm_propose(LMState& st) {
+IA3_HDN void lm_propose(LMState& st) {
   lm_lmpar(st, st.p);
   for (int j = 0; j < NP; ++j) {
     st.p[j] = -st.p[j];
@@ -287,7 +287,7 @@ IA3_HD void lm_propose(LMState& st) {
 enum { LM_RETRY = 0, LM_ACCEPTED = 1, LM_DONE = 2 };
 
 // Given fnorm1 = |f(st.xt)|: ratio test, trust-region update, convergence tests.
-IA3_HD int lm_judge(LMState& st, const LMConfig& cfg, double fnorm1) {
+IA3_HDN int lm_judge(LMState& st, const LMConfig& cfg, double fnorm1) {
   st.nfev += 1;
   st.fnorm1 = fnorm1;
   const double fnorm = st.fnorm;

@@ -1,0 +1,428 @@
+// Seed stage kernels (sm_100a): exact separable Gaussian, 3D rank filters + candidate mask,
+// ordered prefix-sum stream compaction.
+//
+// What "exact" means here (spot_tools/fitting.py:91-125): scipy's
+// gaussian_filter on a uint16 stack runs three 1-D correlations (axes 0,1,2); each pass
+// accumulates in double as   acc = x[0]*w[0];  for j = r..1: acc += (x[-j] + x[+j]) * w[j]
+// (outermost pair first, multiply and add NOT fused) and stores (uint16)acc -- truncation --
+// before the next axis reads it; boundary = reflect.  The kernels below reproduce that
+// arithmetic operation for operation (__dmul_rn / __dadd_rn are never contracted to FMA), so
+// the filtered volumes, and therefore the seeds, are bit-identical to scipy's.  The price is
+// ~91 FP64 instructions per voxel for the sigma=7.5 (61-tap) passes: this stage is bound by the
+// FP64 pipe, not by HBM; DESIGN.md states both rooflines.
+//
+// Layout of one pass: the volume is viewed as [outer][L][inner] with the filter axis of
+// length L in the middle.  A block owns 128 "lines" x TL axis positions; the (TL + 2r) x 128
+// input tile is staged in shared memory as float (exact for uint16 and float32 inputs) with an
+// odd pitch, one thread walks one line and produces 8 outputs per step from a register window
+// of 8 + 2r doubles (8.5 shared loads per output instead of 61).
+#include "ia3_device.h"
+#include "seed_kernels.h"
+
+namespace ia3 {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  // scipy NI_EXTEND_REFLECT: (d c b a | a b c d | d c b a), any number of reflections
+  if (n <= 1) return 0;
+  const int p = 2 * n;
+  int m = i % p;
+  if (m < 0) m += p;
+  return m < n ? m : p - 1 - m;
+}
+
+template <typename T> __device__ __forceinline__ T store_cast(double acc);
+template <> __device__ __forceinline__ uint16_t store_cast<uint16_t>(double acc) {
+  return (uint16_t)__double2int_rz(acc);   // C cast double -> npy_uint16: truncation
+}
+template <> __device__ __forceinline__ float store_cast<float>(double acc) { return __double2float_rn(acc); }
+
+constexpr int LINES = 128;   // lines per block = threads per block
+constexpr int CHMAX = 8;     // outputs per register-window step (4 for the 81-tap legacy filter: register budget)
+
+// R > 0: compile-time radius (fully unrolled register window).  R == 0: runtime radius gw.r,
+// taps read straight from shared memory (slow path for unusual sigmas).
+template <int R, typename Tin, bool INNER1>
+__global__ void __launch_bounds__(LINES, 2)
+k_gauss_axis(const Tin* __restrict__ in, Tin* __restrict__ out, int L, long long inner, long long n_lines,
+             int TL, GaussW gw) {
+  extern __shared__ float smem[];
+  constexpr int CH = (R > 32) ? 4 : CHMAX;
+  const int r = (R > 0) ? R : gw.r;
+  const int span = TL + 2 * r;
+  const int pitch = span | 1;
+  float* tile = smem;
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * TL;
+  const long long l0 = (long long)blockIdx.x * LINES;
+  const bool interior = (a0 - r >= 0) && (a0 + TL + r <= L);
+
+  long long base = 0;
+  bool ok = false;
+  if (!INNER1) {
+    const long long l = l0 + tid;
+    ok = l < n_lines;
+    if (ok) base = (l / inner) * ((long long)L * inner) + (l % inner);
+    const Tin* src = in + base;
+    if (interior) {
+      const Tin* s2 = src + (long long)(a0 - r) * inner;
+#pragma unroll 4
+      for (int a = 0; a < span; ++a) tile[tid * pitch + a] = ok ? (float)s2[(long long)a * inner] : 0.f;
+    } else {
+      for (int a = 0; a < span; ++a) {
+        const int sidx = reflect_idx(a0 - r + a, L);
+        tile[tid * pitch + a] = ok ? (float)src[(long long)sidx * inner] : 0.f;
+      }
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int ll = warp; ll < LINES; ll += LINES / 32) {
+      const long long l = l0 + ll;
+      if (l >= n_lines) break;
+      const Tin* row = in + l * (long long)L;
+      if (interior) {
+        for (int a = lane; a < span; a += 32) tile[ll * pitch + a] = (float)row[a0 - r + a];
+      } else {
+        for (int a = lane; a < span; a += 32) tile[ll * pitch + a] = (float)row[reflect_idx(a0 - r + a, L)];
+      }
+    }
+    ok = (l0 + tid) < n_lines;
+  }
+  __syncthreads();
+
+  // staging tile for the contiguous-axis pass (outputs must leave coalesced)
+  Tin* otile = reinterpret_cast<Tin*>(smem + LINES * pitch);
+  const int opitch = (sizeof(Tin) == 2) ? (TL + 2) : (TL + 1);
+
+  const float* my = tile + tid * pitch;
+  const int nvalid = ok ? min(TL, L - a0) : 0;
+  for (int c = 0; c < nvalid; c += CH) {
+    double acc[CH];
+    if (R > 0) {
+      double v[CH + 2 * (R > 0 ? R : 1)];
+#pragma unroll
+      for (int i = 0; i < CH + 2 * R; ++i) v[i] = (double)my[c + i];
+#pragma unroll
+      for (int o = 0; o < CH; ++o) {
+        double a = __dmul_rn(v[o + R], gw.w[0]);
+#pragma unroll
+        for (int j = R; j >= 1; --j) a = __dadd_rn(a, __dmul_rn(__dadd_rn(v[o + R - j], v[o + R + j]), gw.w[j]));
+        acc[o] = a;
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < CH; ++o) {
+        const float* ctr = my + c + o + r;
+        double a = __dmul_rn((double)ctr[0], gw.w[0]);
+        for (int j = r; j >= 1; --j) a = __dadd_rn(a, __dmul_rn(__dadd_rn((double)ctr[-j], (double)ctr[j]), gw.w[j]));
+        acc[o] = a;
+      }
+    }
+    if (!INNER1) {
+      if (ok) {
+#pragma unroll
+        for (int o = 0; o < CH; ++o)
+          if (c + o < nvalid) out[base + (long long)(a0 + c + o) * inner] = store_cast<Tin>(acc[o]);
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < CH; ++o) otile[tid * opitch + c + o] = store_cast<Tin>(acc[o]);
+    }
+  }
+  if (INNER1) {
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int ll = warp; ll < LINES; ll += LINES / 32) {
+      const long long l = l0 + ll;
+      if (l >= n_lines) break;
+      Tin* row = out + l * (long long)L + a0;
+      const int nout = min(TL, L - a0);
+      for (int a = lane; a < nout; a += 32) row[a] = otile[ll * opitch + a];
+    }
+  }
+}
+
+template <int R, typename Tin, bool INNER1>
+static int launch_axis(const Tin* in, Tin* out, int L, long long inner, long long n_lines, const GaussW& gw,
+                       cudaStream_t st) {
+  const int r = (R > 0) ? R : gw.r;
+  int TL = 64;
+  if (L < TL) TL = ((L + CHMAX - 1) / CHMAX) * CHMAX;
+  const int span = TL + 2 * r, pitch = span | 1;
+  size_t smem = (size_t)LINES * pitch * sizeof(float);
+  if (INNER1) smem += (size_t)LINES * (TL + 2) * sizeof(Tin);
+  auto kern = k_gauss_axis<R, Tin, INNER1>;
+  IA3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((n_lines + LINES - 1) / LINES), (unsigned)((L + TL - 1) / TL));
+  kern<<<grid, LINES, smem, st>>>(in, out, L, inner, n_lines, TL, gw);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename Tin, bool INNER1>
+static int dispatch_axis(const Tin* in, Tin* out, int L, long long inner, long long n_lines, const GaussW& gw,
+                         cudaStream_t st) {
+  switch (gw.r) {
+    case 3: return launch_axis<3, Tin, INNER1>(in, out, L, inner, n_lines, gw, st);
+    case 30: return launch_axis<30, Tin, INNER1>(in, out, L, inner, n_lines, gw, st);
+    case 40: return launch_axis<40, Tin, INNER1>(in, out, L, inner, n_lines, gw, st);
+    default: return launch_axis<0, Tin, INNER1>(in, out, L, inner, n_lines, gw, st);
+  }
+}
+
+// in -> bufA (z pass) -> bufB (x pass) -> bufA (y pass); result in bufA.
+template <typename Tin>
+int gaussian_filter_exact(const Tin* in, Tin* bufA, Tin* bufB, int Z, int X, int Y, const GaussW& gw,
+                          cudaStream_t st) {
+  if (gw.r > GaussW::MAXR) { set_error("gaussian radius too large (max 95)"); return -1; }
+  const long long XY = (long long)X * Y;
+  int rc;
+  if ((rc = dispatch_axis<Tin, false>(in, bufA, Z, XY, XY, gw, st))) return rc;
+  if ((rc = dispatch_axis<Tin, false>(bufA, bufB, X, Y, (long long)Z * Y, gw, st))) return rc;
+  if ((rc = dispatch_axis<Tin, true>(bufB, bufA, Y, 1, (long long)Z * X, gw, st))) return rc;
+  return 0;
+}
+template int gaussian_filter_exact<uint16_t>(const uint16_t*, uint16_t*, uint16_t*, int, int, int, const GaussW&, cudaStream_t);
+template int gaussian_filter_exact<float>(const float*, float*, float*, int, int, int, const GaussW&, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// Rank filters + candidate mask.  scipy's maximum_filter/minimum_filter(size=s) with reflect
+// boundary equal the max/min over the in-bounds part of the window [i - s/2, i + s - s/2 - 1]
+// on every axis (a reflected sample is always already inside the window).  One thread owns 8
+// consecutive voxels of a row ("chunk"); chunks are numbered in C order so that the later
+// prefix sum yields np.where's ordering.
+// ------------------------------------------------------------------------------------------
+constexpr int FLAG_THREADS = 256;
+
+template <typename Tin> __device__ __forceinline__ void load10(const Tin* row, int y0, int Y, bool vec, Tin* v);
+template <>
+__device__ __forceinline__ void load10<uint16_t>(const uint16_t* row, int y0, int Y, bool vec, uint16_t* v) {
+  if (vec) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + y0);
+    v[1] = q.x & 0xffff; v[2] = q.x >> 16; v[3] = q.y & 0xffff; v[4] = q.y >> 16;
+    v[5] = q.z & 0xffff; v[6] = q.z >> 16; v[7] = q.w & 0xffff; v[8] = q.w >> 16;
+    v[0] = row[max(y0 - 1, 0)];
+    v[9] = row[min(y0 + 8, Y - 1)];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = row[min(max(y0 - 1 + i, 0), Y - 1)];
+  }
+}
+template <>
+__device__ __forceinline__ void load10<float>(const float* row, int y0, int Y, bool vec, float* v) {
+  if (vec) {
+    const float4 a = *reinterpret_cast<const float4*>(row + y0);
+    const float4 b = *reinterpret_cast<const float4*>(row + y0 + 4);
+    v[1] = a.x; v[2] = a.y; v[3] = a.z; v[4] = a.w; v[5] = b.x; v[6] = b.y; v[7] = b.z; v[8] = b.w;
+    v[0] = row[max(y0 - 1, 0)];
+    v[9] = row[min(y0 + 8, Y - 1)];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = row[min(max(y0 - 1 + i, 0), Y - 1)];
+  }
+}
+
+template <typename Tin> struct DiffT;
+template <> struct DiffT<uint16_t> {
+  static __device__ __forceinline__ double diff(uint16_t a, uint16_t b) { return (double)((int)a - (int)b); }
+  static __device__ __forceinline__ bool nonzero(uint16_t a) { return a != 0; }
+};
+template <> struct DiffT<float> {
+  // numpy: float32 - float32 in float32
+  static __device__ __forceinline__ double diff(float a, float b) { return (double)__fsub_rn(a, b); }
+  static __device__ __forceinline__ bool nonzero(float a) { return a != 0.f; }
+};
+
+// generic (any filt_size) rank value at one voxel
+template <typename Tin, bool ISMAX>
+__device__ Tin rank_at(const Tin* vol, int z, int x, int y, int Z, int X, int Y, int s1, int s2) {
+  Tin best = vol[((long long)z * X + x) * Y + y];
+  for (int dz = -s1; dz <= s2; ++dz) {
+    const int zz = z + dz; if (zz < 0 || zz >= Z) continue;
+    for (int dx = -s1; dx <= s2; ++dx) {
+      const int xx = x + dx; if (xx < 0 || xx >= X) continue;
+      const Tin* row = vol + ((long long)zz * X + xx) * Y;
+      for (int dy = -s1; dy <= s2; ++dy) {
+        const int yy = y + dy; if (yy < 0 || yy >= Y) continue;
+        const Tin v = row[yy];
+        if (ISMAX ? (v > best) : (v < best)) best = v;
+      }
+    }
+  }
+  return best;
+}
+
+template <typename Tin, int VARIANT>
+__global__ void __launch_bounds__(FLAG_THREADS)
+k_flags(const Tin* __restrict__ fg, const Tin* __restrict__ bg, SeedDims d, uint8_t* __restrict__ bits,
+        int* __restrict__ block_counts) {
+  const long long cidx = (long long)blockIdx.x * FLAG_THREADS + threadIdx.x;
+  uint32_t mask = 0;
+  if (cidx < d.n_chunks) {
+    const long long row = cidx / d.cpr;
+    const int y0 = (int)(cidx % d.cpr) * 8;
+    const int z = (int)(row / d.X), x = (int)(row % d.X);
+    const int nv = min(8, d.Y - y0);
+    const bool vec = (d.Y % 8 == 0);
+    if (d.fs == 3) {
+      Tin cmax[10], cmin[10], fc[10], bc[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) { cmax[i] = 0; cmin[i] = 0; }
+      bool first = true;
+      for (int dz = -1; dz <= 1; ++dz) {
+        const int zz = z + dz; if (zz < 0 || zz >= d.Z) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx; if (xx < 0 || xx >= d.X) continue;
+          const long long ro = ((long long)zz * d.X + xx) * d.Y;
+          Tin vf[10], vb[10];
+          load10<Tin>(fg + ro, y0, d.Y, vec, vf);
+          load10<Tin>(bg + ro, y0, d.Y, vec, vb);
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            cmax[i] = first ? vf[i] : (vf[i] > cmax[i] ? vf[i] : cmax[i]);
+            cmin[i] = first ? vb[i] : (vb[i] < cmin[i] ? vb[i] : cmin[i]);
+          }
+          if (dz == 0 && dx == 0) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) { fc[i] = vf[i]; bc[i] = vb[i]; }
+          }
+          first = false;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i >= nv) break;
+        Tin mx = cmax[i + 1]; if (cmax[i] > mx) mx = cmax[i]; if (cmax[i + 2] > mx) mx = cmax[i + 2];
+        Tin mn = cmin[i + 1]; if (cmin[i] < mn) mn = cmin[i]; if (cmin[i + 2] < mn) mn = cmin[i + 2];
+        const Tin f = fc[i + 1], b = bc[i + 1];
+        bool keep = (mx == f) && (mn != b);
+        if (VARIANT == 0) {
+          keep = keep && (DiffT<Tin>::diff(f, b) >= d.h_min);
+        } else {
+          keep = keep && DiffT<Tin>::nonzero(mn) && (DiffT<Tin>::diff(f, mn) >= d.h_min);
+        }
+        if (keep) mask |= (1u << i);
+      }
+    } else {
+      for (int i = 0; i < nv; ++i) {
+        const int y = y0 + i;
+        const long long li = ((long long)z * d.X + x) * d.Y + y;
+        const Tin f = fg[li], b = bg[li];
+        const Tin mx = rank_at<Tin, true>(fg, z, x, y, d.Z, d.X, d.Y, d.s1, d.s2);
+        if (!(mx == f)) continue;
+        const Tin mn = rank_at<Tin, false>(bg, z, x, y, d.Z, d.X, d.Y, d.s1, d.s2);
+        bool keep = (mn != b);
+        if (VARIANT == 0) keep = keep && (DiffT<Tin>::diff(f, b) >= d.h_min);
+        else keep = keep && DiffT<Tin>::nonzero(mn) && (DiffT<Tin>::diff(f, mn) >= d.h_min);
+        if (keep) mask |= (1u << i);
+      }
+    }
+    if (VARIANT == 0 && d.edge_on) {
+      // remove_edge_points (spot_tools/fitting.py:156-165): d <= c <= size - d, inclusive
+      if (z < d.lo || z > d.hiZ || x < d.lo || x > d.hiX) mask = 0;
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int y = y0 + i; if (y < d.lo || y > d.hiY) mask &= ~(1u << i); }
+      }
+    }
+    bits[cidx] = (uint8_t)mask;
+  }
+  // block count (warp popc reduce + shared)
+  __shared__ int wsum[FLAG_THREADS / 32];
+  int c = __popc(mask);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < FLAG_THREADS / 32; ++i) t += wsum[i];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// Exclusive scan of the per-block counts by one 1024-thread block (n is ~1e5: one pass of
+// contiguous per-thread segments + a block scan of the segment sums).  offsets[n] = total.
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, int n) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = t * per, e = min(n, b + per);
+  long long s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+    long long v = (t >= o) ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = part[t] - s;
+  for (int i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
+  if (t == 1023) offsets[n] = part[1023];
+}
+
+template <typename Tin, int VARIANT>
+__global__ void __launch_bounds__(FLAG_THREADS)
+k_emit(const Tin* __restrict__ fg, const Tin* __restrict__ bg, SeedDims d, const uint8_t* __restrict__ bits,
+       const long long* __restrict__ offsets, int32_t* __restrict__ out_zxy, float* __restrict__ out_h) {
+  const long long cidx = (long long)blockIdx.x * FLAG_THREADS + threadIdx.x;
+  const uint32_t mask = (cidx < d.n_chunks) ? bits[cidx] : 0u;
+  const int c = __popc(mask);
+  // block-exclusive prefix of c
+  __shared__ int wsum[FLAG_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int i = 0; i < warp; ++i) wbase += wsum[i];
+  if (mask == 0) return;
+  long long pos = offsets[blockIdx.x] + wbase + (incl - c);
+  const long long row = cidx / d.cpr;
+  const int y0 = (int)(cidx % d.cpr) * 8;
+  const int z = (int)(row / d.X), x = (int)(row % d.X);
+  for (int i = 0; i < 8; ++i) {
+    if (!(mask & (1u << i))) continue;
+    const int y = y0 + i;
+    const long long li = ((long long)z * d.X + x) * d.Y + y;
+    float h;
+    if (VARIANT == 0) h = (float)DiffT<Tin>::diff(fg[li], bg[li]);
+    else h = (float)DiffT<Tin>::diff(fg[li], rank_at<Tin, false>(bg, z, x, y, d.Z, d.X, d.Y, d.s1, d.s2));
+    out_zxy[3 * pos] = z; out_zxy[3 * pos + 1] = x; out_zxy[3 * pos + 2] = y;
+    out_h[pos] = h;
+    ++pos;
+  }
+}
+
+template <typename Tin>
+int seed_flags(const Tin* fg, const Tin* bg, const SeedDims& d, int variant, uint8_t* bits, int* counts,
+               long long* offsets, cudaStream_t st) {
+  const int nb = d.n_blocks;
+  if (variant == 0) k_flags<Tin, 0><<<nb, FLAG_THREADS, 0, st>>>(fg, bg, d, bits, counts);
+  else k_flags<Tin, 1><<<nb, FLAG_THREADS, 0, st>>>(fg, bg, d, bits, counts);
+  IA3_LAUNCH_CHECK();
+  k_scan_counts<<<1, 1024, 0, st>>>(counts, offsets, nb);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+template <typename Tin>
+int seed_emit(const Tin* fg, const Tin* bg, const SeedDims& d, int variant, const uint8_t* bits,
+              const long long* offsets, int32_t* out_zxy, float* out_h, cudaStream_t st) {
+  const int nb = d.n_blocks;
+  if (variant == 0) k_emit<Tin, 0><<<nb, FLAG_THREADS, 0, st>>>(fg, bg, d, bits, offsets, out_zxy, out_h);
+  else k_emit<Tin, 1><<<nb, FLAG_THREADS, 0, st>>>(fg, bg, d, bits, offsets, out_zxy, out_h);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+template int seed_flags<uint16_t>(const uint16_t*, const uint16_t*, const SeedDims&, int, uint8_t*, int*, long long*, cudaStream_t);
+template int seed_flags<float>(const float*, const float*, const SeedDims&, int, uint8_t*, int*, long long*, cudaStream_t);
+template int seed_emit<uint16_t>(const uint16_t*, const uint16_t*, const SeedDims&, int, const uint8_t*, const long long*, int32_t*, float*, cudaStream_t);
+template int seed_emit<float>(const float*, const float*, const SeedDims&, int, const uint8_t*, const long long*, int32_t*, float*, cudaStream_t);
+
+int seed_flag_threads() { return FLAG_THREADS; }
+
+}  // namespace ia3

@@ -1,0 +1,141 @@
+/* ia3b200.h -- C ABI of libia3b200.so: B200 (sm_100a) spot finding for 3D FISH stacks.
+ *
+ * The reference (zhengpuas47/ImageAnalysis3) has no FFI for this path: the boundary is a set of
+ * Python call signatures.  Each entry point below is what the Python mirror in
+ * imageanalysis3_b200/{spot_tools/fitting.py, External/Fitting_v4.py, External/Fitting_v3.py,
+ * visual_tools.py} binds through ctypes, and cites the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every pointer is HOST memory unless the name
+ * starts with d_; stacks are C-contiguous (Z, X, Y); return value 0 = OK, negative = error
+ * (ia3_last_error() gives the text).  Calls on one handle are not thread-safe; different
+ * handles may be used from different threads.  CUDA is initialised lazily inside the calling
+ * process (fork-safe as long as the parent has not called into the library).
+ */
+#ifndef IA3B200_H
+#define IA3B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IA3_DTYPE_U16 0
+#define IA3_DTYPE_F32 1
+#define IA3_DTYPE_F64 2   /* fit stage only */
+
+typedef struct ia3_stack ia3_stack;   /* one image stack resident in HBM + its work buffers */
+typedef struct ia3_fit ia3_fit;       /* one iter_fit_seed_points object on a stack */
+
+/* ---- process / device ---------------------------------------------------------------- */
+int ia3_init(int device);                 /* select device (default: IA3_DEVICE env or 0) */
+const char* ia3_last_error(void);
+int ia3_version(void);
+int ia3_device_sm_count(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t ia3_launch_count(void);
+/* CUDA-event stopwatch on the library's stream (all kernels and copies of this process are issued
+ * on it): start records an event after a device sync, stop returns the elapsed device time. */
+int ia3_timer_start(void);
+int ia3_timer_stop(float* ms);
+
+/* ---- stacks ---------------------------------------------------------------------------- */
+/* Upload a host stack (pageable or pinned) -- one H2D copy per stack; seed and fit stages then
+ * share the resident copy.  Replaces the implicit "im" argument of get_seeds / fit_fov_image /
+ * iter_fit_seed_points (spot_tools/fitting.py:20,169; External/Fitting_v4.py:560). */
+int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack** out);
+/* Wrap a stack that is already in device memory (no copy, not owned). */
+int ia3_stack_wrap_device(const void* d_im, int dtype, int Z, int X, int Y, ia3_stack** out);
+int ia3_stack_destroy(ia3_stack* s);
+
+/* ---- seed stage ------------------------------------------------------------------------ */
+typedef struct {
+  /* half kernels: w[j] = weight at distance j from the centre tap, j = 0..r (scipy
+   * _gaussian_kernel1d, truncate=4 -> r = int(4*sigma+0.5)); r < 0 = "no blur" (gfilt_size
+   * falsy, spot_tools/fitting.py:93-94,100-101) */
+  const double* w_fg; int r_fg;
+  const double* w_bg; int r_bg;
+  int filt_size;          /* maximum_filter / minimum_filter size (3) */
+  int variant;            /* 0: spot_tools.fitting.get_seeds (:91-125)
+                             1: visual_tools.get_seed_points_base (visual_tools.py:348-367) */
+  double edge;            /* variant 0: min_edge_distance (keep d <= c <= size-d); <=0 = off */
+  double h_min;           /* keep candidates with h >= h_min (host folds >, >=, float32/float64
+                             comparison semantics into this number) */
+} ia3_seed_cfg;
+
+typedef struct {
+  float ms_gauss_fg, ms_gauss_bg, ms_rank, ms_compact, ms_total;
+} ia3_seed_timing;
+
+/* Runs the whole device part of the seed stage: two separable Gaussian blurs with scipy's exact
+ * integer semantics (per-axis uint16 truncation, reflect boundary, FP64 symmetric-pair order),
+ * 3D max / min rank filters, mask, threshold, edge filter, and an ordered (C order: z, x, y)
+ * prefix-sum stream compaction.  Candidates stay on the device until fetched.
+ * Replaces spot_tools/fitting.py:91-125 and visual_tools.py:350-367. */
+int ia3_seed_run(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, ia3_seed_timing* t);
+/* Copy candidates to the host: zxy is n x 3 int32 (C order of the stack), h is n float32
+ * (variant 0: max_im - min_im; variant 1: max_im - min_filter(min_im)). */
+int ia3_seed_fetch(ia3_stack* s, int32_t* zxy, float* h, int64_t cap);
+/* Debug/parity taps: copy an intermediate volume back (which: 0 = foreground blur,
+ * 1 = background blur), same dtype as the stack. */
+int ia3_seed_fetch_volume(ia3_stack* s, int which, void* out);
+
+/* ---- fit stage ------------------------------------------------------------------------- */
+typedef struct {
+  int personality;      /* 4: External/Fitting_v4.py GaussianFit; 3: External/Fitting_v3.py */
+  int radius;           /* radius_fit (5): window = offsets -r..r-1 with d^2 <= r^2 */
+  double min_w, max_w;  /* sigma bounds (0.5, 4) */
+  double init_w[3];     /* v4: scalar init_w replicated; v3: per-axis init_w (_sigma_zxy) */
+  double weight_sigma;  /* v3 width prior (0 = off) */
+  int maxfev;           /* 1000 (v4, Fitting_v4.py:388) / 1100 (v3, leastsq default) */
+  int eval_fp32;        /* 0: per-voxel model in FP64 (reference precision); 1: FP32 fast mode */
+} ia3_fit_cfg;
+
+/* iter_fit_seed_points.__init__ (Fitting_v4.py:560-588 / Fitting_v3.py:313-335):
+ * centers is n x 3 float64 (z, x, y). */
+int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_fit_cfg* cfg, ia3_fit** out);
+int ia3_fit_destroy(ia3_fit* f);
+
+/* firstfit, step 1: Voronoi membership of every window voxel (v4: cKDTree nearest seed,
+ * Fitting_v4.py:422-424,612; v3: brute-force argmin, lowest index wins, Fitting_v3.py:40-47).
+ * v4 only: voxels whose nearest seed is not unique are reported so that the caller can resolve
+ * them with the very same cKDTree (its tie-break is an implementation detail of scipy). */
+int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties);
+int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap);
+int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n);
+/* firstfit, step 2: all fits in one launch + ordered subtraction of the reconstructions
+ * (Fitting_v4.py:606-639).  Outputs (each may be NULL): ps n x 11 float32 (NaN rows on
+ * failure), p_raw n x 10 float64, success n, nfev n, info n. */
+int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw, uint8_t* success,
+                      int32_t* nfev, int32_t* info);
+/* one sweep of repeatfit over the seeds with active[i] != 0, in seed order (dependency levels
+ * keep the reference's sequential Gauss-Seidel semantics, Fitting_v4.py:651-675).  Only rows of
+ * active seeds are written. */
+int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active, float* ps, double* p_raw,
+                         uint8_t* success, int32_t* nfev, int32_t* info);
+/* lazily materialised attributes: which = 0 -> im_subtr snapshot taken after firstfit (only if
+ * requested before repeatfit), 1 -> im_add; float64 volume of the stack's shape. */
+int ia3_fit_get_volume(ia3_fit* f, int which, double* out);
+/* ims_rec[i]: reconstruction over the clipped window of seed i (float64, <= K values);
+ * also returns the window voxel coordinates (count x 3 int32) if zxy != NULL. */
+int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* count);
+int ia3_fit_num_levels(ia3_fit* f);
+float ia3_fit_last_ms(ia3_fit* f);        /* device time of the last first_run / repeat_sweep */
+
+/* ---- standalone GaussianFit ------------------------------------------------------------ */
+/* A batch of independent GaussianFit(im, X, center, ...).fit() calls (Fitting_v4.py:165-396,
+ * Fitting_v3.py:50-257).  Problem b uses values[off[b]:off[b+1]] (float64, as handed to
+ * GaussianFit) and coords[3*off[b] : 3*off[b+1]] (k x 3, float32-representable).
+ * rec (optional, same layout as values) receives get_im() on the same coordinates. */
+int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_problems, const int64_t* off,
+                       const double* values, const float* coords, const double* centers,
+                       float* ps, double* p_raw, uint8_t* success, int32_t* nfev, int32_t* info, double* rec);
+
+/* GaussianFit.get_im() (Fitting_v4.py:394-396): Gaussian part exp(h - q/2) of the model with raw
+ * parameters p_raw (10) on m coordinates (m x 3 float32). */
+int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_raw, const double* center,
+                   const float* coords, int64_t m, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

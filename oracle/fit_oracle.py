@@ -1,0 +1,282 @@
+"""ORACLE (test infrastructure, CPU) -- fit stage of ImageAnalysis3 restated.
+
+Not part of the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this.
+
+Restates, in a functional style,
+  GaussianFit (v4)          External/Fitting_v4.py:165-396
+  GaussianFit (v3)          External/Fitting_v3.py:50-257   (to_center quirk :86, width prior :173-177,:216-221)
+  iter_fit_seed_points      External/Fitting_v4.py:559-683 / External/Fitting_v3.py:312-421
+  fit_fov_image / get_centers  spot_tools/fitting.py:169-334 (post-filters)
+on top of scipy.optimize.leastsq (MINPACK lmder), scipy.spatial.cKDTree and numpy -- the
+reference's own third-party layer (scipy 1.18.1 / numpy 2.3.5 in this image; unpinned upstream).
+Precision follows what the reference does under numpy >= 2: data and voxel
+coordinates are cast to float32, the model is evaluated in float64, the Jacobian is cast to
+float32 before MINPACK sees it.
+
+Pinned: yes -- tests/test_oracle_pinned.py compares with the unmodified reference executed under
+the import shims (oracle/ref_loader.py) and with the committed fixtures in tests/golden/.
+"""
+import numpy as np
+from scipy.optimize import leastsq
+from scipy.spatial import cKDTree
+from scipy.spatial.distance import cdist
+
+from . import seed_oracle
+
+SIGMA_ZXY = [1.35, 1.9, 1.9]
+_LOGMAX = np.log(np.finfo(np.float64).max)
+
+
+class _Problem:
+    """One GaussianFit problem: data, coordinates, constraints."""
+
+    def __init__(self, vals, X, center, version, delta, min_w, max_w, init_w, weight_sigma):
+        self.version = version
+        self.wlo, self.whi = min_w * min_w, max_w * max_w
+        self.delta = delta
+        self.ws = weight_sigma
+        self.data = np.array(vals, dtype=np.float32)
+        self.X = np.array(X, dtype=np.float32)
+        order = np.argsort(vals)
+        if center is None:
+            center = np.median(np.asarray(X)[:, order][:, -10:], -1)
+        self.c_est = center
+        srt = np.asarray(vals)[order]
+        tiny = np.exp(-10.)
+        bk0 = np.log(np.max([np.mean(srt[:10]), tiny]))
+        h0 = np.log(np.max([np.mean(srt[-10:]), tiny]))
+        if version == 4:
+            w2 = init_w ** 2
+            g = np.log((self.whi - w2) / (w2 - self.wlo))
+            wg = [g, g, g]
+            self.prior = None
+        else:
+            iw = np.array(init_w[:3]).copy()
+            for i in range(3):
+                v = iw[i]
+                if v ** 2 > max_w or v ** 2 < min_w:      # sic: squared value vs unsquared bound
+                    iw[i] = 1.5 ** 2
+                iw[i] = np.log((self.whi - iw[i] ** 2) / (iw[i] ** 2 - self.wlo))
+            wg = list(iw)
+            self.prior = iw
+        self.p0 = np.array([bk0, h0, 0, 0, 0, wg[0], wg[1], wg[2], 0, 0], dtype=np.float32)
+
+    # ---- constraint maps ------------------------------------------------------------------
+    def _sig(self, a, num, off, lo, hi):
+        if self.version == 4:
+            if a >= _LOGMAX:
+                return lo
+            if a <= -_LOGMAX:
+                return hi
+        return num / (1. + np.exp(a)) + off
+
+    def centre(self, a0, a1, a2):
+        d, c = self.delta, self.c_est
+        if self.version == 4:
+            out = []
+            for a, ce in zip((a0, a1, a2), c):
+                if a >= _LOGMAX:
+                    out.append(-d + ce)
+                elif a <= -_LOGMAX:
+                    out.append(d + ce)
+                else:
+                    out.append(2. * d / (1. + np.exp(a)) - d + ce)
+            return out
+        e0, e1, e2 = np.exp(-a0), np.exp(-a1), np.exp(-a2)
+        return [2. * d * e0 / (1. + e0) - d + c[0],
+                2. * d * e1 / (1. + e1) - d + c[1],
+                2. * d * e1 / (1. + e2) - d + c[2]]      # sic (Fitting_v3.py:86)
+
+    def shape_terms(self, q):
+        bk, h, a0, a1, a2, w1, w2, w3, pp, tp = q
+        t = self._sig(tp, 2., -1., -1, 1)
+        p = self._sig(pp, 2., -1., -1, 1)
+        dw = self.whi - self.wlo
+        v = [self._sig(w, dw, self.wlo, self.wlo, dw + self.wlo) for w in (w1, w2, w3)]
+        return t, p, v
+
+    def quad(self, q, X=None):
+        """returns (xt, yt, zt, coefficient tuple, t, p, s)"""
+        X = self.X if X is None else X
+        t, p, v = self.shape_terms(q)
+        c = self.centre(q[2], q[3], q[4])
+        xt, yt, zt = X[0] - c[0], X[1] - c[1], X[2] - c[2]
+        p2, t2 = p * p, t * t
+        tc2, pc2 = 1 - t2, 1 - p2
+        tc, pc = np.sqrt(tc2), np.sqrt(pc2)
+        s1, s2, s3 = 1. / v[0], 1. / v[1], 1. / v[2]
+        A = pc2 * tc2 * s1 + t2 * s2 + p2 * tc2 * s3
+        B = pc2 * t2 * s1 + tc2 * s2 + p2 * t2 * s3
+        Cc = p2 * s1 + pc2 * s3
+        D = 2 * tc * t * (pc2 * s1 - s2 + p2 * s3)
+        E = 2 * p * pc * tc * (s3 - s1)
+        F = 2 * p * pc * t * (s3 - s1)
+        return xt, yt, zt, (A, B, Cc, D, E, F), (t, p, tc, pc, t2, p2, tc2, pc2), (s1, s2, s3)
+
+    def gauss(self, q, X=None):
+        xt, yt, zt, (A, B, Cc, D, E, F), _, _ = self.quad(q, X)
+        arg = A * xt * xt + B * yt * yt + Cc * zt * zt + D * xt * yt + E * xt * zt + F * yt * zt
+        return np.exp(q[1] - 0.5 * arg)
+
+    def residual(self, q):
+        bk = q[0]
+        if self.version == 4:
+            bk = np.clip(bk, -709.78, 709.78)
+        r = (np.exp(bk) + self.gauss(q)) - self.data
+        if self.version == 3 and self.ws > 0:
+            r = r + self.ws * np.linalg.norm(self.prior - np.array([q[5], q[6], q[7]]))
+        return r
+
+    @staticmethod
+    def _nw(w, lo, hi):
+        if w > 0:
+            e = np.exp(-w)
+            return 0.5 * (hi - lo) * e / (hi * e + lo) ** 2
+        e = np.exp(w)
+        return 0.5 * (hi - lo) * e / (lo * e + hi) ** 2
+
+    def jacobian(self, q):
+        bk, h, a0, a1, a2, w1, w2, w3, pp, tp = q
+        xt, yt, zt, (A, B, Cc, D, E, F), (t, p, tc, pc, t2, p2, tc2, pc2), (s1, s2, s3) = self.quad(q)
+        xx, xy, xz, yy, yz, zz = xt * xt, xt * yt, xt * zt, yt * yt, yt * zt, zt * zt
+        arg = A * xx + B * yy + Cc * zz + D * xy + E * xz + F * yz
+        g = np.exp(h - 0.5 * arg)
+        d, lo, hi = self.delta, self.wlo, self.whi
+        cols = [np.exp(bk) + np.zeros(len(g)), g]
+        for a, lin in ((a0, 2 * A * xt + D * yt + E * zt), (a1, xt * D + 2 * B * yt + F * zt), (a2, xt * E + yt * F + 2 * Cc * zt)):
+            e = np.exp(-np.abs(a))
+            cols.append((g * lin) * (-d * e / ((1 + e) * (1 + e))))
+        c6 = (g * (-pc2 * tc2 * xx - 2 * pc2 * t * tc * xy - pc2 * t2 * yy + 2 * p * pc * tc * xz + 2 * p * pc * t * yz - p2 * zz)) * self._nw(w1, lo, hi)
+        c7 = (g * (-t2 * xx + 2 * t * tc * xy - tc2 * yy)) * self._nw(w2, lo, hi)
+        c8 = (g * (-p2 * tc2 * xx - 2 * p2 * t * tc * xy - p2 * t2 * yy - 2 * p * pc * tc * xz - 2 * p * pc * t * yz - pc2 * zz)) * self._nw(w3, lo, hi)
+        if self.version == 3:
+            pr, ws = self.prior, self.ws
+            c6 = c6 + int(pr[0] > w1) * ws - int(pr[0] < w1) * ws
+            c7 = c7 + int(pr[1] > w2) * ws - int(pr[1] < w2) * ws
+            c8 = c8 + int(pr[2] > w3) * ws - int(pr[2] < w3) * ws
+        cols += [c6, c7, c8]
+        ep = np.exp(-np.abs(pp) / 2)
+        cols.append(g * (s3 - s1) * ((2 * pc2 - 1.) * (tc * xz + t * yz) + p * pc * (tc2 * xx + 2 * t * tc * xy + t2 * yy - zz)) * (ep / (1 + ep * ep)))
+        et = np.exp(-np.abs(tp) / 2)
+        cols.append(g * ((pc2 * s1 - s2 + p2 * s3) * (t * tc * (yy - xx) - (t2 - tc2) * xy) + p * pc * (s1 - s3) * (t * xz - tc * yz)) * (et / (1 + et * et)))
+        return np.array(cols, np.float32).T
+
+    def natural(self, q):
+        t, p, v = self.shape_terms(q)
+        c = self.centre(q[2], q[3], q[4])
+        eps = np.mean(np.abs(self.residual(q)))
+        return np.array([np.exp(q[1]), c[0], c[1], c[2], np.exp(q[0]), np.sqrt(v[0]), np.sqrt(v[1]), np.sqrt(v[2]), t, p, eps],
+                        dtype=np.float32)
+
+    def solve(self):
+        """-> (ok, natural parameters float32 (11), raw parameters float64 (10), nfev, ier)"""
+        if len(self.p0) > len(self.data):
+            return False, None, None, 0, 0
+        with np.errstate(all='ignore'):
+            kw = dict(maxfev=1000) if self.version == 4 else {}
+            q, _, info, _, ier = leastsq(self.residual, self.p0, Dfun=self.jacobian, full_output=True, **kw)
+            return True, self.natural(q), q, info['nfev'], ier
+
+
+def gaussian_fit(vals, X, center=None, version=4, delta_center=3., min_w=0.5, max_w=4., init_w=None, weight_sigma=0):
+    if init_w is None:
+        init_w = 1.5 if version == 4 else SIGMA_ZXY
+    pr = _Problem(vals, X, center, version, delta_center, min_w, max_w, init_w, weight_sigma)
+    ok, nat, q, nfev, ier = pr.solve()
+    return dict(success=ok, p=nat, p_raw=q, nfev=nfev, ier=ier, problem=pr)
+
+
+def window(radius):
+    g = np.reshape(np.indices([radius * 2] * 3) - radius, [3, -1])
+    return g[:, (g * g).sum(0) <= radius ** 2]
+
+
+def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_delta_center=2.5, n_max_iter=10,
+             max_dist_th=0.1, min_w=0.5, max_w=4., init_w=None, weight_sigma=0, do_repeat=True):
+    """firstfit (+ repeatfit) -> dict(ps=list, success, converged, n_iter, dists, first_ps, nfev_first, im_add)."""
+    if init_w is None:
+        init_w = 1.5 if version == 4 else SIGMA_ZXY
+    cen = np.asarray(centers_3xn).T
+    n = len(cen)
+    if n == 0:
+        if version == 3:
+            raise ValueError(f"{n} points have been seeded, exit.")
+        raise AttributeError("'iter_fit_seed_points' object has no attribute 'im_subtr'")
+    off = window(radius_fit)
+    shape = np.array(im.shape)[:, None]
+    work = np.array(im, dtype=float)
+    tree = cKDTree(cen) if version == 4 else None
+    mk = lambda v, X, c, d: _Problem(v, X, c, version, d, min_w, max_w, init_w, weight_sigma)
+    ps, cfit, ok_l, recs, nfevs = [], [], [], [], []
+
+    def ball(c):
+        v = off + np.array([int(c[0]), int(c[1]), int(c[2])])[:, None]
+        return v[:, ((v >= 0) & (v < shape)).all(0)]
+
+    for i, c in enumerate(cen):
+        full = ball(c)
+        if version == 4:
+            _, nn = tree.query(full.T, distance_upper_bound=radius_fit * 2)
+            mine = full[:, nn == i]
+        else:
+            near = np.argmin(cdist(full.T, cen), axis=-1)
+            me = np.argmin(cdist([c], cen)[0, :])
+            mine = full[:, near == me]
+        pr = mk(im[mine[0], mine[1], mine[2]], mine, [c[0], c[1], c[2]], min_delta_center)
+        ok, nat, q, nfev, _ = pr.solve()
+        ok_l.append(ok)
+        nfevs.append(nfev)
+        if ok:
+            rec = pr.gauss(q, full)
+            work[full[0], full[1], full[2]] -= rec
+            ps.append(nat); cfit.append(nat[1:4]); recs.append(rec)
+        else:
+            ps.append([np.nan] * 11); cfit.append([np.nan] * 3); recs.append(np.nan)
+    out = dict(first_ps=list(ps), first_success=list(ok_l), nfev_first=nfevs, im_subtr=work.copy())
+    n_iter, done = 0, np.zeros(n, dtype=bool)
+    dists = np.zeros(n) + np.inf
+    nfev_rep = []
+    stop = not do_repeat
+    while not stop:
+        ok_old, cf_old = np.array(ok_l), np.array(cfit)
+        for i, c in enumerate(cen):
+            if done[i]:
+                continue
+            full = ball(c)
+            vals = work[full[0], full[1], full[2]]
+            if ok_old[i]:
+                vals = recs[i] + vals
+            pr = mk(vals, full, [c[0], c[1], c[2]], max_delta_center)
+            ok, nat, q, nfev, _ = pr.solve()
+            ok_l[i] = ok
+            nfev_rep.append(nfev)
+            if ok:
+                rec = pr.gauss(q)
+                ps[i], cfit[i], recs[i] = nat, nat[1:4], rec
+                work[full[0], full[1], full[2]] = vals - rec
+        both = (np.array(ok_l) & ok_old) > 0
+        dists[~both] = 0
+        dists[both] = np.sum((cf_old[both] - np.array(cfit)[both]) ** 2, axis=-1)
+        done = dists < max_dist_th ** 2
+        n_iter += 1
+        stop = np.all(done) or (n_iter > n_max_iter)
+    out.update(ps=ps, success=ok_l, converged=done, n_iter=n_iter, dists=dists, im_add=work, nfev_repeat=nfev_rep)
+    return out
+
+
+def fit_fov_image_oracle(im, th_seed=300, max_num_seeds=500, fit_radius=5, remove_boundary_points=True,
+                         seed_backend="scipy", seeds=None, **seed_kw):
+    """spot_tools/fitting.py:169-262 without the optional intensity normalisation."""
+    if seeds is None:
+        seeds = seed_oracle.get_seeds_oracle(im, max_num_seeds=max_num_seeds, th_seed=float(th_seed),
+                                             backend=seed_backend, **seed_kw)
+    if len(seeds) == 0:
+        return np.array([]), seeds
+    res = iter_fit(im, seeds.T, version=4, radius_fit=fit_radius)
+    spots = np.array(res['ps'])
+    spots = spots[np.sum(np.isnan(spots), axis=1) == 0]
+    if remove_boundary_points:
+        inside = (spots[:, 1:4] > np.zeros(3)).all(1) * (spots[:, 1:4] < np.array(im.shape)).all(1)
+        spots = spots[np.where(inside)[0]]
+    return spots, seeds

@@ -1,0 +1,85 @@
+"""CPU: the numerical core of the fit kernel (csrc/lm_core.h, gauss_model.h, fit_spot.h), compiled
+with g++ and a one-lane executor (tests/hostsim), against the oracle (= scipy MINPACK on the
+reference's objective).  This is a debugging harness for a container without a GPU; the product
+never runs this code path."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import fit_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = ctypes.POINTER
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    out = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def _hostfit(lib, version, use_float, vals, X, cen, delta, init_w, ws=0.0, maxfev=1000):
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    coords = np.ascontiguousarray(np.asarray(X).T, dtype=np.int32)
+    cen = np.ascontiguousarray(cen, dtype=np.float64)
+    iw = np.ascontiguousarray(init_w, dtype=np.float64)
+    praw, ps, st = np.zeros(10), np.zeros(11, np.float32), np.zeros(3, np.int32)
+    rc = lib.hostsim_fit(version, use_float, vals.ctypes.data_as(P(ctypes.c_double)), coords.ctypes.data_as(P(ctypes.c_int)),
+                         len(vals), cen.ctypes.data_as(P(ctypes.c_double)), ctypes.c_double(delta), ctypes.c_double(0.5),
+                         ctypes.c_double(4.0), iw.ctypes.data_as(P(ctypes.c_double)), ctypes.c_double(ws), maxfev,
+                         praw.ctypes.data_as(P(ctypes.c_double)), ps.ctypes.data_as(P(ctypes.c_float)),
+                         st.ctypes.data_as(P(ctypes.c_int)))
+    return rc, praw, ps, st
+
+
+def _problems(golden_fits, n=12):
+    im, seeds = golden_fits["im"], golden_fits["seeds"]
+    off = fit_oracle.window(5)
+    shape = np.array(im.shape)[:, None]
+    for c in seeds[:n]:
+        v = off + np.array([int(c[0]), int(c[1]), int(c[2])])[:, None]
+        v = v[:, ((v >= 0) & (v < shape)).all(0)]
+        yield im[v[0], v[1], v[2]].astype(np.float64), v, [c[0], c[1], c[2]]
+
+
+@pytest.mark.parametrize("version,ws,delta", [(4, 0.0, 1.0), (4, 0.0, 2.5), (3, 0.0, 1.0), (3, 1000.0, 2.5)])
+def test_lm_core_follows_minpack(hostsim, golden_fits, version, ws, delta):
+    init_w = [1.5] * 3 if version == 4 else fit_oracle.SIGMA_ZXY
+    for vals, X, cen in _problems(golden_fits):
+        ref = fit_oracle.gaussian_fit(vals, X, center=cen, version=version, delta_center=delta, weight_sigma=ws)
+        rc, praw, ps, st = _hostfit(hostsim, version, 0, vals, X, cen, delta, init_w, ws, 1000 if version == 4 else 1100)
+        assert rc == 0
+        assert st[0] == ref["nfev"], "trust-region trajectory differs from lmder"
+        assert st[2] == ref["ier"]
+        assert np.abs(ps[1:4] - ref["p"][1:4]).max() <= 1e-4
+        assert np.allclose(ps, ref["p"], rtol=2e-5, atol=1e-5)
+
+
+def test_lm_core_blowup_path_matches_enorm(hostsim, golden_fits):
+    """v3 has no overflow guards: starting from a window whose 10 smallest values are negative
+    (bk0 = -10) MINPACK proposes bk ~ 1e6, residuals overflow, and enorm's inf/NaN semantics decide
+    how the trust region shrinks (fit_spot.h:pass_residual)."""
+    for vals, X, cen in _problems(golden_fits, 4):
+        vals = vals - 330.0
+        ref = fit_oracle.gaussian_fit(vals, X, center=cen, version=3, delta_center=2.5)
+        rc, praw, ps, st = _hostfit(hostsim, 3, 0, vals, X, cen, 2.5, fit_oracle.SIGMA_ZXY, 0.0, 1100)
+        assert st[0] == ref["nfev"] and st[2] == ref["ier"]
+        assert np.allclose(praw, ref["p_raw"], rtol=1e-6, atol=1e-6)
+
+
+def test_get_im_matches(hostsim, golden_fits):
+    g = golden_fits
+    X = np.ascontiguousarray(g["gf_X"].T, dtype=np.int32)
+    out = np.zeros(len(X))
+    praw = np.ascontiguousarray(g["gf_p_raw"], dtype=np.float64)
+    vals = g["im"][g["gf_X"][0], g["gf_X"][1], g["gf_X"][2]]
+    cen = np.ascontiguousarray(np.median(g["gf_X"][:, np.argsort(vals)][:, -10:], -1), dtype=np.float64)
+    hostsim.hostsim_get_im(4, praw.ctypes.data_as(P(ctypes.c_double)), cen.ctypes.data_as(P(ctypes.c_double)),
+                           ctypes.c_double(2.5), ctypes.c_double(0.5), ctypes.c_double(4.0),
+                           X.ctypes.data_as(P(ctypes.c_int)), len(X), out.ctypes.data_as(P(ctypes.c_double)))
+    assert np.allclose(out, g["gf_rec"], rtol=1e-12, atol=1e-12)

@@ -1,0 +1,112 @@
+"""CPU: the restated oracle against (i) the committed fixtures the unmodified reference produced,
+(ii) scipy itself for the C restatement, (iii) the live reference when /root/reference exists."""
+import numpy as np
+import pytest
+from scipy import ndimage
+
+from oracle import fit_oracle, ref_loader, seed_oracle
+from oracle.make_golden import SEED_CASES
+
+
+@pytest.mark.parametrize("name", sorted(SEED_CASES))
+@pytest.mark.parametrize("backend", ["scipy", "c"])
+def test_get_seeds_oracle_matches_golden(golden_seeds, name, backend):
+    got = seed_oracle.get_seeds_oracle(golden_seeds["im"], backend=backend, **SEED_CASES[name])
+    want = golden_seeds["seeds_" + name]
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+def test_get_seeds_oracle_float32(golden_seeds):
+    imf = golden_seeds["im"].astype(np.float32) / np.float32(301.7)
+    for backend in ("scipy", "c"):
+        assert np.array_equal(seed_oracle.get_seeds_oracle(imf, th_seed=1.0, backend=backend), golden_seeds["seeds_f32"])
+
+
+def test_legacy_seed_oracle_matches_golden(golden_seeds):
+    im = golden_seeds["im"]
+    for backend in ("scipy", "c"):
+        a = seed_oracle.legacy_seed_in_distance(im, center=None, th_seed=300, return_h=True, backend=backend)
+        assert a.dtype == np.int64 and np.array_equal(a, golden_seeds["legacy_all_h"])
+        b = seed_oracle.legacy_seed_in_distance(im, center=[10, 40, 50], th_seed=3000, num_seeds=6, backend=backend)
+        assert np.array_equal(b, golden_seeds["legacy_center"])
+        c = seed_oracle.legacy_seed_points_base(im, th_seed=200, hot_pix_th=3, return_h=True, backend=backend)
+        assert np.array_equal(c, golden_seeds["legacy_base"])
+
+
+@pytest.mark.parametrize("sigma", [0.75, 7.5, 10.0, 2.3])
+def test_c_gaussian_is_scipy_bit_exact(golden_seeds, sigma):
+    im = golden_seeds["im"]
+    assert np.array_equal(seed_oracle.gaussian_filter_c(im, sigma), ndimage.gaussian_filter(im, sigma))
+    imf = im.astype(np.float32) * np.float32(0.37)
+    assert np.array_equal(seed_oracle.gaussian_filter_c(imf, sigma), ndimage.gaussian_filter(imf, sigma))
+    tiny = np.ascontiguousarray(im[:5, :7, :9])      # radius > length: repeated reflection
+    assert np.array_equal(seed_oracle.gaussian_filter_c(tiny, sigma), ndimage.gaussian_filter(tiny, sigma))
+
+
+@pytest.mark.parametrize("size", [3, 4, 5])
+def test_c_rank_filters_are_scipy(golden_seeds, size):
+    im = golden_seeds["im"]
+    assert np.array_equal(seed_oracle.rank_filter_c(im, size, True), ndimage.maximum_filter(im, size))
+    assert np.array_equal(seed_oracle.rank_filter_c(im, size, False), ndimage.minimum_filter(im, size))
+
+
+def _rows(ps):
+    return np.array([np.asarray(r, dtype=np.float64) for r in ps])
+
+
+def test_iter_fit_oracle_v4_matches_golden(golden_fits):
+    g = golden_fits
+    o = fit_oracle.iter_fit(g["im"], g["seeds"].T, version=4)
+    assert np.array_equal(_rows(o["first_ps"]), g["v4_first"], equal_nan=True)
+    assert np.array_equal(_rows(o["ps"]), g["v4_final"], equal_nan=True)
+    assert o["n_iter"] == int(g["v4_n_iter"]) and np.array_equal(o["converged"], g["v4_converged"])
+    assert np.array_equal(o["dists"], g["v4_dists"])
+
+
+@pytest.mark.parametrize("ws", [0, 1000])
+def test_iter_fit_oracle_v3_matches_golden(golden_fits, ws):
+    g = golden_fits
+    o = fit_oracle.iter_fit(g["im"], g["seeds"].T, version=3, weight_sigma=ws)
+    assert np.array_equal(_rows(o["first_ps"]), g[f"v3_ws{ws}_first"], equal_nan=True)
+    assert np.array_equal(_rows(o["ps"]), g[f"v3_ws{ws}_final"], equal_nan=True)
+    assert o["n_iter"] == int(g[f"v3_ws{ws}_n_iter"])
+
+
+def test_iter_fit_oracle_edge_seeds(golden_fits):
+    g = golden_fits
+    o = fit_oracle.iter_fit(g["im"], g["edge_seeds"].T, version=4)
+    got = _rows(o["ps"])
+    assert np.array_equal(got, g["edge_final"], equal_nan=True)
+    assert np.isnan(got).any(1).sum() == 1          # the seed whose clipped window has < 10 voxels
+
+
+def test_fit_fov_image_oracle_matches_golden(golden_fits):
+    g = golden_fits
+    spots, _ = fit_oracle.fit_fov_image_oracle(g["im"], th_seed=300, max_num_seeds=None)
+    assert spots.dtype == np.float32 and np.array_equal(spots, g["fov_spots"])
+    spots, _ = fit_oracle.fit_fov_image_oracle(g["im"], th_seed=300, max_num_seeds=20)
+    assert np.array_equal(spots, g["fov_spots_top20"])
+
+
+def test_gaussian_fit_oracle_matches_golden(golden_fits):
+    g = golden_fits
+    X = g["gf_X"]
+    r = fit_oracle.gaussian_fit(g["im"][X[0], X[1], X[2]], X, center=None, version=4, delta_center=2.5)
+    assert np.array_equal(r["p"], g["gf_p"]) and np.array_equal(r["p_raw"], g["gf_p_raw"])
+    assert np.array_equal(r["problem"].gauss(r["p_raw"]), g["gf_rec"])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+def test_oracle_against_live_reference():
+    import warnings
+    warnings.simplefilter("ignore")
+    from imageanalysis3_b200.synth import synth
+    ns = ref_loader.load()
+    im = synth((16, 64, 72), 35, 21)
+    s_ref = ns.fitting.get_seeds(im, th_seed=250, return_h=True)
+    assert np.array_equal(seed_oracle.get_seeds_oracle(im, th_seed=250, return_h=True), s_ref)
+    f = ns.Fitting_v4.iter_fit_seed_points(im, s_ref[:, :3].T)
+    f.firstfit(); f.repeatfit()
+    o = fit_oracle.iter_fit(im, s_ref[:, :3].T, version=4)
+    assert np.array_equal(_rows(o["ps"]), _rows(f.ps), equal_nan=True)
+    assert np.array_equal(o["im_add"], f.im_add)
