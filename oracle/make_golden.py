@@ -14,7 +14,7 @@ import scipy
 
 from imageanalysis3_b200.synth import synth
 
-from . import ref_loader
+from . import fit_oracle, ref_loader
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -63,6 +63,11 @@ def main():
     f.repeatfit()
     out.update(v4_final=_rows(f.ps), v4_converged=f.converged, v4_n_iter=f.n_iter, v4_dists=f.dists,
                v4_success=np.array(f.success))
+    # which rows are determined by their data (fit_oracle.comparable_mask), from the oracle after
+    # checking that it reproduces the reference bit for bit
+    o = fit_oracle.iter_fit(im, seeds.T, version=4)
+    assert np.array_equal(_rows(o["ps"]), out["v4_final"], equal_nan=True)
+    out["v4_comparable"] = o["comparable"]
     for ws in (0, 1000):
         f = ns.Fitting_v3.iter_fit_seed_points(im, seeds.T, weight_sigma=ws)
         f.firstfit()
@@ -71,8 +76,17 @@ def main():
         out[f"v3_ws{ws}_final"] = _rows(f.ps)
         out[f"v3_ws{ws}_converged"] = f.converged
         out[f"v3_ws{ws}_n_iter"] = f.n_iter
+        o = fit_oracle.iter_fit(im, seeds.T, version=3, weight_sigma=ws)
+        assert np.array_equal(_rows(o["ps"]), out[f"v3_ws{ws}_final"], equal_nan=True)
+        out[f"v3_ws{ws}_comparable"] = o["comparable"]
     out["fov_spots"] = ns.fitting.fit_fov_image(im, '647', th_seed=300, max_num_seeds=None, verbose=False)
+    sp, _ = fit_oracle.fit_fov_image_oracle(im, th_seed=300, max_num_seeds=None)
+    assert np.array_equal(sp, out["fov_spots"])
+    out["fov_spots_comparable"] = fit_oracle.fit_fov_image_oracle.last_comparable
     out["fov_spots_top20"] = ns.fitting.fit_fov_image(im, '647', th_seed=300, max_num_seeds=20, verbose=False)
+    sp, _ = fit_oracle.fit_fov_image_oracle(im, th_seed=300, max_num_seeds=20)
+    assert np.array_equal(sp, out["fov_spots_top20"])
+    out["fov_spots_top20_comparable"] = fit_oracle.fit_fov_image_oracle.last_comparable
     out["centers"] = ns.fitting.get_centers(im, th_seed=300)
     out["std_centers"] = ns.visual.get_STD_centers(im, th_seed=300)
     # seeds at the border: windows clipped by the image, one seed with < 10 voxels -> NaN row
@@ -82,6 +96,10 @@ def main():
     f.firstfit(); f.repeatfit()
     out["edge_seeds"] = np.concatenate([seeds[:6], edge_seeds])
     out["edge_final"] = _rows(f.ps)
+    o = fit_oracle.iter_fit(im, out["edge_seeds"].T, version=4)
+    assert np.array_equal(_rows(o["ps"]), out["edge_final"], equal_nan=True)
+    out["edge_comparable"] = o["comparable"]
+    out["edge_cond_max"], out["edge_nfev_max"] = o["cond_max"], o["nfev_max"]
     # single GaussianFit problems
     zb, xb, yb = f.zb, f.xb, f.yb
     c = seeds[0]

@@ -83,3 +83,47 @@ def test_get_im_matches(hostsim, golden_fits):
                            ctypes.c_double(2.5), ctypes.c_double(0.5), ctypes.c_double(4.0),
                            X.ctypes.data_as(P(ctypes.c_int)), len(X), out.ctypes.data_as(P(ctypes.c_double)))
     assert np.allclose(out, g["gf_rec"], rtol=1e-12, atol=1e-12)
+
+
+def _hostfit_qr(lib, version, vals, X, cen, delta, init_w, ws=0.0, maxfev=1000):
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    coords = np.ascontiguousarray(np.asarray(X).T, dtype=np.int32)
+    cen = np.ascontiguousarray(cen, dtype=np.float64)
+    iw = np.ascontiguousarray(init_w, dtype=np.float64)
+    praw, ps, st = np.zeros(10), np.zeros(11, np.float32), np.zeros(3, np.int32)
+    lib.hostsim_fit_qr(version, vals.ctypes.data_as(P(ctypes.c_double)), coords.ctypes.data_as(P(ctypes.c_int)),
+                       len(vals), cen.ctypes.data_as(P(ctypes.c_double)), ctypes.c_double(delta), ctypes.c_double(0.5),
+                       ctypes.c_double(4.0), iw.ctypes.data_as(P(ctypes.c_double)), ctypes.c_double(ws), maxfev,
+                       praw.ctypes.data_as(P(ctypes.c_double)), ps.ctypes.data_as(P(ctypes.c_float)),
+                       st.ctypes.data_as(P(ctypes.c_int)))
+    return praw, ps, st
+
+
+def test_ill_posed_reference_fits_are_not_reproducible_by_minpack_itself(hostsim, golden_fits):
+    """Why tests exempt "ill-posed" rows (fit_oracle.comparable_mask): a second transcription of
+    MINPACK's own algorithm (Householder qrfac on the full Jacobian, same lmder / lmpar) that only
+    sums in a different order lands > 1e-3 px / > 1e-4 away from scipy on the junk corner seed that
+    runs into maxfev, while it agrees to 1e-5 on every well-posed fit.  No implementation other than
+    a bit-for-bit copy of MINPACK's instruction stream can "match the reference" on such rows."""
+    g = golden_fits
+    im, off = g["im"], fit_oracle.window(5)
+    shape = np.array(im.shape)[:, None]
+
+    def problem(c):
+        v = off + np.array([int(c[0]), int(c[1]), int(c[2])])[:, None]
+        v = v[:, ((v >= 0) & (v < shape)).all(0)]
+        return im[v[0], v[1], v[2]].astype(np.float64), v, [c[0], c[1], c[2]]
+
+    vals, X, cen = problem(g["edge_seeds"][7])          # [19, 71, 79]: 99-voxel corner window on noise
+    ref = fit_oracle.gaussian_fit(vals, X, center=cen, version=4, delta_center=2.5)
+    assert ref["nfev"] >= 1000 and ref["ier"] == 5
+    _, ps, st = _hostfit_qr(hostsim, 4, vals, X, cen, 2.5, [1.5] * 3)
+    assert st[0] >= 1000
+    assert np.abs(ps[1:4] - ref["p"][1:4]).max() > 1e-3
+    for c in g["seeds"][:8]:                            # real spots: same driver agrees to 1e-5
+        vals, X, cen = problem(c)
+        ref = fit_oracle.gaussian_fit(vals, X, center=cen, version=4, delta_center=2.5)
+        assert ref["problem"].cond < 10
+        _, ps, st = _hostfit_qr(hostsim, 4, vals, X, cen, 2.5, [1.5] * 3)
+        assert st[0] == ref["nfev"]
+        assert np.allclose(ps, ref["p"], rtol=1e-5, atol=1e-5)

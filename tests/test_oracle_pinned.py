@@ -110,3 +110,34 @@ def test_oracle_against_live_reference():
     o = fit_oracle.iter_fit(im, s_ref[:, :3].T, version=4)
     assert np.array_equal(_rows(o["ps"]), _rows(f.ps), equal_nan=True)
     assert np.array_equal(o["im_add"], f.im_add)
+
+
+def test_well_posed_statistics(golden_fits):
+    """the cut-off of fit_oracle.comparable_mask is far from what real spots need: isolated and densely
+    overlapping spots have cond(J D^-1) < 30 over the non-zero columns, while the junk seeds of the edge
+    case end on 1e6 .. 1e8-conditioned Jacobians or run into maxfev."""
+    from imageanalysis3_b200.synth import synth
+    g = golden_fits
+    o = fit_oracle.iter_fit(g["im"], g["seeds"].T, version=4)
+    assert o["cond_max"].max() < 10 and o["nfev_max"].max() < 60
+    assert o["well_posed"].all() and o["comparable"].all()
+    assert np.array_equal(o["comparable"], g["v4_comparable"])
+    e = fit_oracle.iter_fit(g["im"], g["edge_seeds"].T, version=4)
+    assert np.array_equal(e["comparable"], g["edge_comparable"])
+    junk = ~e["well_posed"] & np.array(e["success"])
+    assert junk.sum() >= 3 and (e["cond_max"][junk] > 1e5).all()
+    im = synth((24, 96, 96), 220, 31, h_range=(500.0, 3000.0))     # crowded: merged / overlapping spots
+    seeds = seed_oracle.get_seeds_oracle(im, th_seed=200, backend="c")
+    d = fit_oracle.iter_fit(im, seeds.T, version=4)
+    assert len(seeds) > 90 and d["cond_max"].max() < 50 and d["comparable"].all()
+
+
+def test_comparable_mask_taints_window_overlap_components():
+    cen = np.array([[10., 10, 10], [10, 10, 18], [10, 10, 26.5], [10, 40, 40], [2.2, 3, 3]])
+    well = np.array([True, False, True, True, True])
+    # 0 and 2 overlap the ill-posed seed 1 (|d| = 8 <= 2r-1), 3 and 4 are far away
+    assert fit_oracle.comparable_mask(cen, well, 5).tolist() == [False, False, False, True, True]
+    well = np.array([False, True, True, True, True])
+    # taint travels through the chain 0 -> 1 -> 2
+    assert fit_oracle.comparable_mask(cen, well, 5).tolist() == [False, False, False, True, True]
+    assert fit_oracle.comparable_mask(cen[:0], well[:0], 5).shape == (0,)
