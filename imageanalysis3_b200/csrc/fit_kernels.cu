@@ -50,6 +50,44 @@ struct WarpExec {
       if (ov < v || (ov == v && ok < k)) { v = ov; k = ok; }
     }
   }
+  // lane-private "already selected" bits of select10: slot i = this lane's i-th voxel (K <= 2048)
+  struct TakenMask {
+    unsigned long long bits;
+    __device__ __forceinline__ void clear() { bits = 0ull; }
+    __device__ __forceinline__ bool test(int i) const { return (bits >> i) & 1ull; }
+    __device__ __forceinline__ void set(int i) { bits |= 1ull << i; }
+  };
+  // Butterfly reduce-scatter: N per-lane partial sums -> N totals with ~N + 2 log N shuffles instead
+  // of 5 N.  At the step with lane offset O a lane keeps the even (bit clear) or odd (bit set) entry of
+  // every pair and sends the other one to its partner, halving the live array; after 5 steps entry f of
+  // lane l is the total of index 32 f + bitreverse5(l).  Fixed tree order -> deterministic sums.
+  template <int N, int O>
+  __device__ __forceinline__ void rs_step(double* v) const {
+    const bool up = (threadIdx.x & O) != 0;
+#pragma unroll
+    for (int i = 0; i < (N + 1) / 2; ++i) {
+      const double a = v[2 * i];
+      const double b = (2 * i + 1 < N) ? v[2 * i + 1] : 0.0;
+      const double send = up ? a : b;
+      const double keep = up ? b : a;
+      v[i] = keep + __shfl_xor_sync(FULL, send, O);
+    }
+  }
+  template <int N>
+  __device__ __forceinline__ void reduce_store(double (&v)[N], double* out) const {
+    constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2, N5 = (N4 + 1) / 2;
+    rs_step<N, 16>(v);
+    rs_step<N1, 8>(v);
+    rs_step<N2, 4>(v);
+    rs_step<N3, 2>(v);
+    rs_step<N4, 1>(v);
+    const int base = (int)(__brev((unsigned)(threadIdx.x & 31)) >> 27);
+#pragma unroll
+    for (int f = 0; f < N5; ++f) {
+      const int idx = 32 * f + base;
+      if (idx < N) out[idx] = v[f];
+    }
+  }
 };
 
 __device__ __forceinline__ double load_im(const void* im, int dtype, long long idx) {
@@ -67,13 +105,13 @@ template <typename T>
 struct BallVox {
   int m;
   const uint32_t* pk;
-  const float* data;
+  const double* dv;
   __device__ __forceinline__ void get(int k, T& X0, T& X1, T& X2, T& d) const {
     const uint32_t p = pk[k];
     X0 = (T)((int)(p & 63u) - 32);
     X1 = (T)((int)((p >> 6) & 63u) - 32);
     X2 = (T)((int)((p >> 12) & 63u) - 32);
-    d = (T)data[k];
+    d = (T)__double2float_rn(dv[k]);              // self.im = float32(im) (Fitting_v4.py:172)
   }
 };
 
@@ -164,13 +202,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const in
   const long long s = work ? (long long)work[wi] : wi;
   const int K = d.K;
   // per-warp shared layout
-  const size_t per_warp = (sizeof(SpotShared<T>) + 15) / 16 * 16 + (size_t)K * (8 + 8 + 4 + 4);
+  const size_t per_warp = (sizeof(SpotShared<T>) + 15) / 16 * 16 + ((size_t)K * (8 + 4) + 15) / 16 * 16;
   unsigned char* base = smem_raw + per_warp * warp;
   SpotShared<T>& sh = *reinterpret_cast<SpotShared<T>*>(base);
   double* dv = reinterpret_cast<double*>(base + (sizeof(SpotShared<T>) + 15) / 16 * 16);
-  double* tmp = dv + K;
-  float* data = reinterpret_cast<float*>(tmp + K);
-  uint32_t* pk = reinterpret_cast<uint32_t*>(data + K);
+  uint32_t* pk = reinterpret_cast<uint32_t*>(dv + K);
 
   WarpExec ex;
   const double c[3] = {d.centers[3 * s], d.centers[3 * s + 1], d.centers[3 * s + 2]};
@@ -199,7 +235,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const in
       if (mode == 0) v = load_im(d.im, d.im_dtype, idx);
       else { v = d.vol[idx]; if (had_rec) v = d.rec[s * K + k] + v; }   // im_ = im_rec + im_  (:662)
       dv[pos] = v;
-      data[pos] = (float)v;                                            // self.im = float32(im) (:172)
       pk[pos] = pack_vox(dz, dx, dy, k);
     }
     m += __popc(bal);
@@ -220,12 +255,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const in
   }
 
   FitParams fp = d.fp;
-  select10(ex, dv, tmp, m, false, sh.small10);
-  select10(ex, dv, tmp, m, true, sh.large10);
+  select10(ex, dv, m, false, sh.small10);
+  select10(ex, dv, m, true, sh.large10);
   if (lane == 0) initial_guess(fp, sh.small10, sh.large10, d.init_w, sh.x0);
   __syncwarp();
 
-  BallVox<T> vox{m, pk, data};
+  BallVox<T> vox{m, pk, dv};
   run_lm<T>(ex, fp, d.lm, c, origin, vox, sh);
   __shared__ FitResult res_s[WARPS];
   FitResult& res = res_s[warp];
@@ -239,9 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const in
     __shared__ VoxConsts<double> vcd_s[WARPS];
     VoxConsts<double>& vcd = vcd_s[warp];
     if (lane == 0) {
-      ModelConsts mc;
-      model_consts(fp, c, sh.st.x, false, mc);
-      narrow_consts<double>(mc, origin, false, vcd);
+      build_consts<double>(fp, c, origin, sh.st.x, false, vcd);
     }
     __syncwarp();
     for (int pos = lane; pos < m; pos += 32) {
@@ -271,9 +304,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_subtract(FitDev d, const int* __
     const double origin[3] = {(double)ic[0], (double)ic[1], (double)ic[2]};
     double x[NP];
     for (int i = 0; i < NP; ++i) x[i] = d.p_raw[s * NP + i];
-    ModelConsts mc;
-    model_consts(d.fp, c, x, false, mc);
-    narrow_consts<double>(mc, origin, false, vcd);
+    build_consts<double>(d.fp, c, origin, x, false, vcd);
   }
   __syncwarp();
   for (int k = lane; k < d.K; k += 32) {
@@ -320,8 +351,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_generic_fit(GenericFitDev d) {
   FitParams fp = d.fp;
   const double c[3] = {d.centers[3 * b], d.centers[3 * b + 1], d.centers[3 * b + 2]};
   const double origin[3] = {0.0, 0.0, 0.0};
-  select10(ex, d.values + o0, d.tmp + o0, m, false, sh.small10);
-  select10(ex, d.values + o0, d.tmp + o0, m, true, sh.large10);
+  select10_scratch(ex, d.values + o0, d.tmp + o0, m, false, sh.small10);
+  select10_scratch(ex, d.values + o0, d.tmp + o0, m, true, sh.large10);
   if (lane == 0) initial_guess(fp, sh.small10, sh.large10, d.init_w, sh.x0);
   __syncwarp();
   GlobalVox vox{m, d.values + o0, d.coords + 3 * o0};
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_generic_fit(GenericFitDev d) {
 // ------------------------------------------------------------------------------------------
 int fit_smem_bytes(int K, bool fp32) {
   const size_t shs = fp32 ? sizeof(SpotShared<float>) : sizeof(SpotShared<double>);
-  const size_t per_warp = (shs + 15) / 16 * 16 + (size_t)K * (8 + 8 + 4 + 4);
+  const size_t per_warp = (shs + 15) / 16 * 16 + ((size_t)K * (8 + 4) + 15) / 16 * 16;
   return (int)(per_warp * WARPS);
 }
 
@@ -439,9 +470,7 @@ __global__ void k_eval_f0(FitParams fp, const double* p_raw, const double* cente
     double x[NP], c[3] = {center[0], center[1], center[2]};
     for (int i = 0; i < NP; ++i) x[i] = p_raw[i];
     const double origin[3] = {0.0, 0.0, 0.0};
-    ModelConsts mc;
-    model_consts(fp, c, x, false, mc);
-    narrow_consts<double>(mc, origin, false, vc);
+    build_consts<double>(fp, c, origin, x, false, vc);
   }
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;

@@ -17,26 +17,56 @@ template <typename T>
 struct SpotShared {
   LMState st;
   VoxConsts<T> vc;
-  double A[NTRI];
-  double g[NP];
+  double Ag[NTRI + NP];   // J^T J (packed upper triangle) followed by J^T f
   double x0[NP];
   double small10[10], large10[10];
-  double bcast[4];
-  int ibcast[4];
 };
 
+// Executor interface (WarpExec in fit_kernels.cu, SerialExec in tests/hostsim):
+//   static constexpr int W           lanes that share one spot
+//   int lane(); void sync();
+//   double allsum(double), int allsum_int(int), double allmax(double)   -> same value on every lane
+//   void argmin(double& v, int& k)    -> smallest v (lowest k on ties) on every lane
+//   void reduce_store<N>(double (&v)[N], double* out)   out[i] = sum over lanes of v[i] (v is clobbered;
+//                                                        visible to all lanes after the next sync())
+
 // ---- initial guess (GaussianFit.__init__, Fitting_v4.py:174-185) ---------------------------
-// dv[0..m) holds the float64 voxel values in voxel order; tmp[0..m) is scratch of the same size.
+// dv[0..m) holds the float64 voxel values in voxel order.  Selects the 10 smallest (or largest)
+// values in ascending (descending) order; equal values are taken in voxel order, like a stable
+// sort.  Lane l owns voxels l, l+W, l+2W, ...; `taken` is its private bitmask (m <= 32*W... the
+// host executor (W = 1) keeps the mask in a caller-provided array instead).
 template <typename Exec>
-IA3_HD void select10(Exec& ex, const double* dv, double* tmp, int m, bool largest, double* out10) {
+IA3_HD void select10(Exec& ex, const double* dv, int m, bool largest, double* out10) {
+  typename Exec::TakenMask taken;
+  taken.clear();
+  for (int r = 0; r < 10; ++r) {
+    double best = INFINITY;
+    int bk = 0x7fffffff;
+    int slot = 0;
+    for (int k = ex.lane(); k < m; k += Exec::W, ++slot) {
+      if (taken.test(slot)) continue;
+      const double v = largest ? -dv[k] : dv[k];
+      if (v < best) { best = v; bk = k; }   // ascending k inside a lane: first minimum kept
+    }
+    ex.argmin(best, bk);
+    if (bk != 0x7fffffff && (bk % Exec::W) == ex.lane()) taken.set(bk / Exec::W);
+    if (ex.lane() == 0) out10[r] = largest ? -best : best;
+  }
+  ex.sync();
+}
+
+// Same selection for windows of any size, with the "taken" marks in a scratch array of m doubles
+// (standalone GaussianFit on arbitrary voxel lists).
+template <typename Exec>
+IA3_HD void select10_scratch(Exec& ex, const double* dv, double* tmp, int m, bool largest, double* out10) {
   for (int k = ex.lane(); k < m; k += Exec::W) tmp[k] = largest ? -dv[k] : dv[k];
   ex.sync();
   for (int r = 0; r < 10; ++r) {
     double best = INFINITY;
     int bk = 0x7fffffff;
     for (int k = ex.lane(); k < m; k += Exec::W) {
-      double v = tmp[k];
-      if (v < best) { best = v; bk = k; }   // ascending k inside a lane: first minimum kept
+      const double v = tmp[k];
+      if (v < best) { best = v; bk = k; }
     }
     ex.argmin(best, bk);
     if (ex.lane() == 0) { out10[r] = largest ? -best : best; if (bk != 0x7fffffff) tmp[bk] = INFINITY; }
@@ -133,13 +163,12 @@ IA3_HD double pass_residual(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, do
   return big * sqrt(s1 + (s2 / big) / big);
 }
 
+// Ag_out[0..55) = J^T J (packed upper triangle), Ag_out[55..65) = J^T f
 template <typename T, typename Exec, typename Vox>
-IA3_HD void pass_jacobian(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* A_out, double* g_out) {
-  double A[NTRI], g[NP];
+IA3_HD void pass_jacobian(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* Ag_out) {
+  double acc[NTRI + NP];
 #pragma unroll
-  for (int i = 0; i < NTRI; ++i) A[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < NP; ++i) g[i] = 0.0;
+  for (int i = 0; i < NTRI + NP; ++i) acc[i] = 0.0;
   for (int k = ex.lane(); k < vox.m; k += Exec::W) {
     T X0, X1, X2, d, res;
     float J[NP];
@@ -150,15 +179,12 @@ IA3_HD void pass_jacobian(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, doub
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       const double ji = (double)J[i];
-      g[i] += ji * r;
+      acc[NTRI + i] += ji * r;
 #pragma unroll
-      for (int j = i; j < NP; ++j) { A[idx] += ji * (double)J[j]; ++idx; }
+      for (int j = i; j < NP; ++j) { acc[idx] += ji * (double)J[j]; ++idx; }
     }
   }
-#pragma unroll
-  for (int i = 0; i < NTRI; ++i) { double s = ex.allsum(A[i]); if (ex.lane() == 0) A_out[i] = s; }
-#pragma unroll
-  for (int i = 0; i < NP; ++i) { double s = ex.allsum(g[i]); if (ex.lane() == 0) g_out[i] = s; }
+  ex.template reduce_store<NTRI + NP>(acc, Ag_out);
 }
 
 struct FitResult {
@@ -167,48 +193,36 @@ struct FitResult {
   int nfev, njev, info;
 };
 
-// Runs leastsq from sh.x0.  Every lane must call this; results are valid on lane 0 after return
-// (and in sh.st.x for everybody after the final sync).
+// Runs leastsq from sh.x0.  Every lane must call this; results are in sh.st (shared) after return.
 template <typename T, typename Exec, typename Vox>
 IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen_est,
                    const double* origin, const Vox& vox, SpotShared<T>& sh) {
   LMState& st = sh.st;
   // f(x0)
   if (ex.lane() == 0) {
-    ModelConsts mc;
-    model_consts(fp, cen_est, sh.x0, false, mc);
-    narrow_consts<T>(mc, origin, false, sh.vc);
+    build_consts<T>(fp, cen_est, origin, sh.x0, false, sh.vc);
   }
   ex.sync();
-  double fn0 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
-  if (ex.lane() == 0) lm_init(st, sh.x0, fn0);
-  ex.sync();
+  const double fn0 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
+  lm_init(ex, st, sh.x0, fn0);
   for (;;) {
     // Jacobian at st.x
     if (ex.lane() == 0) {
-      ModelConsts mc;
-      model_consts(fp, cen_est, st.x, true, mc);
-      narrow_consts<T>(mc, origin, true, sh.vc);
+      build_consts<T>(fp, cen_est, origin, st.x, true, sh.vc);
     }
     ex.sync();
-    pass_jacobian<T>(ex, sh.vc, vox, sh.A, sh.g);
+    pass_jacobian<T>(ex, sh.vc, vox, sh.Ag);
     ex.sync();
-    if (ex.lane() == 0) sh.ibcast[0] = lm_outer(st, cfg, sh.A, sh.g) ? 1 : 0;
-    ex.sync();
-    if (!sh.ibcast[0]) break;
+    if (!lm_outer(ex, st, cfg, sh.Ag, sh.Ag + NTRI)) break;
     int action;
     for (;;) {
+      lm_propose(ex, st);
       if (ex.lane() == 0) {
-        lm_propose(st);
-        ModelConsts mc;
-        model_consts(fp, cen_est, st.xt, false, mc);
-        narrow_consts<T>(mc, origin, false, sh.vc);
+        build_consts<T>(fp, cen_est, origin, st.xt, false, sh.vc);
       }
       ex.sync();
-      double fn1 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
-      if (ex.lane() == 0) sh.ibcast[1] = lm_judge(st, cfg, fn1);
-      ex.sync();
-      action = sh.ibcast[1];
+      const double fn1 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
+      action = lm_judge(ex, st, cfg, fn1);
       if (action != LM_RETRY) break;
     }
     if (action == LM_DONE) break;
@@ -222,9 +236,7 @@ template <typename T, typename Exec, typename Vox>
 IA3_HD void finish_fit(Exec& ex, const FitParams& fp, const double* cen_est, const double* origin,
                        const Vox& vox, SpotShared<T>& sh, FitResult* out /*lane 0 writes*/) {
   if (ex.lane() == 0) {
-    ModelConsts mc;
-    model_consts(fp, cen_est, sh.st.x, false, mc);
-    narrow_consts<T>(mc, origin, false, sh.vc);
+    build_consts<T>(fp, cen_est, origin, sh.st.x, false, sh.vc);
   }
   ex.sync();
   double sa = 0.0;

@@ -43,29 +43,33 @@ struct ModelConsts {
   double jpen[3];        // v3: +-weight_sigma added to f6..f8
 };
 
+// One out-of-line copy of the FP64 exp for the per-parameter (scalar) code: model_consts alone has
+// ~20 call sites and an inlined exp is ~60 instructions.
+IA3_HDN double exp_s(double v) { return exp(v); }
+
 IA3_HD double v4_sigmoid_guarded(double a, double lo_val, double hi_val, double num, double off) {
   // value = num/(1+exp(a)) + off with the reference's saturation guards at |a| >= log(DBL_MAX)
   const double LOGMAX = 709.782712893384;  // np.log(np.finfo(np.float64).max)
   if (a >= LOGMAX) return lo_val;
   if (a <= -LOGMAX) return hi_val;
-  return num / (1.0 + exp(a)) + off;
+  return num / (1.0 + exp_s(a)) + off;
 }
 
 IA3_HD double norm_w_fn(double w, double minw, double maxw) {
   // Fitting_v4.py:369-375 / Fitting_v3.py:232-238
   if (w > 0) {
-    double e = exp(-w);
+    double e = exp_s(-w);
     double d = maxw * e + minw;
     return 0.5 * (maxw - minw) * e / (d * d);
   } else {
-    double e = exp(w);
+    double e = exp_s(w);
     double d = minw * e + maxw;
     return 0.5 * (maxw - minw) * e / (d * d);
   }
 }
 
 // want_jac = false skips the Jacobian-only constants.
-IA3_HDN void model_consts(const FitParams& fp, const double* cen_est, const double* x, bool want_jac,
+IA3_HD void model_consts(const FitParams& fp, const double* cen_est, const double* x, bool want_jac,
                          ModelConsts& mc) {
   const double bk = x[0], h = x[1], xp = x[2], yp = x[3], zp = x[4];
   const double w1 = x[5], w2 = x[6], w3 = x[7], pp = x[8], tp = x[9];
@@ -84,15 +88,15 @@ IA3_HDN void model_consts(const FitParams& fp, const double* cen_est, const doub
     for (int i = 0; i < 3; ++i) {
       if (raw[i] >= LOGMAX) mc.c[i] = -d + cen_est[i];
       else if (raw[i] <= -LOGMAX) mc.c[i] = d + cen_est[i];
-      else mc.c[i] = 2.0 * d / (1.0 + exp(raw[i])) - d + cen_est[i];
+      else mc.c[i] = 2.0 * d / (1.0 + exp_s(raw[i])) - d + cen_est[i];
     }
   } else {
-    t = 2.0 / (1.0 + exp(tp)) - 1.0;
-    p = 2.0 / (1.0 + exp(pp)) - 1.0;
-    ws1 = dws / (1.0 + exp(w1)) + minw;
-    ws2 = dws / (1.0 + exp(w2)) + minw;
-    ws3 = dws / (1.0 + exp(w3)) + minw;
-    const double e0 = exp(-xp), e1 = exp(-yp), e2 = exp(-zp);
+    t = 2.0 / (1.0 + exp_s(tp)) - 1.0;
+    p = 2.0 / (1.0 + exp_s(pp)) - 1.0;
+    ws1 = dws / (1.0 + exp_s(w1)) + minw;
+    ws2 = dws / (1.0 + exp_s(w2)) + minw;
+    ws3 = dws / (1.0 + exp_s(w3)) + minw;
+    const double e0 = exp_s(-xp), e1 = exp_s(-yp), e2 = exp_s(-zp);
     mc.c[0] = 2.0 * d * e0 / (1.0 + e0) - d + cen_est[0];
     mc.c[1] = 2.0 * d * e1 / (1.0 + e1) - d + cen_est[1];
     mc.c[2] = 2.0 * d * e1 / (1.0 + e2) - d + cen_est[2];   // Fitting_v3.py:86 (sic)
@@ -109,9 +113,9 @@ IA3_HDN void model_consts(const FitParams& fp, const double* cen_est, const doub
   mc.h = h;
   if (v4) {
     double bkc = bk < -709.78 ? -709.78 : (bk > 709.78 ? 709.78 : bk);  // np.clip, :287 (NaN passes through)
-    mc.ebk_f = exp(bkc);
+    mc.ebk_f = exp_s(bkc);
   } else {
-    mc.ebk_f = exp(bk);
+    mc.ebk_f = exp_s(bk);
   }
   mc.pen = 0.0;
   if (!v4 && fp.weight_sigma > 0) {
@@ -119,16 +123,16 @@ IA3_HDN void model_consts(const FitParams& fp, const double* cen_est, const doub
     mc.pen = fp.weight_sigma * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
   }
   if (!want_jac) return;
-  mc.ebk_j = exp(bk);
+  mc.ebk_j = exp_s(bk);
   {
-    const double ex = exp(-fabs(xp)), ey = exp(-fabs(yp)), ez = exp(-fabs(zp));
+    const double ex = exp_s(-fabs(xp)), ey = exp_s(-fabs(yp)), ez = exp_s(-fabs(zp));
     mc.ncen[0] = -d * ex / ((1 + ex) * (1 + ex));
     mc.ncen[1] = -d * ey / ((1 + ey) * (1 + ey));
     mc.ncen[2] = -d * ez / ((1 + ez) * (1 + ez));
   }
   const double nw1 = norm_w_fn(w1, minw, maxw), nw2 = norm_w_fn(w2, minw, maxw), nw3 = norm_w_fn(w3, minw, maxw);
-  const double e_p = exp(-fabs(pp) / 2), norm_p = e_p / (1 + e_p * e_p);
-  const double e_t = exp(-fabs(tp) / 2), norm_t = e_t / (1 + e_t * e_t);
+  const double e_p = exp_s(-fabs(pp) / 2), norm_p = e_p / (1 + e_p * e_p);
+  const double e_t = exp_s(-fabs(tp) / 2), norm_t = e_t / (1 + e_t * e_t);
   // order of the six monomials: xt2, yt2, zt2, xtyt, xtzt, ytzt
   // f6 (Fitting_v4.py:355)
   mc.a6[0] = -pc2 * tc2 * nw1; mc.a6[1] = -pc2 * t2 * nw1; mc.a6[2] = -p2 * nw1;
@@ -180,6 +184,16 @@ IA3_HD void narrow_consts(const ModelConsts& mc, const double* origin, bool want
     vc.a6[i] = (T)mc.a6[i]; vc.a7[i] = (T)mc.a7[i]; vc.a8[i] = (T)mc.a8[i];
     vc.a9[i] = (T)mc.a9[i]; vc.a10[i] = (T)mc.a10[i];
   }
+}
+
+// model_consts + narrow_consts as ONE out-of-line routine writing straight into the (shared-memory)
+// per-voxel constants: the intermediate ModelConsts then lives in registers, not on the stack.
+template <typename T>
+IA3_HDN void build_consts(const FitParams& fp, const double* cen_est, const double* origin, const double* x,
+                          bool want_jac, VoxConsts<T>& vc) {
+  ModelConsts mc;
+  model_consts(fp, cen_est, x, want_jac, mc);
+  narrow_consts<T>(mc, origin, want_jac, vc);
 }
 
 template <typename T> IA3_HD T exp_t(T v);
@@ -234,13 +248,13 @@ IA3_HDN void natural_params(const FitParams& fp, const double* cen_est, const do
     t = v4_sigmoid_guarded(x[9], -1.0, 1.0, 2.0, -1.0);
     p = v4_sigmoid_guarded(x[8], -1.0, 1.0, 2.0, -1.0);
   } else {
-    for (int i = 0; i < 3; ++i) ws[i] = dws / (1.0 + exp(x[5 + i])) + minw;
-    t = 2.0 / (1.0 + exp(x[9])) - 1.0;
-    p = 2.0 / (1.0 + exp(x[8])) - 1.0;
+    for (int i = 0; i < 3; ++i) ws[i] = dws / (1.0 + exp_s(x[5 + i])) + minw;
+    t = 2.0 / (1.0 + exp_s(x[9])) - 1.0;
+    p = 2.0 / (1.0 + exp_s(x[8])) - 1.0;
   }
-  out10[0] = exp(x[1]);
+  out10[0] = exp_s(x[1]);
   out10[1] = mc.c[0]; out10[2] = mc.c[1]; out10[3] = mc.c[2];
-  out10[4] = exp(x[0]);
+  out10[4] = exp_s(x[0]);
   out10[5] = sqrt(ws[0]); out10[6] = sqrt(ws[1]); out10[7] = sqrt(ws[2]);
   out10[8] = t; out10[9] = p;
 }

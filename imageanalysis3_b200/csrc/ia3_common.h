@@ -7,7 +7,7 @@
 
 #if defined(__CUDACC__)
 #define IA3_HD __host__ __device__ __forceinline__
-#define IA3_HDN __host__ __device__ inline       /* big scalar routines: let the compiler decide */
+#define IA3_HDN __host__ __device__ __noinline__ inline  /* big scalar routines: one copy each, the fit kernel must fit the I-cache */
 #define IA3_D __device__ __forceinline__
 #else
 #define IA3_HD inline

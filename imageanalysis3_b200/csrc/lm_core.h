@@ -5,15 +5,25 @@
 // (External/Fitting_v4.py:388, External/Fitting_v3.py:250), i.e. MINPACK lmder with
 // ftol = xtol = 1.49012e-8, gtol = 0, factor = 100, mode = 1.  SURVEY.md App. G / B.8 shows
 // that the result is only reproducible if the *trust-region logic* is lmder's, so this file
-// restates lmder / lmpar / qrsolv (public-domain MINPACK, Argonne 1980) step by step.  The one
-// deliberate change: lmder's Householder QR of the m x 10 Jacobian (qrfac with column
-// pivoting) is replaced by a pivoted Cholesky factorisation of the FP64 10x10 matrix J^T J
-// with qrfac's pivot rule (largest remaining column norm, first index wins ties).  R^T R =
-// P^T J^T J P, so R agrees with qrfac's R up to row signs, which cancel everywhere R is used
-// together with qtf = R^-T P^T J^T f.
+// restates lmder / lmpar (public-domain MINPACK, Argonne 1980) step by step.  Two deliberate
+// changes, both in how the small linear algebra is carried out, not in what is computed:
+//   * lmder's Householder QR of the m x 10 Jacobian (qrfac with column pivoting) is replaced
+//     by a pivoted Cholesky factorisation of the FP64 10x10 matrix J^T J with qrfac's pivot
+//     rule (largest remaining column norm, first index wins ties).  R^T R = P^T J^T J P, so R
+//     agrees with qrfac's R up to row signs, which cancel everywhere R is used together with
+//     qtf = R^-T P^T J^T f.
+//   * lmpar's qrsolv (55 Givens rotations eliminating sqrt(par)*D against R) is replaced by a
+//     Cholesky factorisation of R^T R + par*D^2: the same upper-triangular S up to row signs
+//     (S^T S = R^T R + par D^2), the same step x = (S^T S)^-1 R^T qtf, a tenth of the
+//     sequential depth.
 //
-// Everything here is scalar FP64 on a 10-vector / 10x10 matrix and is executed by ONE lane of
-// the warp that owns the spot (state lives in shared memory).  No per-voxel work.
+// Everything here is FP64 on 10-vectors / 10x10 matrices held in the spot's shared-memory
+// state.  The routines are written for an executor `Ex` (fit_spot.h): the O(n^2)/O(n^3) loops
+// are strided over the lanes of the warp that owns the spot (`for (k = ex.lane(); ...; k +=
+// Ex::W)`), short reductions over 10 numbers are done redundantly by every lane from shared
+// memory (so all lanes hold bit-identical scalars and take the same branches), and
+// `ex.sync()` separates dependent phases.  With the one-lane host executor (tests/hostsim)
+// the same code runs serially.  No per-voxel work here.
 #pragma once
 #include "ia3_common.h"
 
@@ -31,8 +41,11 @@ struct LMState {
   double diag[NP];     // variable scaling
   double acn[NP];      // column norms of J                      (qrfac acnorm / lmder wa2)
   double qtf[NP];      // first n entries of Q^T f
-  double R[NP][NP];    // upper triangle: R; strict lower triangle: scratch for qrsolv's S^T
-  double sdiag[NP];
+  double R[NP][NP];    // upper triangle: R (pivoted order)
+  double B0[NTRI];     // R^T R, packed upper triangle (pivoted order)
+  double S[NTRI];      // Cholesky factor of R^T R + par D^2, packed upper triangle
+  double rq[NP];       // R^T qtf (pivoted order)
+  double rd[NP], gp[NP], y[NP];
   double w1[NP], w2[NP], w3[NP];
   int ipvt[NP];
   double fnorm, fnorm1, xnorm, delta, par, gnorm, pnorm;
@@ -45,157 +58,173 @@ IA3_HD double enorm_n(const double* v, int n) {
   return sqrt(s);
 }
 
-// Pivoted Cholesky of the packed symmetric A (55 entries) with MINPACK qrfac's pivoting.
-// Outputs st.R (upper), st.ipvt, st.acn and st.qtf = R^-T (g permuted).
-IA3_HDN void lm_factor(LMState& st, const double* A, const double* g) {
-  double M[NP][NP];
-  double rd[NP];  // remaining squared norms (Schur complement diagonal)
-  double gp[NP];
-  for (int i = 0; i < NP; ++i) {
-    for (int j = i; j < NP; ++j) { double a = A[tri(i, j)]; M[i][j] = a; M[j][i] = a; }
-    st.acn[i] = sqrt(A[tri(i, i)]);
-    rd[i] = A[tri(i, i)];
-    st.ipvt[i] = i;
-    gp[i] = g[i];
-    for (int j = 0; j < NP; ++j) st.R[i][j] = 0.0;
-  }
-  // M is permuted symmetrically in place as pivots are chosen.
-  for (int j = 0; j < NP; ++j) {
-    int kmax = j;
-    for (int k = j + 1; k < NP; ++k) if (rd[k] > rd[kmax]) kmax = k;
-    if (kmax != j) {
-      for (int i = 0; i < NP; ++i) { double t = M[i][j]; M[i][j] = M[i][kmax]; M[i][kmax] = t; }
-      for (int i = 0; i < NP; ++i) { double t = M[j][i]; M[j][i] = M[kmax][i]; M[kmax][i] = t; }
-      for (int i = 0; i < j; ++i) { double t = st.R[i][j]; st.R[i][j] = st.R[i][kmax]; st.R[i][kmax] = t; }
-      { double t = rd[j]; rd[j] = rd[kmax]; rd[kmax] = t; }
-      { double t = gp[j]; gp[j] = gp[kmax]; gp[kmax] = t; }
-      { int t = st.ipvt[j]; st.ipvt[j] = st.ipvt[kmax]; st.ipvt[kmax] = t; }
-    }
-    double d = rd[j];
-    if (!(d > 0.0)) {
-      // exactly dependent / zero column: qrfac leaves rdiag = 0 and lmpar then treats this and
-      // all later columns as singular.
-      st.R[j][j] = 0.0;
-      for (int k = j + 1; k < NP; ++k) st.R[j][k] = 0.0;
-      continue;
-    }
-    double rjj = sqrt(d);
-    st.R[j][j] = rjj;
-    for (int k = j + 1; k < NP; ++k) {
-      double s = M[j][k];
-      for (int i = 0; i < j; ++i) s -= st.R[i][j] * st.R[i][k];
-      double r = s / rjj;
-      st.R[j][k] = r;
-      rd[k] -= r * r;
+// B0 = R^T R and rq = R^T qtf (both in pivoted order) from st.R / st.qtf
+template <typename Ex>
+IA3_HDN void lm_post_factor(Ex& ex, LMState& st) {
+  for (int e = ex.lane(); e < NTRI + NP; e += Ex::W) {
+    if (e < NTRI) {
+      int a = 0, rem = e;
+      while (rem >= NP - a) { rem -= NP - a; ++a; }
+      const int b = a + rem;                     // entry (a, b), a <= b
+      double s = 0.0;
+      for (int i = 0; i <= a; ++i) s += st.R[i][a] * st.R[i][b];
+      st.B0[e] = s;
+    } else {
+      const int j = e - NTRI;
+      double s = 0.0;
+      for (int i = 0; i <= j; ++i) s += st.R[i][j] * st.qtf[i];
+      st.rq[j] = s;
     }
   }
-  // qtf = R^-T gp  (forward substitution; rows with zero pivot give 0)
-  for (int j = 0; j < NP; ++j) {
-    double s = gp[j];
-    for (int i = 0; i < j; ++i) s -= st.R[i][j] * st.qtf[i];
-    st.qtf[j] = (st.R[j][j] != 0.0) ? s / st.R[j][j] : 0.0;
-  }
+  ex.sync();
 }
 
-// MINPACK qrsolv: solve min |R P^T x - qtb|^2 + |D x|^2 given d = sqrt(par)*diag.
-IA3_HDN void lm_qrsolv(LMState& st, const double* d, double* x /*out, unpermuted*/, double* wa) {
-  double (*r)[NP] = st.R;
-  double xsave[NP];
-  for (int j = 0; j < NP; ++j) {
-    for (int i = j; i < NP; ++i) r[i][j] = r[j][i];
-    xsave[j] = r[j][j];
-    wa[j] = st.qtf[j];
+// Pivoted Cholesky of the packed symmetric A (55 entries) with MINPACK qrfac's pivoting.
+// Outputs st.R (upper), st.ipvt, st.acn, st.qtf = R^-T (g permuted), st.B0 = R^T R, st.rq = R^T qtf.
+template <typename Ex>
+IA3_HDN void lm_factor(Ex& ex, LMState& st, const double* A, const double* g) {
+  const int ln = ex.lane();
+  for (int i = ln; i < NP; i += Ex::W) {
+    const double a = A[tri(i, i)];
+    st.acn[i] = sqrt(a);
+    st.rd[i] = a;              // remaining squared norms (Schur complement diagonal)
+    st.ipvt[i] = i;
+    st.gp[i] = g[i];
+    for (int j = 0; j < NP; ++j) st.R[i][j] = 0.0;
   }
+  ex.sync();
   for (int j = 0; j < NP; ++j) {
-    int l = st.ipvt[j];
-    if (d[l] != 0.0) {
-      for (int k = j; k < NP; ++k) st.sdiag[k] = 0.0;
-      st.sdiag[j] = d[l];
-      double qtbpj = 0.0;
-      for (int k = j; k < NP; ++k) {
-        if (st.sdiag[k] == 0.0) continue;
-        double c, s;
-        if (fabs(r[k][k]) < fabs(st.sdiag[k])) {
-          double cotan = r[k][k] / st.sdiag[k];
-          s = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
-          c = s * cotan;
-        } else {
-          double tn = st.sdiag[k] / r[k][k];
-          c = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
-          s = c * tn;
-        }
-        r[k][k] = c * r[k][k] + s * st.sdiag[k];
-        double temp = c * wa[k] + s * qtbpj;
-        qtbpj = -s * wa[k] + c * qtbpj;
-        wa[k] = temp;
-        for (int i = k + 1; i < NP; ++i) {
-          double t2 = c * r[i][k] + s * st.sdiag[i];
-          st.sdiag[i] = -s * r[i][k] + c * st.sdiag[i];
-          r[i][k] = t2;
-        }
+    int kmax = j;
+    for (int k = j + 1; k < NP; ++k) if (st.rd[k] > st.rd[kmax]) kmax = k;
+    ex.sync();                                   // everybody has read rd[] before it is permuted
+    if (kmax != j) {
+      for (int i = ln; i < j; i += Ex::W) { const double t = st.R[i][j]; st.R[i][j] = st.R[i][kmax]; st.R[i][kmax] = t; }
+      if (ln == 0) {
+        { const double t = st.rd[j]; st.rd[j] = st.rd[kmax]; st.rd[kmax] = t; }
+        { const double t = st.gp[j]; st.gp[j] = st.gp[kmax]; st.gp[kmax] = t; }
+        { const int t = st.ipvt[j]; st.ipvt[j] = st.ipvt[kmax]; st.ipvt[kmax] = t; }
       }
+      ex.sync();
     }
-    st.sdiag[j] = r[j][j];
-    r[j][j] = xsave[j];
+    const double d = st.rd[j];
+    if (!(d > 0.0)) {
+      // exactly dependent / zero column: qrfac leaves rdiag = 0 and lmpar then treats this and
+      // all later columns as singular (row j of R stays zero).
+      continue;
+    }
+    const double rjj = sqrt(d);
+    const int pj = st.ipvt[j];
+    for (int k = j + ln; k < NP; k += Ex::W) {
+      if (k == j) { st.R[j][j] = rjj; continue; }
+      const int pk = st.ipvt[k];
+      double s = A[pj < pk ? tri(pj, pk) : tri(pk, pj)];
+      for (int i = 0; i < j; ++i) s -= st.R[i][j] * st.R[i][k];
+      const double r = s / rjj;
+      st.R[j][k] = r;
+      st.rd[k] -= r * r;
+    }
+    ex.sync();
   }
-  int nsing = NP;
+  // qtf = R^-T gp (forward substitution in axpy form; rows with zero pivot give 0)
+  for (int k = ln; k < NP; k += Ex::W) st.w1[k] = st.gp[k];
+  ex.sync();
   for (int j = 0; j < NP; ++j) {
-    if (st.sdiag[j] == 0.0 && nsing == NP) nsing = j;
-    if (nsing < NP) wa[j] = 0.0;
+    const double rjj = st.R[j][j];
+    const double q = (rjj != 0.0) ? st.w1[j] / rjj : 0.0;
+    if (ln == 0) st.qtf[j] = q;
+    for (int k = j + 1 + ln; k < NP; k += Ex::W) st.w1[k] -= st.R[j][k] * q;
+    ex.sync();
   }
-  for (int k = 0; k < nsing; ++k) {
-    int j = nsing - 1 - k;
-    double sum = 0.0;
-    for (int i = j + 1; i < nsing; ++i) sum += r[i][j] * wa[i];
-    wa[j] = (wa[j] - sum) / st.sdiag[j];
+  lm_post_factor(ex, st);
+}
+
+// Solve min |R P^T x - qtf|^2 + par |D x|^2 (MINPACK qrsolv's job): S = chol(R^T R + par D^2),
+// z = S^-1 S^-T rq, x[ipvt[j]] = z[j].  Leaves S in st.S; x in xout (unpermuted); uses st.w3, st.y.
+template <typename Ex>
+IA3_HDN void lm_damped_solve(Ex& ex, LMState& st, double par, double* xout) {
+  const int ln = ex.lane();
+  // left-looking Cholesky: at step j every lane forms the pivot itself, lane k-j the entry (j, k)
+  for (int j = 0; j < NP; ++j) {
+    const double dj = st.diag[st.ipvt[j]];
+    double d = st.B0[tri(j, j)] + par * (dj * dj);
+    for (int i = 0; i < j; ++i) { const double v = st.S[tri(i, j)]; d -= v * v; }
+    const double sjj = (d > 0.0) ? sqrt(d) : 0.0;
+    for (int k = j + ln; k < NP; k += Ex::W) {
+      if (k == j) { st.S[tri(j, j)] = sjj; continue; }
+      double v = st.B0[tri(j, k)];
+      for (int i = 0; i < j; ++i) v -= st.S[tri(i, j)] * st.S[tri(i, k)];
+      st.S[tri(j, k)] = (sjj != 0.0) ? v / sjj : 0.0;
+    }
+    ex.sync();
   }
-  for (int j = 0; j < NP; ++j) x[st.ipvt[j]] = wa[j];
+  // forward: S^T y = rq  (axpy form)
+  for (int k = ln; k < NP; k += Ex::W) st.w3[k] = st.rq[k];
+  ex.sync();
+  for (int j = 0; j < NP; ++j) {
+    const double sjj = st.S[tri(j, j)];
+    const double y = (sjj != 0.0) ? st.w3[j] / sjj : 0.0;
+    if (ln == 0) st.y[j] = y;
+    for (int k = j + 1 + ln; k < NP; k += Ex::W) st.w3[k] -= st.S[tri(j, k)] * y;
+    ex.sync();
+  }
+  // backward: S z = y
+  for (int j = NP - 1; j >= 0; --j) {
+    const double sjj = st.S[tri(j, j)];
+    const double z = (sjj != 0.0) ? st.y[j] / sjj : 0.0;
+    if (ln == 0) xout[st.ipvt[j]] = z;
+    for (int i = ln; i < j; i += Ex::W) st.y[i] -= st.S[tri(i, j)] * z;
+    ex.sync();
+  }
 }
 
 // MINPACK lmpar: on return st.par is the LM parameter and xout the (positive-sign) step.
-IA3_HDN void lm_lmpar(LMState& st, double* xout) {
+template <typename Ex>
+IA3_HDN void lm_lmpar(Ex& ex, LMState& st, double* xout) {
   const double dwarf = DBL_MIN;
+  const int ln = ex.lane();
   double* wa1 = st.w1;
   double* wa2 = st.w2;
   double (*r)[NP] = st.R;
   const double delta = st.delta;
   int nsing = NP;
-  for (int j = 0; j < NP; ++j) {
-    wa1[j] = st.qtf[j];
-    if (r[j][j] == 0.0 && nsing == NP) nsing = j;
-    if (nsing < NP) wa1[j] = 0.0;
+  for (int j = 0; j < NP; ++j) if (r[j][j] == 0.0 && nsing == NP) nsing = j;
+  for (int j = ln; j < NP; j += Ex::W) {
+    wa1[j] = (j < nsing) ? st.qtf[j] : 0.0;
+    if (j >= nsing) xout[st.ipvt[j]] = 0.0;
   }
+  ex.sync();
+  // Gauss-Newton direction: back substitution with the non-singular leading block of R
   for (int k = 0; k < nsing; ++k) {
-    int j = nsing - 1 - k;
-    wa1[j] = wa1[j] / r[j][j];
-    double temp = wa1[j];
-    for (int i = 0; i < j; ++i) wa1[i] -= r[i][j] * temp;
+    const int j = nsing - 1 - k;
+    const double temp = wa1[j] / r[j][j];
+    if (ln == 0) xout[st.ipvt[j]] = temp;
+    for (int i = ln; i < j; i += Ex::W) wa1[i] -= r[i][j] * temp;
+    ex.sync();
   }
-  for (int j = 0; j < NP; ++j) xout[st.ipvt[j]] = wa1[j];
-
+  for (int j = ln; j < NP; j += Ex::W) wa2[j] = st.diag[j] * xout[j];
+  ex.sync();
   int iter = 0;
-  for (int j = 0; j < NP; ++j) wa2[j] = st.diag[j] * xout[j];
   double dxnorm = enorm_n(wa2, NP);
   double fp = dxnorm - delta;
-  if (fp <= 0.1 * delta) { st.par = 0.0; return; }
+  if (fp <= 0.1 * delta) { if (ln == 0) st.par = 0.0; ex.sync(); return; }
 
   double parl = 0.0;
   if (nsing >= NP) {
-    for (int j = 0; j < NP; ++j) { int l = st.ipvt[j]; wa1[j] = st.diag[l] * (wa2[l] / dxnorm); }
-    for (int j = 0; j < NP; ++j) {
-      double sum = 0.0;
-      for (int i = 0; i < j; ++i) sum += r[i][j] * wa1[i];
-      wa1[j] = (wa1[j] - sum) / r[j][j];
+    for (int j = ln; j < NP; j += Ex::W) { const int l = st.ipvt[j]; wa1[j] = st.diag[l] * (wa2[l] / dxnorm); }
+    ex.sync();
+    double n2 = 0.0;
+    for (int j = 0; j < NP; ++j) {               // R^T w = wa1, axpy form; only |w| is needed
+      const double t = wa1[j] / r[j][j];
+      n2 += t * t;
+      for (int k = j + 1 + ln; k < NP; k += Ex::W) wa1[k] -= r[j][k] * t;
+      ex.sync();
     }
-    double temp = enorm_n(wa1, NP);
+    const double temp = sqrt(n2);
     parl = ((fp / delta) / temp) / temp;
   }
-  for (int j = 0; j < NP; ++j) {
-    double sum = 0.0;
-    for (int i = 0; i <= j; ++i) sum += r[i][j] * st.qtf[i];
-    wa1[j] = sum / st.diag[st.ipvt[j]];
-  }
-  double gnorm = enorm_n(wa1, NP);
+  double g2 = 0.0;
+  for (int j = 0; j < NP; ++j) { const double v = st.rq[j] / st.diag[st.ipvt[j]]; g2 += v * v; }
+  const double gnorm = sqrt(g2);
   double paru = gnorm / delta;
   if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
 
@@ -207,131 +236,185 @@ IA3_HDN void lm_lmpar(LMState& st, double* xout) {
   for (;;) {
     ++iter;
     if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
-    double temp = sqrt(par);
-    for (int j = 0; j < NP; ++j) wa1[j] = temp * st.diag[j];
-    lm_qrsolv(st, wa1, xout, st.w3);
-    for (int j = 0; j < NP; ++j) wa2[j] = st.diag[j] * xout[j];
+    ex.sync();
+    lm_damped_solve(ex, st, par, xout);
+    for (int j = ln; j < NP; j += Ex::W) wa2[j] = st.diag[j] * xout[j];
+    ex.sync();
     dxnorm = enorm_n(wa2, NP);
-    temp = fp;
+    double temp = fp;
     fp = dxnorm - delta;
     if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-    for (int j = 0; j < NP; ++j) { int l = st.ipvt[j]; wa1[j] = st.diag[l] * (wa2[l] / dxnorm); }
-    for (int j = 0; j < NP; ++j) {
-      wa1[j] = wa1[j] / st.sdiag[j];
-      double t2 = wa1[j];
-      for (int i = j + 1; i < NP; ++i) wa1[i] -= r[i][j] * t2;
+    for (int j = ln; j < NP; j += Ex::W) { const int l = st.ipvt[j]; wa1[j] = st.diag[l] * (wa2[l] / dxnorm); }
+    ex.sync();
+    double n2 = 0.0;
+    for (int j = 0; j < NP; ++j) {               // S^T w = wa1, axpy form; only |w| is needed
+      const double t = wa1[j] / st.S[tri(j, j)];
+      n2 += t * t;
+      for (int k = j + 1 + ln; k < NP; k += Ex::W) wa1[k] -= st.S[tri(j, k)] * t;
+      ex.sync();
     }
-    temp = enorm_n(wa1, NP);
-    double parc = ((fp / delta) / temp) / temp;
+    temp = sqrt(n2);
+    const double parc = ((fp / delta) / temp) / temp;
     if (fp > 0.0) parl = fmax(parl, par);
     if (fp < 0.0) paru = fmin(paru, par);
     par = fmax(parl, par + parc);
   }
-  st.par = par;
+  ex.sync();
+  if (ln == 0) st.par = par;
+  ex.sync();
 }
 
 // ---- lmder split into the three places where the warp has to evaluate the model ----------
+// Scalars of LMState are written by every lane with the same value (benign), arrays by the
+// lanes that own the elements.
 
-IA3_HD void lm_init(LMState& st, const double* x0, double fnorm0) {
-  for (int j = 0; j < NP; ++j) st.x[j] = x0[j];
-  st.fnorm = fnorm0;
-  st.par = 0.0;
-  st.iter = 1;
-  st.nfev = 1;
-  st.njev = 0;
-  st.info = 0;
-  st.xnorm = 0.0;
-  st.delta = 0.0;
+template <typename Ex>
+IA3_HD void lm_init(Ex& ex, LMState& st, const double* x0, double fnorm0) {
+  for (int j = ex.lane(); j < NP; j += Ex::W) st.x[j] = x0[j];
+  if (ex.lane() == 0) {
+    st.fnorm = fnorm0;
+    st.par = 0.0;
+    st.iter = 1;
+    st.nfev = 1;
+    st.njev = 0;
+    st.info = 0;
+    st.xnorm = 0.0;
+    st.delta = 0.0;
+  }
+  ex.sync();
 }
 
 // After a Jacobian pass at st.x (A = J^T J, g = J^T f).  Returns false if lmder stops here.
-IA3_HDN bool lm_outer(LMState& st, const LMConfig& cfg, const double* A, const double* g) {
-  st.njev += 1;
-  lm_factor(st, A, g);
-  if (st.iter == 1) {
-    for (int j = 0; j < NP; ++j) { st.diag[j] = st.acn[j]; if (st.acn[j] == 0.0) st.diag[j] = 1.0; }
-    for (int j = 0; j < NP; ++j) st.w3[j] = st.diag[j] * st.x[j];
-    st.xnorm = enorm_n(st.w3, NP);
-    st.delta = cfg.factor * st.xnorm;
-    if (st.delta == 0.0) st.delta = cfg.factor;
+template <typename Ex>
+IA3_HDN bool lm_outer(Ex& ex, LMState& st, const LMConfig& cfg, const double* A, const double* g) {
+  const int ln = ex.lane();
+  lm_factor(ex, st, A, g);
+  const int iter = st.iter;
+  if (iter == 1) {
+    for (int j = ln; j < NP; j += Ex::W) {
+      const double d = (st.acn[j] == 0.0) ? 1.0 : st.acn[j];
+      st.diag[j] = d;
+      st.w3[j] = d * st.x[j];
+    }
+    ex.sync();
+    const double xnorm = enorm_n(st.w3, NP);
+    double delta = cfg.factor * xnorm;
+    if (delta == 0.0) delta = cfg.factor;
+    ex.sync();
+    if (ln == 0) { st.xnorm = xnorm; st.delta = delta; }
   }
   double gnorm = 0.0;
-  if (st.fnorm != 0.0) {
-    for (int j = 0; j < NP; ++j) {
-      int l = st.ipvt[j];
+  const double fnorm = st.fnorm;
+  if (fnorm != 0.0) {
+    for (int j = ln; j < NP; j += Ex::W) {
+      const int l = st.ipvt[j];
       if (st.acn[l] != 0.0) {
+        // sum_{i<=j} R[i][j] * (qtf[i] / fnorm), as lmder does
         double sum = 0.0;
-        for (int i = 0; i <= j; ++i) sum += st.R[i][j] * (st.qtf[i] / st.fnorm);
+        for (int i = 0; i <= j; ++i) sum += st.R[i][j] * (st.qtf[i] / fnorm);
         gnorm = fmax(gnorm, fabs(sum / st.acn[l]));
       }
     }
   }
-  st.gnorm = gnorm;
-  if (gnorm <= cfg.gtol) { st.info = 4; return false; }
-  for (int j = 0; j < NP; ++j) st.diag[j] = fmax(st.diag[j], st.acn[j]);
+  gnorm = ex.allmax(gnorm);
+  ex.sync();
+  if (ln == 0) { st.njev += 1; st.gnorm = gnorm; }
+  if (gnorm <= cfg.gtol) { if (ln == 0) st.info = 4; ex.sync(); return false; }
+  for (int j = ln; j < NP; j += Ex::W) st.diag[j] = fmax(st.diag[j], st.acn[j]);
+  ex.sync();
   return true;
 }
 
 // Compute the LM step and the trial point st.xt (model must then be evaluated at st.xt).
-IA3_HDN void lm_propose(LMState& st) {
-  lm_lmpar(st, st.p);
-  for (int j = 0; j < NP; ++j) {
-    st.p[j] = -st.p[j];
-    st.xt[j] = st.x[j] + st.p[j];
-    st.w3[j] = st.diag[j] * st.p[j];
+template <typename Ex>
+IA3_HDN void lm_propose(Ex& ex, LMState& st) {
+  const int ln = ex.lane();
+  lm_lmpar(ex, st, st.p);
+  ex.sync();
+  for (int j = ln; j < NP; j += Ex::W) {
+    const double pj = -st.p[j];
+    st.p[j] = pj;
+    st.xt[j] = st.x[j] + pj;
+    st.w3[j] = st.diag[j] * pj;
   }
-  st.pnorm = enorm_n(st.w3, NP);
-  if (st.iter == 1) st.delta = fmin(st.delta, st.pnorm);
+  ex.sync();
+  const double pnorm = enorm_n(st.w3, NP);
+  const double delta = st.delta;
+  const int iter = st.iter;
+  ex.sync();
+  if (ln == 0) {
+    st.pnorm = pnorm;
+    if (iter == 1) st.delta = fmin(delta, pnorm);
+  }
+  ex.sync();
 }
 
 enum { LM_RETRY = 0, LM_ACCEPTED = 1, LM_DONE = 2 };
 
-// Given fnorm1 = |f(st.xt)|: ratio test, trust-region update, convergence tests.
-IA3_HDN int lm_judge(LMState& st, const LMConfig& cfg, double fnorm1) {
-  st.nfev += 1;
-  st.fnorm1 = fnorm1;
+// Given fnorm1 = |f(st.xt)|: ratio test, trust-region update, convergence tests.  Every lane
+// computes the (identical) decision; lane-strided / lane-0 writes.
+template <typename Ex>
+IA3_HDN int lm_judge(Ex& ex, LMState& st, const LMConfig& cfg, double fnorm1) {
+  const int ln = ex.lane();
   const double fnorm = st.fnorm;
+  const double pnorm = st.pnorm;
+  double delta = st.delta, par = st.par, xnorm = st.xnorm;
+  const double gnorm = st.gnorm;
+  const int nfev = st.nfev + 1;
   double actred = -1.0;
-  if (0.1 * fnorm1 < fnorm) { double q = fnorm1 / fnorm; actred = 1.0 - q * q; }
-  for (int j = 0; j < NP; ++j) st.w3[j] = 0.0;
-  for (int j = 0; j < NP; ++j) {
-    double temp = st.p[st.ipvt[j]];
-    for (int i = 0; i <= j; ++i) st.w3[i] += st.R[i][j] * temp;
+  if (0.1 * fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1.0 - q * q; }
+  // w3 = R * p[ipvt]  (row i: sum_{j>=i} R[i][j] p[ipvt[j]], j ascending as lmder accumulates)
+  for (int i = ln; i < NP; i += Ex::W) {
+    double s = 0.0;
+    for (int j = i; j < NP; ++j) s += st.R[i][j] * st.p[st.ipvt[j]];
+    st.w3[i] = s;
   }
-  double temp1 = enorm_n(st.w3, NP) / fnorm;
-  double temp2 = (sqrt(st.par) * st.pnorm) / fnorm;
-  double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
-  double dirder = -(temp1 * temp1 + temp2 * temp2);
+  ex.sync();
+  const double temp1 = enorm_n(st.w3, NP) / fnorm;
+  const double temp2 = (sqrt(par) * pnorm) / fnorm;
+  const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+  const double dirder = -(temp1 * temp1 + temp2 * temp2);
   double ratio = 0.0;
   if (prered != 0.0) ratio = actred / prered;
   if (ratio <= 0.25) {
     double temp = 0.5;
     if (actred < 0.0) temp = 0.5 * dirder / (dirder + 0.5 * actred);
     if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
-    st.delta = temp * fmin(st.delta, st.pnorm / 0.1);
-    st.par = st.par / temp;
-  } else if (st.par == 0.0 || ratio >= 0.75) {
-    st.delta = st.pnorm / 0.5;
-    st.par = 0.5 * st.par;
+    delta = temp * fmin(delta, pnorm / 0.1);
+    par = par / temp;
+  } else if (par == 0.0 || ratio >= 0.75) {
+    delta = pnorm / 0.5;
+    par = 0.5 * par;
   }
-  bool accepted = false;
-  if (ratio >= 1.0e-4) {
-    for (int j = 0; j < NP; ++j) { st.x[j] = st.xt[j]; st.w3[j] = st.diag[j] * st.x[j]; }
-    st.xnorm = enorm_n(st.w3, NP);
-    st.fnorm = fnorm1;
-    st.iter += 1;
-    accepted = true;
+  const bool accepted = ratio >= 1.0e-4;
+  ex.sync();
+  if (accepted) {
+    for (int j = ln; j < NP; j += Ex::W) { const double v = st.xt[j]; st.x[j] = v; st.w3[j] = st.diag[j] * v; }
+    ex.sync();
+    xnorm = enorm_n(st.w3, NP);
   }
+  int info = 0;
   const bool small = fabs(actred) <= cfg.ftol && prered <= cfg.ftol && 0.5 * ratio <= 1.0;
-  if (small) st.info = 1;
-  if (st.delta <= cfg.xtol * st.xnorm) st.info = 2;
-  if (small && st.info == 2) st.info = 3;
-  if (st.info != 0) return LM_DONE;
-  if (st.nfev >= cfg.maxfev) st.info = 5;
-  if (fabs(actred) <= DBL_EPSILON && prered <= DBL_EPSILON && 0.5 * ratio <= 1.0) st.info = 6;
-  if (st.delta <= DBL_EPSILON * st.xnorm) st.info = 7;
-  if (st.gnorm <= DBL_EPSILON) st.info = 8;
-  if (st.info != 0) return LM_DONE;
+  if (small) info = 1;
+  if (delta <= cfg.xtol * xnorm) info = 2;
+  if (small && info == 2) info = 3;
+  if (info == 0) {
+    if (nfev >= cfg.maxfev) info = 5;
+    if (fabs(actred) <= DBL_EPSILON && prered <= DBL_EPSILON && 0.5 * ratio <= 1.0) info = 6;
+    if (delta <= DBL_EPSILON * xnorm) info = 7;
+    if (gnorm <= DBL_EPSILON) info = 8;
+  }
+  ex.sync();
+  if (ln == 0) {
+    st.nfev = nfev;
+    st.fnorm1 = fnorm1;
+    st.delta = delta;
+    st.par = par;
+    st.info = info;
+    if (accepted) { st.xnorm = xnorm; st.fnorm = fnorm1; st.iter += 1; }
+  }
+  ex.sync();
+  if (info != 0) return LM_DONE;
   return accepted ? LM_ACCEPTED : LM_RETRY;
 }
 

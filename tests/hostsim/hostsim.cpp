@@ -18,6 +18,14 @@ struct SerialExec {
   int allsum_int(int v) const { return v; }
   double allmax(double v) const { return v; }
   void argmin(double&, int&) const {}
+  struct TakenMask {
+    std::vector<bool> bits;
+    void clear() { bits.assign(1 << 15, false); }
+    bool test(int i) const { return bits[i]; }
+    void set(int i) { bits[i] = true; }
+  };
+  template <int N>
+  void reduce_store(double (&v)[N], double* out) const { for (int i = 0; i < N; ++i) out[i] = v[i]; }
 };
 
 template <typename T>
@@ -49,9 +57,8 @@ static int run(int personality, const double* values, const int* coords, int m, 
   }
   SerialExec ex;
   static SpotShared<T> sh;
-  std::vector<double> tmp(m);
-  select10(ex, values, tmp.data(), m, false, sh.small10);
-  select10(ex, values, tmp.data(), m, true, sh.large10);
+  select10(ex, values, m, false, sh.small10);
+  select10(ex, values, m, true, sh.large10);
   initial_guess(fp, sh.small10, sh.large10, init_w, sh.x0);
   ArrayVox<T> vox{m, rel.data(), data.data()};
   run_lm<T>(ex, fp, cfg, cen, origin, vox, sh);
@@ -153,24 +160,25 @@ extern "C" int hostsim_fit_qr(int personality, const double* values, const int* 
   SerialExec ex;
   static SpotShared<T> sh;
   std::vector<double> tmp(m);
-  select10(ex, values, tmp.data(), m, false, sh.small10);
-  select10(ex, values, tmp.data(), m, true, sh.large10);
+  select10_scratch(ex, values, tmp.data(), m, false, sh.small10);
+  select10_scratch(ex, values, tmp.data(), m, true, sh.large10);
   initial_guess(fp, sh.small10, sh.large10, init_w, sh.x0);
   ArrayVox<T> vox{m, rel.data(), data.data()};
   LMState& st = sh.st;
   std::vector<double> fvec(m), ftrial(m), J((size_t)m * NP);
   auto evalf = [&](const double* x, std::vector<double>& out) {
-    ModelConsts mc; model_consts(fp, cen, x, false, mc); narrow_consts<T>(mc, origin, false, sh.vc);
+    build_consts<T>(fp, cen, origin, x, false, sh.vc);
     for (int k = 0; k < m; ++k) { T a, b, c, d; vox.get(k, a, b, c, d); out[k] = eval_res<T>(sh.vc, a, b, c, d); }
     return pass_residual<T>(ex, sh.vc, vox, (double*)0);
   };
-  lm_init(st, sh.x0, evalf(sh.x0, fvec));
+  lm_init(ex, st, sh.x0, evalf(sh.x0, fvec));
   for (;;) {
-    ModelConsts mc; model_consts(fp, cen, st.x, true, mc); narrow_consts<T>(mc, origin, true, sh.vc);
+    build_consts<T>(fp, cen, origin, st.x, true, sh.vc);
     for (int k = 0; k < m; ++k) { T a, b, c, d, r; float Jr[NP]; vox.get(k, a, b, c, d); eval_jac<T>(sh.vc, a, b, c, d, r, Jr); for (int j = 0; j < NP; ++j) J[(size_t)j * m + k] = Jr[j]; }
     // same as lm_outer but with the Householder factorisation
     st.njev += 1;
     qrfac_full(J, m, st, fvec.data());
+    lm_post_factor(ex, st);
     if (st.iter == 1) {
       for (int j = 0; j < NP; ++j) { st.diag[j] = st.acn[j]; if (st.acn[j] == 0.0) st.diag[j] = 1.0; }
       for (int j = 0; j < NP; ++j) st.w3[j] = st.diag[j] * st.x[j];
@@ -183,10 +191,10 @@ extern "C" int hostsim_fit_qr(int personality, const double* values, const int* 
     for (int j = 0; j < NP; ++j) st.diag[j] = fmax(st.diag[j], st.acn[j]);
     int action;
     for (;;) {
-      lm_propose(st);
+      lm_propose(ex, st);
       double f1 = evalf(st.xt, ftrial);
       if (getenv("HOSTSIM_DEBUG")) { printf("f par=%.6e delta=%.6e pnorm=%.6e fnorm1=%.17g x:", st.par, st.delta, st.pnorm, f1); for (int j=0;j<NP;++j) printf(" %.5e", st.xt[j]); printf("\n"); }
-      action = lm_judge(st, cfg, f1);
+      action = lm_judge(ex, st, cfg, f1);
       if (action != LM_RETRY) { if (action == LM_ACCEPTED || st.fnorm == f1) fvec = ftrial; }
       if (action != LM_RETRY) break;
     }
