@@ -1,6 +1,7 @@
 // C ABI of libia3b200.so (declared in include/ia3b200.h): handles, host-side orchestration
 // (buffer management, neighbour lists, dependency levels) and kernel launches.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -17,11 +18,36 @@
 namespace ia3 {
 
 static thread_local std::string g_err;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 static int g_device = -1;
-static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_stream = nullptr;          // standalone GaussianFit batches and the stopwatch
 static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
 static std::mutex g_mu;
+
+// Every stack owns a stream (taken from a small pool): stacks handled by different host threads
+// overlap on the device -- the copy of one stack with the seed kernels of the next and with the
+// long tail of a third one's fit sweeps (a few junk seeds run MINPACK to maxfev while the rest of
+// the GPU would otherwise idle).
+static std::vector<cudaStream_t> g_stream_pool;
+static int acquire_stream(cudaStream_t* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_stream_pool.empty()) { *out = g_stream_pool.back(); g_stream_pool.pop_back(); return 0; }
+  }
+  IA3_CUDA(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
+  return 0;
+}
+static int global_stream(cudaStream_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  *out = g_stream;
+  return 0;
+}
+static void release_stream(cudaStream_t st) {
+  if (!st) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_stream_pool.push_back(st);
+}
 
 void set_error(const std::string& msg) { g_err = msg; }
 
@@ -105,6 +131,12 @@ static int upload(T** d, const std::vector<T>& h, cudaStream_t st) {
 
 using namespace ia3;
 
+// A cudaMemcpyAsync into pageable host memory blocks the calling thread until the stream reaches the
+// copy, and the driver serialises other host threads' calls behind it meanwhile.  With several stacks
+// in flight that turned one stack's 80 ms straggler kernel into a stall of every other stack.  So:
+// wait for the stream first (cudaStreamSynchronize waits without blocking other threads), copy after.
+#define IA3_DRAIN(st) IA3_CUDA(cudaStreamSynchronize(st))
+
 struct ia3_stack {
   int dtype = 0, Z = 0, X = 0, Y = 0;
   size_t nvox = 0;
@@ -161,11 +193,12 @@ int ia3_device_sm_count(void) {
   cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, g_device);
   return v;
 }
-int64_t ia3_launch_count(void) { return g_launches; }
+int64_t ia3_launch_count(void) { return g_launches.load(); }
 
 int ia3_timer_start(void) {
   if (ensure_device()) return -1;
-  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaStream_t gs;
+  if (global_stream(&gs)) return -1;
   if (!g_t0) { IA3_CUDA(cudaEventCreate(&g_t0)); IA3_CUDA(cudaEventCreate(&g_t1)); }
   IA3_CUDA(cudaDeviceSynchronize());
   IA3_CUDA(cudaEventRecord(g_t0, g_stream));
@@ -174,9 +207,9 @@ int ia3_timer_start(void) {
 int ia3_timer_stop(float* ms) {
   if (ensure_device()) return -1;
   if (!g_t0) { set_error("timer not started"); return -1; }
+  IA3_CUDA(cudaDeviceSynchronize());               // work of every stream of this process is done
   IA3_CUDA(cudaEventRecord(g_t1, g_stream));
   IA3_CUDA(cudaEventSynchronize(g_t1));
-  IA3_CUDA(cudaDeviceSynchronize());
   IA3_CUDA(cudaEventElapsedTime(ms, g_t0, g_t1));
   return 0;
 }
@@ -186,8 +219,7 @@ static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
   if (dtype < 0 || dtype > 2 || Z <= 0 || X <= 0 || Y <= 0) { set_error("bad stack dtype/shape"); return -1; }
   s->dtype = dtype; s->Z = Z; s->X = X; s->Y = Y;
   s->nvox = (size_t)Z * X * Y;
-  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  s->stream = g_stream;   // one stream per process: stage timings bracket everything with events on it
+  if (acquire_stream(&s->stream)) return -1;
   for (auto& e : s->ev) IA3_CUDA(cudaEventCreate(&e));
   return 0;
 }
@@ -225,6 +257,7 @@ int ia3_stack_destroy(ia3_stack* s) {
   dev_free(s->bits); dev_free(s->counts); dev_free(s->offsets);
   dev_free(s->cand_zxy); dev_free(s->cand_h);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  release_stream(s->stream);
   delete s;
   return 0;
 }
@@ -278,6 +311,7 @@ static int seed_run_t(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidat
   if (seed_flags<Tin>(fg, bg, d, cfg->variant, s->bits, s->counts, s->offsets, st)) return -1;
   IA3_CUDA(cudaEventRecord(s->ev[3], st));
   long long total = 0;
+  IA3_DRAIN(st);
   IA3_CUDA(cudaMemcpyAsync(&total, s->offsets + d.n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
   IA3_CUDA(cudaStreamSynchronize(st));
   dev_free(s->cand_zxy); dev_free(s->cand_h);
@@ -339,7 +373,7 @@ static inline long long cell_key(long long a, long long b, long long c) {
 int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_fit_cfg* cfg, ia3_fit** out) {
   if (ensure_device()) return -1;
   if (!s || !cfg || !out || (n > 0 && !centers_zxy)) { set_error("null argument"); return -1; }
-  if (cfg->radius < 1 || cfg->radius > 15) { set_error("radius_fit must be in 1..15"); return -1; }
+  if (cfg->radius < 1 || cfg->radius > 7) { set_error("radius_fit must be in 1..7 (window of at most 2048 voxels)"); return -1; }
   if (cfg->personality != 3 && cfg->personality != 4) { set_error("personality must be 3 or 4"); return -1; }
   for (int64_t i = 0; i < 3 * n; ++i)
     if (!(std::fabs(centers_zxy[i]) < 1e6)) { set_error("seed coordinates must be finite and |c| < 1e6"); return -1; }
@@ -435,7 +469,7 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
 int ia3_fit_destroy(ia3_fit* f) {
   if (!f) return 0;
   if (g_device >= 0) cudaSetDevice(g_device);
-  if (g_stream) cudaStreamSynchronize(g_stream);
+  if (f->s && f->s->stream) cudaStreamSynchronize(f->s->stream);
   void* ptrs[] = {f->d_centers, f->d_own, f->d_nbr_start, f->d_nbr_idx, f->d_offs, f->d_mask, f->d_tie_count,
                   f->d_tie_spot, f->d_tie_k, f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info, f->d_rec,
                   f->d_snap, f->d_vol, f->d_work};
@@ -462,6 +496,7 @@ int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
     IA3_CUDA(cudaMemsetAsync(f->d_tie_count, 0, sizeof(int), st));
     if (launch_voronoi(f->d, st)) return -1;
     int cnt = 0;
+    IA3_DRAIN(st);
     IA3_CUDA(cudaMemcpyAsync(&cnt, f->d_tie_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     IA3_CUDA(cudaStreamSynchronize(st));
     f->n_ties = cnt;
@@ -479,8 +514,9 @@ int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
   const int64_t n = std::min<int64_t>(cap, f->n_ties);
   if (n <= 0) return 0;
   std::vector<int> sp(n), kk(n);
-  IA3_CUDA(cudaMemcpy(sp.data(), f->d_tie_spot, sizeof(int) * n, cudaMemcpyDeviceToHost));
-  IA3_CUDA(cudaMemcpy(kk.data(), f->d_tie_k, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  IA3_CUDA(cudaMemcpyAsync(sp.data(), f->d_tie_spot, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
+  IA3_CUDA(cudaMemcpyAsync(kk.data(), f->d_tie_k, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
+  IA3_CUDA(cudaStreamSynchronize(f->s->stream));
   for (int64_t i = 0; i < n; ++i) {
     const int sidx = sp[i], k = kk[i];
     spot[i] = sidx;
@@ -508,6 +544,7 @@ static int fetch_results(ia3_fit* f, float* ps, double* p_raw, uint8_t* success,
   cudaStream_t st = f->s->stream;
   const size_t n = (size_t)f->n;
   if (n == 0) return 0;
+  IA3_DRAIN(st);
   if (ps) IA3_CUDA(cudaMemcpyAsync(ps, f->d_ps, n * NOUT * 4, cudaMemcpyDeviceToHost, st));
   if (p_raw) IA3_CUDA(cudaMemcpyAsync(p_raw, f->d_praw, n * NP * 8, cudaMemcpyDeviceToHost, st));
   if (success) IA3_CUDA(cudaMemcpyAsync(success, f->d_succ, n, cudaMemcpyDeviceToHost, st));
@@ -594,6 +631,7 @@ int ia3_fit_get_volume(ia3_fit* f, int which, double* out) {
     IA3_CUDA(cudaStreamSynchronize(st));
     dev_free(snap2);
   }
+  IA3_DRAIN(st);
   IA3_CUDA(cudaMemcpyAsync(out, tmp, f->s->nvox * 8, cudaMemcpyDeviceToHost, st));
   IA3_CUDA(cudaStreamSynchronize(st));
   dev_free(tmp);
@@ -605,7 +643,8 @@ int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* c
   if (!f || i < 0 || i >= f->n) { set_error("bad seed index"); return -1; }
   const int K = f->d.K;
   std::vector<double> full(K);
-  IA3_CUDA(cudaMemcpy(full.data(), f->d_rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost));
+  IA3_CUDA(cudaMemcpyAsync(full.data(), f->d_rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost, f->s->stream));
+  IA3_CUDA(cudaStreamSynchronize(f->s->stream));
   int m = 0;
   for (int k = 0; k < K; ++k) {
     int v[3];
@@ -630,8 +669,8 @@ int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_pr
   if (!cfg || n_problems < 0 || (n_problems > 0 && (!off || !values || !coords || !centers))) { set_error("null argument"); return -1; }
   if (n_problems == 0) return 0;
   const int64_t total = off[n_problems];
-  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  if (global_stream(&st)) return -1;
   GenericFitDev d;
   memset(&d, 0, sizeof(d));
   long long* d_off; double* d_val; float* d_co; double* d_cen; double* d_tmp; double* d_rec = nullptr;
@@ -653,6 +692,7 @@ int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_pr
   d.lm.maxfev = cfg->maxfev > 0 ? cfg->maxfev : (cfg->personality == 4 ? 1000 : 1100);
   for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
   if (launch_generic_fit(d, st)) return -1;
+  IA3_DRAIN(st);
   if (ps) IA3_CUDA(cudaMemcpyAsync(ps, d_ps, np_ * NOUT * 4, cudaMemcpyDeviceToHost, st));
   if (p_raw) IA3_CUDA(cudaMemcpyAsync(p_raw, d_praw, np_ * NP * 8, cudaMemcpyDeviceToHost, st));
   if (success) IA3_CUDA(cudaMemcpyAsync(success, d_s, np_, cudaMemcpyDeviceToHost, st));
@@ -674,8 +714,8 @@ int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_
   memset(&fp, 0, sizeof(fp));
   fp.min_w2 = cfg->min_w * cfg->min_w; fp.max_w2 = cfg->max_w * cfg->max_w; fp.delta = delta_center;
   fp.weight_sigma = 0.0; fp.personality = cfg->personality;
-  if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  if (global_stream(&st)) return -1;
   double* d_p; double* d_c; float* d_co; double* d_out;
   if (dev_alloc((void**)&d_p, 80) || dev_alloc((void**)&d_c, 24) || dev_alloc((void**)&d_co, (size_t)m * 12) ||
       dev_alloc((void**)&d_out, (size_t)m * 8)) return -1;
@@ -683,6 +723,7 @@ int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_
   IA3_CUDA(cudaMemcpyAsync(d_c, center, 24, cudaMemcpyHostToDevice, st));
   IA3_CUDA(cudaMemcpyAsync(d_co, coords, (size_t)m * 12, cudaMemcpyHostToDevice, st));
   if (launch_eval_f0(fp, d_p, d_c, d_co, m, d_out, st)) return -1;
+  IA3_DRAIN(st);
   IA3_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
   IA3_CUDA(cudaStreamSynchronize(st));
   dev_free(d_p); dev_free(d_c); dev_free(d_co); dev_free(d_out);

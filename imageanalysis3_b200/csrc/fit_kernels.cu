@@ -14,6 +14,7 @@
 // level only if their windows are disjoint, and a seed's level is above that of every
 // lower-index seed it overlaps (levels are computed on the host, capi.cu).
 #include <algorithm>
+#include <mutex>
 #include "ia3_device.h"
 #include "fit_kernels.h"
 #include "fit_spot.h"
@@ -395,13 +396,21 @@ int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, boo
   if (n_work == 0) return 0;
   const int smem = fit_smem_bytes(d.K, fp32);
   const unsigned grid = (unsigned)((n_work + WARPS - 1) / WARPS);
-  if (fp32) {
-    IA3_CUDA(cudaFuncSetAttribute(k_fit<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_fit<float><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
-  } else {
-    IA3_CUDA(cudaFuncSetAttribute(k_fit<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k_fit<double><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
-  }
+  // same value from every host thread (the attribute is per-function state); k_fit also has ~2 KB static
+  constexpr int kMaxDynSmem = 227 * 1024 - 4096;
+  if (smem > kMaxDynSmem) { set_error("radius_fit too large for the shared-memory window"); return -1; }
+  // once per process and device: changing a function attribute while an instance of the kernel is
+  // running (another stack's sweep) would serialise the streams
+  static std::once_flag once;
+  static cudaError_t once_err = cudaSuccess;
+  std::call_once(once, [] {
+    once_err = cudaFuncSetAttribute(k_fit<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (once_err == cudaSuccess)
+      once_err = cudaFuncSetAttribute(k_fit<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  });
+  IA3_CUDA(once_err);
+  if (fp32) k_fit<float><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
+  else k_fit<double><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
   IA3_LAUNCH_CHECK();
   return 0;
 }

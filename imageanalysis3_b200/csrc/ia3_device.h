@@ -4,13 +4,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include "ia3_common.h"
 
 namespace ia3 {
 
 void set_error(const std::string& msg);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;
 
 #define IA3_CUDA(expr)                                                                          \
   do {                                                                                          \

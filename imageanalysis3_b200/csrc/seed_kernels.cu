@@ -16,6 +16,7 @@
 // input tile is staged in shared memory as float (exact for uint16 and float32 inputs) with an
 // odd pitch, one thread walks one line and produces 8 outputs per step from a register window
 // of 8 + 2r doubles (8.5 shared loads per output instead of 61).
+#include <mutex>
 #include "ia3_device.h"
 #include "seed_kernels.h"
 
@@ -36,6 +37,7 @@ template <> __device__ __forceinline__ uint16_t store_cast<uint16_t>(double acc)
 }
 template <> __device__ __forceinline__ float store_cast<float>(double acc) { return __double2float_rn(acc); }
 
+constexpr size_t kMaxDynSmem = 227 * 1024;   // opt-in maximum per CTA on sm_100a
 constexpr int LINES = 128;   // lines per block = threads per block
 constexpr int CHMAX = 8;     // outputs per register-window step (4 for the 81-tap legacy filter: register budget)
 
@@ -151,7 +153,13 @@ static int launch_axis(const Tin* in, Tin* out, int L, long long inner, long lon
   size_t smem = (size_t)LINES * pitch * sizeof(float);
   if (INNER1) smem += (size_t)LINES * (TL + 2) * sizeof(Tin);
   auto kern = k_gauss_axis<R, Tin, INNER1>;
-  IA3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // always the same (maximum) value: concurrent host threads launch the same instantiation with
+  // different tile sizes, and the attribute is per-function state
+  if (smem > kMaxDynSmem) { set_error("gaussian tile does not fit in shared memory"); return -1; }
+  static std::once_flag once;                  // one flag per template instantiation
+  static cudaError_t once_err = cudaSuccess;
+  std::call_once(once, [&] { once_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem); });
+  IA3_CUDA(once_err);
   dim3 grid((unsigned)((n_lines + LINES - 1) / LINES), (unsigned)((L + TL - 1) / TL));
   kern<<<grid, LINES, smem, st>>>(in, out, L, inner, n_lines, TL, gw);
   IA3_LAUNCH_CHECK();

@@ -1,0 +1,58 @@
+"""GPU: where the wall time of D concurrent fit_fov_image-like steps goes (host-side phase trace).
+    python tools/trace_pipeline.py [D] [K]
+"""
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from imageanalysis3_b200 import _lib
+from imageanalysis3_b200.External import Fitting_v4
+from imageanalysis3_b200.spot_tools import fitting
+from imageanalysis3_b200.synth import synth_torch
+
+D = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+K = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+SHAPE = (50, 2048, 2048)
+_lib.init(0)
+dev = torch.device("cuda", 0)
+stacks = []
+for i in range(min(D, 4)):
+    d = synth_torch(SHAPE, 5000, 1 + i, dev)
+    stacks.append((d, d.cpu().numpy().view(np.uint16)))
+torch.cuda.synchronize()
+T0 = time.perf_counter()
+trace = []
+
+
+def step(i):
+    d, host = stacks[i % len(stacks)]
+    ev = []
+    def mark(name, t0):
+        ev.append((name, 1e3 * (t0 - T0), 1e3 * (time.perf_counter() - T0)))
+    t = time.perf_counter()
+    st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
+    seeds = fitting.get_seeds(host, max_num_seeds=None, th_seed=300.0, _stack=st)
+    mark("seed", t); t = time.perf_counter()
+    f = Fitting_v4.iter_fit_seed_points(host, seeds.T, _stack=st)
+    f.firstfit()
+    mark("first", t); t = time.perf_counter()
+    f.repeatfit()
+    mark(f"repeat x{f.n_iter}", t)
+    trace.append((i, threading.get_ident() % 1000, ev))
+    return len(seeds)
+
+
+pool = ThreadPoolExecutor(D)
+list(pool.map(step, range(D)))       # warm-up
+trace.clear()
+T0 = time.perf_counter()
+list(pool.map(step, range(K)))
+total = 1e3 * (time.perf_counter() - T0)
+for i, tid, ev in sorted(trace):
+    print(f"step {i} thr {tid:3d}: " + "  ".join(f"{n} {a:7.1f}-{b:7.1f}" for n, a, b in ev))
+print(f"D={D} K={K} total {total:.1f} ms -> {total / K:.1f} ms/step")
