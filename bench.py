@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware queue per in-flight stack (the default 8 makes streams share queues, and a stack's long
+# fit tail then blocks unrelated stacks); must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 SHAPE = (50, 2048, 2048)
 N_PLANTED = 5000
@@ -304,11 +307,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=4, help="stacks in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--inflight", type=int, default=16, help="stacks in flight per GPU (host threads / CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

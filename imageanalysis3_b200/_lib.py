@@ -61,6 +61,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    # stacks processed by concurrent host threads each own a CUDA stream; give them separate hardware
+    # queues (effective only if this process has not created its CUDA context yet)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     if not os.path.exists(LIB_PATH):
         raise IA3Error(f"{LIB_PATH} not found: build it with `python -m imageanalysis3_b200.build` "
                        "(there is no CPU fallback)")
