@@ -528,6 +528,151 @@ k_flags(const Tin* __restrict__ fg, const Tin* __restrict__ bg, SeedDims d, uint
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// uint16 fast path of the candidate mask (filt_size 3, Y % 8 == 0): packed 16-bit SIMD min/max.
+// A thread owns one 8-voxel chunk (four u16x2 words) of one (x) row and marches along z, so every
+// plane's 3-row (x-1, x, x+1) max / min is formed once and reused for three output planes; the 3-tap
+// max / min along y needs one voxel from each neighbouring chunk, taken from the neighbouring lanes
+// by shuffle (a warp loads 32 consecutive chunks of one row and produces the inner 30).  Rows, planes
+// and chunks outside the stack contribute the identity (0 for max, 0xffff for min), which is what
+// scipy's `reflect` amounts to for a rank filter.  ~25 instructions per voxel instead of ~215.
+// ------------------------------------------------------------------------------------------
+constexpr int FL_ROWS = 8;          // x rows per CTA (one warp each)
+constexpr int FL_OUT = 30;          // chunks produced per warp
+
+struct W4 { uint32_t w[4]; };
+
+__device__ __forceinline__ W4 ld_chunk(const uint16_t* vol, long long row_off, int cy, bool ok, uint32_t ident) {
+  W4 r;
+  if (ok) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(vol + row_off + (long long)cy * 8));
+    r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w;
+  } else {
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = ident;
+  }
+  return r;
+}
+__device__ __forceinline__ W4 max3(const W4& a, const W4& b, const W4& c) {
+  W4 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.w[i] = __vimax3_u16x2(a.w[i], b.w[i], c.w[i]);
+  return r;
+}
+__device__ __forceinline__ W4 min3(const W4& a, const W4& b, const W4& c) {
+  W4 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.w[i] = __vimin3_u16x2(a.w[i], b.w[i], c.w[i]);
+  return r;
+}
+// 3-tap max / min along y inside the chunk; lh / rh = neighbouring chunks' last / first word
+template <bool ISMAX>
+__device__ __forceinline__ W4 horiz3(const W4& v, uint32_t left_w3, uint32_t right_w0) {
+  W4 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t prev = (i == 0) ? left_w3 : v.w[i - 1];
+    const uint32_t next = (i == 3) ? right_w0 : v.w[i + 1];
+    const uint32_t l = __byte_perm(prev, v.w[i], 0x5432);     // (prev.hi, cur.lo)
+    const uint32_t rr = __byte_perm(v.w[i], next, 0x5432);    // (cur.hi, next.lo)
+    r.w[i] = ISMAX ? __vimax3_u16x2(l, v.w[i], rr) : __vimin3_u16x2(l, v.w[i], rr);
+  }
+  return r;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(FL_ROWS * 32)
+k_flags_u16(const uint16_t* __restrict__ fg, const uint16_t* __restrict__ bg, SeedDims d, int zseg,
+            uint8_t* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int x = blockIdx.y * FL_ROWS + (threadIdx.x >> 5);
+  const int cy = blockIdx.x * FL_OUT + lane - 1;                 // this lane's chunk (may be -1 or >= cpr)
+  const int zs = blockIdx.z * zseg, ze = min(d.Z, zs + zseg);
+  if (x >= d.X) return;                                          // whole warp
+  const bool cok = (cy >= 0) && (cy < d.cpr);
+  const bool produce = cok && lane >= 1 && lane <= FL_OUT;
+  const long long plane = (long long)d.X * d.Y;
+  const bool xm = x > 0, xp = x + 1 < d.X;
+
+  W4 pf0, pf1, pb0, pb1, cf1, cb1;       // 3-row max / min of planes z-1 (0) and z (1); centre row of plane z
+  auto load_plane = [&](int zz, W4& pf, W4& pb, W4& cf, W4& cb) {
+    if (zz < 0 || zz >= d.Z) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { pf.w[i] = 0u; pb.w[i] = 0xffffffffu; cf.w[i] = 0u; cb.w[i] = 0u; }
+      return;
+    }
+    const long long r0 = (long long)zz * plane + (long long)x * d.Y;
+    cf = ld_chunk(fg, r0, cy, cok, 0u);
+    cb = ld_chunk(bg, r0, cy, cok, 0xffffffffu);
+    const W4 fa = ld_chunk(fg, r0 - d.Y, cy, cok && xm, 0u), fc = ld_chunk(fg, r0 + d.Y, cy, cok && xp, 0u);
+    const W4 ba = ld_chunk(bg, r0 - d.Y, cy, cok && xm, 0xffffffffu), bc = ld_chunk(bg, r0 + d.Y, cy, cok && xp, 0xffffffffu);
+    pf = max3(fa, cf, fc);
+    pb = min3(ba, cb, bc);
+  };
+  { W4 t0, t1; load_plane(zs - 1, pf0, pb0, t0, t1); }
+  load_plane(zs, pf1, pb1, cf1, cb1);
+  for (int z = zs; z < ze; ++z) {
+    W4 pf2, pb2, cf2, cb2;
+    load_plane(z + 1, pf2, pb2, cf2, cb2);
+    const W4 vf = max3(pf0, pf1, pf2), vb = min3(pb0, pb1, pb2);
+    const uint32_t fl = __shfl_up_sync(0xffffffffu, vf.w[3], 1), fr = __shfl_down_sync(0xffffffffu, vf.w[0], 1);
+    const uint32_t bl = __shfl_up_sync(0xffffffffu, vb.w[3], 1), br = __shfl_down_sync(0xffffffffu, vb.w[0], 1);
+    if (produce) {
+      const W4 mx = horiz3<true>(vf, fl, fr), mn = horiz3<false>(vb, bl, br);
+      uint32_t mask = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t eqf = mx.w[i] ^ cf1.w[i];          // half == 0  <=>  local max (plateaus count)
+        const uint32_t neb = mn.w[i] ^ cb1.w[i];          // half != 0  <=>  not a local min of the background
+        if ((eqf & 0xffffu) == 0 && (neb & 0xffffu) != 0) mask |= 1u << (2 * i);
+        if ((eqf >> 16) == 0 && (neb >> 16) != 0) mask |= 2u << (2 * i);
+      }
+      if (mask) {
+        // the (rare) survivors: threshold on exact integers, then the inclusive edge filter
+        uint32_t m2 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!(mask & (1u << i))) continue;
+          const int f = (int)((cf1.w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+          const int b = (int)((cb1.w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+          const int m = (int)((mn.w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+          bool keep;
+          if (VARIANT == 0) keep = (double)(f - b) >= d.h_min;
+          else keep = (m != 0) && ((double)(f - m) >= d.h_min);
+          if (keep) m2 |= 1u << i;
+        }
+        mask = m2;
+        if (VARIANT == 0 && d.edge_on && mask) {
+          if (z < d.lo || z > d.hiZ || x < d.lo || x > d.hiX) mask = 0;
+          else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int y = cy * 8 + i; if (y < d.lo || y > d.hiY) mask &= ~(1u << i); }
+          }
+        }
+      }
+      bits[((long long)z * d.X + x) * d.cpr + cy] = (uint8_t)mask;
+    }
+    pf0 = pf1; pb0 = pb1; pf1 = pf2; pb1 = pb2; cf1 = cf2; cb1 = cb2;
+  }
+}
+
+// per-block candidate counts (block = FLAG_THREADS consecutive chunks in C order) from the mask bytes
+__global__ void __launch_bounds__(FLAG_THREADS) k_count_bits(const uint8_t* __restrict__ bits, long long n_chunks,
+                                                             int* __restrict__ block_counts) {
+  const long long cidx = (long long)blockIdx.x * FLAG_THREADS + threadIdx.x;
+  int c = (cidx < n_chunks) ? __popc((unsigned)bits[cidx]) : 0;
+  __shared__ int wsum[FLAG_THREADS / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < FLAG_THREADS / 32; ++i) t += wsum[i];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
 // Exclusive scan of the per-block counts by one 1024-thread block (n is ~1e5: one pass of
 // contiguous per-thread segments + a block scan of the segment sums).  offsets[n] = total.
 __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, int n) {
@@ -589,6 +734,26 @@ template <typename Tin>
 int seed_flags(const Tin* fg, const Tin* bg, const SeedDims& d, int variant, uint8_t* bits, int* counts,
                long long* offsets, cudaStream_t st) {
   const int nb = d.n_blocks;
+  if constexpr (sizeof(Tin) == 2) {
+    if (d.fs == 3 && d.Y % 8 == 0) {
+      // z is split so that the grid has a few waves of CTAs even for thin stacks
+      const int gx = (d.cpr + FL_OUT - 1) / FL_OUT, gy = (d.X + FL_ROWS - 1) / FL_ROWS;
+      int nseg = 1;
+      while ((long long)gx * gy * nseg < 148 * 16 && nseg < d.Z) nseg *= 2;
+      const int zseg = (d.Z + nseg - 1) / nseg;
+      dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((d.Z + zseg - 1) / zseg));
+      const uint16_t* f16 = reinterpret_cast<const uint16_t*>(fg);
+      const uint16_t* b16 = reinterpret_cast<const uint16_t*>(bg);
+      if (variant == 0) k_flags_u16<0><<<grid, FL_ROWS * 32, 0, st>>>(f16, b16, d, zseg, bits);
+      else k_flags_u16<1><<<grid, FL_ROWS * 32, 0, st>>>(f16, b16, d, zseg, bits);
+      IA3_LAUNCH_CHECK();
+      k_count_bits<<<nb, FLAG_THREADS, 0, st>>>(bits, d.n_chunks, counts);
+      IA3_LAUNCH_CHECK();
+      k_scan_counts<<<1, 1024, 0, st>>>(counts, offsets, nb);
+      IA3_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   if (variant == 0) k_flags<Tin, 0><<<nb, FLAG_THREADS, 0, st>>>(fg, bg, d, bits, counts);
   else k_flags<Tin, 1><<<nb, FLAG_THREADS, 0, st>>>(fg, bg, d, bits, counts);
   IA3_LAUNCH_CHECK();
