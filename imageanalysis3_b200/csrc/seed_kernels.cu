@@ -282,6 +282,165 @@ k_gauss_u16(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int L, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-window line kernels (uint16): no shared-memory tile at all.  A thread owns one line
+// segment and slides a window of 2R (+ alignment) + U input values held in registers along the
+// filter axis: per U outputs it loads U new values, computes, stores and shifts the window (moves,
+// not loads).  k_gauss_strided: the axis is strided (z and x passes); the lanes of a warp are
+// consecutive along the contiguous dimension, so every load/store of the warp is one coalesced
+// 64-byte request.  k_gauss_contig: the axis is the contiguous one (y pass); a thread walks its own
+// row with 16-byte loads/stores (L1 keeps the 128-byte lines between a thread's consecutive chunks).
+// Reflection indices of segments that touch the ends of the axis come from a per-CTA table.
+// ------------------------------------------------------------------------------------------
+template <int R>
+__device__ __noinline__ unsigned exact_from_global(const uint16_t* line, long long stride, int a, int L, const double* w) {
+  double acc = __dmul_rn((double)line[(long long)a * stride], w[0]);
+  for (int j = R; j >= 1; --j) {
+    const double lo = (double)line[(long long)reflect_idx(a - j, L) * stride];
+    const double hi = (double)line[(long long)reflect_idx(a + j, L) * stride];
+    acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(lo, hi), w[j]));
+  }
+  return (unsigned)__double2int_rz(acc);
+}
+
+// U outputs from the register window; output o is centred on w[C + o]
+template <int R, int U, int C, int NW>
+__device__ __forceinline__ void window_outputs(const int (&w)[NW], const GaussW& gw, const double* wsh,
+                                               const uint16_t* line, long long stride, int a, int L, unsigned (&res)[U]) {
+  double acc[U];
+#pragma unroll
+  for (int o = 0; o < U; ++o) acc[o] = __hiloint2double(0x41300000 + w[C + o], 0) * gw.w[0];
+#pragma unroll
+  for (int j = R; j >= 1; --j) {
+#pragma unroll
+    for (int o = 0; o < U; ++o)
+      acc[o] = fma(__hiloint2double(0x41300000 + w[C + o - j] + w[C + o + j], 0), gw.w[j], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < U; ++o) {
+    const double v = acc[o] - gw.w[R + 1];
+    const unsigned rlo = (unsigned)__double2loint(__dadd_rz(fmax(v - kTruncGuard, 0.0), 4503599627370496.0));
+    const unsigned rhi = (unsigned)__double2loint(__dadd_rz(v + kTruncGuard, 4503599627370496.0));
+    res[o] = rlo;
+    if (rlo != rhi && a + o < L) res[o] = exact_from_global<R>(line, stride, a + o, L, wsh);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(LINES, (R > 32) ? 3 : 4)
+k_gauss_strided(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int L, long long inner, long long n_lines,
+                int seg, GaussW gw) {
+  constexpr int U = 8, NW = 2 * R + U;
+  extern __shared__ int ridx_s[];                  // seg rounded up to U, + 2R entries
+  __shared__ double wsh[R + 1];
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * seg, a1 = min(L, a0 + seg);
+  const int nload = ((a1 - a0 + U - 1) / U) * U + 2 * R;
+  const bool edge = (a0 - R < 0) || (a0 - R + nload > L);
+  if (tid <= R) wsh[tid] = gw.w[tid];
+  if (edge) for (int i = tid; i < nload; i += LINES) ridx_s[i] = reflect_idx(a0 - R + i, L);
+  __syncthreads();
+  const long long l = (long long)blockIdx.x * LINES + tid;
+  if (l >= n_lines) return;
+  const long long base = (l / inner) * ((long long)L * inner) + (l % inner);
+  const uint16_t* line = in + base;
+  uint16_t* op = out + base + (long long)a0 * inner;
+  int w[NW];
+  unsigned res[U];
+  if (!edge) {
+    const uint16_t* p = line + (long long)(a0 - R) * inner;
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i, p += inner) w[i] = *p;
+    for (int a = a0; a < a1; a += U) {
+#pragma unroll
+      for (int i = 0; i < U; ++i, p += inner) w[2 * R + i] = *p;
+      window_outputs<R, U, R, NW>(w, gw, wsh, line, inner, a, L, res);
+#pragma unroll
+      for (int o = 0; o < U; ++o, op += inner) if (a + o < a1) *op = (uint16_t)res[o];
+#pragma unroll
+      for (int i = 0; i < 2 * R; ++i) w[i] = w[i + U];
+    }
+  } else {
+    const int* ri = ridx_s;
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i) w[i] = line[(long long)ri[i] * inner];
+    ri += 2 * R;
+    for (int a = a0; a < a1; a += U, ri += U) {
+#pragma unroll
+      for (int i = 0; i < U; ++i) w[2 * R + i] = line[(long long)ri[i] * inner];
+      window_outputs<R, U, R, NW>(w, gw, wsh, line, inner, a, L, res);
+#pragma unroll
+      for (int o = 0; o < U; ++o, op += inner) if (a + o < a1) *op = (uint16_t)res[o];
+#pragma unroll
+      for (int i = 0; i < 2 * R; ++i) w[i] = w[i + U];
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(LINES, (R > 32) ? 3 : 4)
+k_gauss_contig(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int L, long long n_rows, int seg, GaussW gw) {
+  constexpr int U = 8, H = (R + 7) / 8 * 8, NW = 2 * H + U;      // window = [a - H, a + U + H), 16-byte aligned
+  extern __shared__ int ridx_s[];
+  __shared__ double wsh[R + 1];
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * seg, a1 = min(L, a0 + seg);          // seg and L are multiples of 8
+  const int nload = (a1 - a0) + 2 * H;
+  const bool edge = (a0 - H < 0) || (a0 - H + nload > L);
+  if (tid <= R) wsh[tid] = gw.w[tid];
+  if (edge) for (int i = tid; i < nload; i += LINES) ridx_s[i] = reflect_idx(a0 - H + i, L);
+  __syncthreads();
+  const long long row = (long long)blockIdx.x * LINES + tid;
+  if (row >= n_rows) return;
+  const uint16_t* line = in + row * (long long)L;
+  uint16_t* op = out + row * (long long)L + a0;
+  int w[NW];
+  unsigned res[U];
+  auto unpack = [&](const uint4& q, int at) {
+    w[at + 0] = q.x & 0xffff; w[at + 1] = q.x >> 16; w[at + 2] = q.y & 0xffff; w[at + 3] = q.y >> 16;
+    w[at + 4] = q.z & 0xffff; w[at + 5] = q.z >> 16; w[at + 6] = q.w & 0xffff; w[at + 7] = q.w >> 16;
+  };
+  const int* ri = ridx_s;
+  if (!edge) {
+    const uint4* p = reinterpret_cast<const uint4*>(line + (a0 - H));
+#pragma unroll
+    for (int c = 0; c < 2 * H / 8; ++c) unpack(__ldg(p + c), 8 * c);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2 * H; ++i) w[i] = line[ri[i]];
+  }
+  for (int a = a0; a < a1; a += U) {
+    if (!edge) unpack(__ldg(reinterpret_cast<const uint4*>(line + (a + H))), 2 * H);
+    else {
+#pragma unroll
+      for (int i = 0; i < U; ++i) w[2 * H + i] = line[ri[(a - a0) + 2 * H + i]];
+    }
+    window_outputs<R, U, H, NW>(w, gw, wsh, line, 1, a, L, res);
+    uint4 q;
+    q.x = res[0] | (res[1] << 16); q.y = res[2] | (res[3] << 16); q.z = res[4] | (res[5] << 16); q.w = res[6] | (res[7] << 16);
+    *reinterpret_cast<uint4*>(op) = q;
+    op += U;
+#pragma unroll
+    for (int i = 0; i < 2 * H; ++i) w[i] = w[i + U];
+  }
+}
+
+template <int R>
+static int launch_line_u16(const uint16_t* in, uint16_t* out, int L, long long inner, long long n_lines, bool contig,
+                           const GaussW& gw, cudaStream_t st) {
+  GaussW gk = gw;                               // w[R + 1] = 2^20 * (w0 + w1 + ... + wR): the offset the kernels remove
+  long double acc = 0.0L;
+  for (int j = 0; j <= R; ++j) acc += (long double)gw.w[j];
+  gk.w[R + 1] = (double)(acc * 1048576.0L);
+  const int seg = (L <= 320) ? ((L + 7) / 8) * 8 : 256;
+  dim3 grid((unsigned)((n_lines + LINES - 1) / LINES), (unsigned)((L + seg - 1) / seg));
+  const size_t smem = (size_t)(seg + 2 * 32 + 2 * R + 16) * sizeof(int);
+  if (contig) k_gauss_contig<R><<<grid, LINES, smem, st>>>(in, out, L, n_lines, seg, gk);
+  else k_gauss_strided<R><<<grid, LINES, smem, st>>>(in, out, L, inner, n_lines, seg, gk);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int R, bool INNER1>
 static int launch_axis_u16(const uint16_t* in, uint16_t* out, int L, long long inner, long long n_lines, const GaussW& gw,
                            cudaStream_t st) {
@@ -336,6 +495,16 @@ static int launch_axis(const Tin* in, Tin* out, int L, long long inner, long lon
 template <bool INNER1>
 static int dispatch_axis_u16(const uint16_t* in, uint16_t* out, int L, long long inner, long long n_lines, const GaussW& gw,
                              cudaStream_t st) {
+  // register-window kernels; the contiguous pass needs 16-byte aligned rows
+  const bool aligned = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  if (!INNER1 || aligned) {
+    switch (gw.r) {
+      case 3: return launch_line_u16<3>(in, out, L, inner, n_lines, INNER1, gw, st);
+      case 30: return launch_line_u16<30>(in, out, L, inner, n_lines, INNER1, gw, st);
+      case 40: return launch_line_u16<40>(in, out, L, inner, n_lines, INNER1, gw, st);
+      default: break;
+    }
+  }
   switch (gw.r) {
     case 3: return launch_axis_u16<3, INNER1>(in, out, L, inner, n_lines, gw, st);
     case 30: return launch_axis_u16<30, INNER1>(in, out, L, inner, n_lines, gw, st);
