@@ -55,7 +55,7 @@ void set_error(const std::string& msg) { g_err = msg; }
 static std::multimap<size_t, void*> g_free;
 static std::unordered_map<void*, size_t> g_sizes;
 static size_t g_cached_bytes = 0;
-static const size_t kCacheLimit = (size_t)48 << 30;
+static const size_t kCacheLimit = (size_t)150 << 30;
 
 int dev_alloc(void** p, size_t bytes) {
   if (bytes == 0) bytes = 256;

@@ -22,6 +22,11 @@
 namespace ia3 {
 
 constexpr int WARPS = 4;
+// One warp (= one spot) per CTA in the fit kernels.  A fit that runs MINPACK to maxfev keeps its CTA
+// resident for ~1000 iterations; with one warp per CTA it pins 8 K registers and 10 KB of shared
+// memory of its SM instead of 32 K / 42 KB, so the seed kernels of the other in-flight stacks keep
+// running next to the stragglers.
+constexpr int FIT_WARPS = 1;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct WarpExec {
@@ -195,10 +200,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_voronoi(FitDev d) {
 
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
+__global__ void __launch_bounds__(FIT_WARPS * 32) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long wi = (long long)blockIdx.x * WARPS + warp;
+  const long long wi = (long long)blockIdx.x * FIT_WARPS + warp;
   if (wi >= n_work) return;
   const long long s = work ? (long long)work[wi] : wi;
   const int K = d.K;
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const in
 
   BallVox<T> vox{m, pk, dv};
   run_lm<T>(ex, fp, d.lm, c, origin, vox, sh);
-  __shared__ FitResult res_s[WARPS];
+  __shared__ FitResult res_s[FIT_WARPS];
   FitResult& res = res_s[warp];
   finish_fit<T>(ex, fp, c, origin, vox, sh, &res);
   if (lane < NOUT) d.ps[s * NOUT + lane] = res.ps[lane];
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_fit(FitDev d, int mode, const in
 
   if (mode == 1) {
     // im_rec = get_im(); ims_rec[ic] = im_rec; im_add[window] = im_ - im_rec   (:671-675)
-    __shared__ VoxConsts<double> vcd_s[WARPS];
+    __shared__ VoxConsts<double> vcd_s[FIT_WARPS];
     VoxConsts<double>& vcd = vcd_s[warp];
     if (lane == 0) {
       build_consts<double>(fp, c, origin, sh.st.x, false, vcd);
@@ -331,11 +336,11 @@ struct GlobalVox {
   }
 };
 
-__global__ void __launch_bounds__(WARPS * 32) k_generic_fit(GenericFitDev d) {
-  __shared__ SpotShared<double> sh_s[WARPS];
-  __shared__ FitResult res_s[WARPS];
+__global__ void __launch_bounds__(FIT_WARPS * 32) k_generic_fit(GenericFitDev d) {
+  __shared__ SpotShared<double> sh_s[FIT_WARPS];
+  __shared__ FitResult res_s[FIT_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long b = (long long)blockIdx.x * WARPS + warp;
+  const long long b = (long long)blockIdx.x * FIT_WARPS + warp;
   if (b >= d.n) return;
   SpotShared<double>& sh = sh_s[warp];
   const long long o0 = d.off[b];
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_generic_fit(GenericFitDev d) {
 int fit_smem_bytes(int K, bool fp32) {
   const size_t shs = fp32 ? sizeof(SpotShared<float>) : sizeof(SpotShared<double>);
   const size_t per_warp = (shs + 15) / 16 * 16 + ((size_t)K * (8 + 4) + 15) / 16 * 16;
-  return (int)(per_warp * WARPS);
+  return (int)(per_warp * FIT_WARPS);
 }
 
 int launch_init_window(const FitDev& d, cudaStream_t st) {
@@ -395,7 +400,7 @@ int launch_voronoi(const FitDev& d, cudaStream_t st) {
 int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, bool fp32, cudaStream_t st) {
   if (n_work == 0) return 0;
   const int smem = fit_smem_bytes(d.K, fp32);
-  const unsigned grid = (unsigned)((n_work + WARPS - 1) / WARPS);
+  const unsigned grid = (unsigned)((n_work + FIT_WARPS - 1) / FIT_WARPS);
   // same value from every host thread (the attribute is per-function state); k_fit also has ~2 KB static
   constexpr int kMaxDynSmem = 227 * 1024 - 4096;
   if (smem > kMaxDynSmem) { set_error("radius_fit too large for the shared-memory window"); return -1; }
@@ -409,8 +414,8 @@ int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, boo
       once_err = cudaFuncSetAttribute(k_fit<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   });
   IA3_CUDA(once_err);
-  if (fp32) k_fit<float><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
-  else k_fit<double><<<grid, WARPS * 32, smem, st>>>(d, mode, work, n_work);
+  if (fp32) k_fit<float><<<grid, FIT_WARPS * 32, smem, st>>>(d, mode, work, n_work);
+  else k_fit<double><<<grid, FIT_WARPS * 32, smem, st>>>(d, mode, work, n_work);
   IA3_LAUNCH_CHECK();
   return 0;
 }
@@ -424,7 +429,7 @@ int launch_subtract(const FitDev& d, const int* work, long long n_work, cudaStre
 
 int launch_generic_fit(const GenericFitDev& d, cudaStream_t st) {
   if (d.n == 0) return 0;
-  k_generic_fit<<<(unsigned)((d.n + WARPS - 1) / WARPS), WARPS * 32, 0, st>>>(d);
+  k_generic_fit<<<(unsigned)((d.n + FIT_WARPS - 1) / FIT_WARPS), FIT_WARPS * 32, 0, st>>>(d);
   IA3_LAUNCH_CHECK();
   return 0;
 }
