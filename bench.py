@@ -145,14 +145,16 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
-    import torch
     rank, world, local = _dist_setup(args.gpus)
+    os.environ.setdefault("IA3_DEVICE", str(local))
+    from imageanalysis3_b200 import _lib
+    _lib.init(local)          # before torch touches the device: the library asks for blocking-sync waits
+    import torch
     use_dist = world > 1
     if use_dist:
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    os.environ.setdefault("IA3_DEVICE", str(local))
     from imageanalysis3_b200 import _lib
     from imageanalysis3_b200.External import Fitting_v4
     from imageanalysis3_b200.spot_tools import fitting

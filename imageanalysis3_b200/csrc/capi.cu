@@ -106,6 +106,13 @@ void dev_cache_clear() {
 }
 
 static int ensure_device() {
+  static std::once_flag flags_once;
+  std::call_once(flags_once, [] {
+    // host threads that wait for a stack's stream should sleep, not spin: many stacks are in flight
+    // per GPU (one host thread each).  Takes effect if this process has not created the device's
+    // primary context yet; otherwise the call fails harmlessly.
+    if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+  });
   if (g_device >= 0) { IA3_CUDA(cudaSetDevice(g_device)); return 0; }
   int dev = 0;
   if (const char* e = getenv("IA3_DEVICE")) dev = atoi(e);
