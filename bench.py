@@ -184,6 +184,7 @@ def run_ours(args):
         d = devt[i % n_stacks]
         st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
         seeds = fitting.get_seeds(host[i % n_stacks], max_num_seeds=None, th_seed=TH_SEED, _stack=st)
+        st.trim(1)
         f = Fitting_v4.iter_fit_seed_points(host[i % n_stacks], seeds.T, _stack=st)
         f.firstfit()
         f.repeatfit()
@@ -309,11 +310,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=16, help="stacks in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--inflight", type=int, default=32, help="stacks in flight per GPU (host threads / CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

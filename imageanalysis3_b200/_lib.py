@@ -42,9 +42,9 @@ class FitCfg(C.Structure):
 
 
 EXPORTS = [
-    "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count",
+    "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count", "ia3_debug_stats",
     "ia3_timer_start", "ia3_timer_stop",
-    "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy",
+    "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
     "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
     "ia3_fit_first_resolve", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_get_volume",
@@ -77,6 +77,7 @@ def load():
     lib.ia3_stack_create.argtypes = [vp, i32, i32, i32, i32, P(vp)]
     lib.ia3_stack_wrap_device.argtypes = [vp, i32, i32, i32, i32, P(vp)]
     lib.ia3_stack_destroy.argtypes = [vp]
+    lib.ia3_stack_trim.argtypes = [vp, i32]
     lib.ia3_seed_run.argtypes = [vp, P(SeedCfg), P(i64), P(SeedTiming)]
     lib.ia3_seed_fetch.argtypes = [vp, vp, vp, i64]
     lib.ia3_seed_fetch_volume.argtypes = [vp, i32, vp]
@@ -114,6 +115,12 @@ def timer_stop():
     ms = C.c_float(0)
     _check(load().ia3_timer_stop(C.byref(ms)))
     return float(ms.value)
+
+
+def debug_stats():
+    buf = C.create_string_buffer(8192)
+    load().ia3_debug_stats(buf, 8192)
+    return buf.value.decode()
 
 
 def launch_count():
@@ -162,6 +169,10 @@ class Stack:
 
     def close(self):
         self._fin()
+
+    def trim(self, what):
+        """release device memory early: 1 = seed-stage work volumes, 2 = the library's copy of the image"""
+        _check(load().ia3_stack_trim(self._h, int(what)))
 
     # ---- seed stage --------------------------------------------------------------------------
     def seed_candidates(self, w_fg, w_bg, filt_size, variant, edge, h_min):

@@ -2,6 +2,7 @@
 // (buffer management, neighbour lists, dependency levels) and kernel launches.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +52,35 @@ static void release_stream(cudaStream_t st) {
 
 void set_error(const std::string& msg) { g_err = msg; }
 
+// ---- wall-clock accounting of the entry points (IA3_STATS=1; tools/trace_pipeline.py prints it) ----
+struct StatSlot { const char* name; std::atomic<long long> ns{0}; std::atomic<long long> calls{0}; };
+static StatSlot g_stats[24];
+static std::atomic<int> g_nstats{0};
+static const bool g_stats_on = getenv("IA3_STATS") != nullptr;
+static StatSlot* stat_slot(const char* name) {
+  const int n = g_nstats.load();
+  for (int i = 0; i < n; ++i) if (g_stats[i].name == name) return &g_stats[i];
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int m = g_nstats.load();
+  for (int i = 0; i < m; ++i) if (g_stats[i].name == name) return &g_stats[i];
+  if (m >= 24) return &g_stats[23];
+  g_stats[m].name = name;
+  g_nstats.store(m + 1);
+  return &g_stats[m];
+}
+struct StatScope {
+  StatSlot* s = nullptr;
+  std::chrono::steady_clock::time_point t0;
+  explicit StatScope(const char* name) { if (g_stats_on) { s = stat_slot(name); t0 = std::chrono::steady_clock::now(); } }
+  ~StatScope() {
+    if (s) {
+      s->ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+      s->calls += 1;
+    }
+  }
+};
+#define IA3_STAT(name) ia3::StatScope _stat_scope(name)
+
 // ---- caching allocator --------------------------------------------------------------------
 static std::multimap<size_t, void*> g_free;
 static std::unordered_map<void*, size_t> g_sizes;
@@ -58,6 +88,7 @@ static size_t g_cached_bytes = 0;
 static const size_t kCacheLimit = (size_t)150 << 30;
 
 int dev_alloc(void** p, size_t bytes) {
+  IA3_STAT("dev_alloc");
   if (bytes == 0) bytes = 256;
   bytes = (bytes + 255) / 256 * 256;
   {
@@ -70,6 +101,7 @@ int dev_alloc(void** p, size_t bytes) {
       return 0;
     }
   }
+  StatScope _m("cudaMalloc");
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) {
     dev_cache_clear();
@@ -175,7 +207,8 @@ struct ia3_fit {
   int8_t* d_offs = nullptr; uint32_t* d_mask = nullptr;
   int* d_tie_count = nullptr; int* d_tie_spot = nullptr; int* d_tie_k = nullptr; int tie_cap = 0;
   float* d_ps = nullptr; double* d_praw = nullptr; uint8_t* d_succ = nullptr; int* d_nfev = nullptr; int* d_info = nullptr;
-  double* d_rec = nullptr; double* d_snap = nullptr; double* d_vol = nullptr;
+  double* d_rec = nullptr; double* d_snap = nullptr; double* d_vol = nullptr; int* d_brick_tab = nullptr;
+  int64_t n_bricks = 0;
   int* d_work = nullptr; size_t work_cap = 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   float last_ms = 0.f;
@@ -201,6 +234,14 @@ int ia3_device_sm_count(void) {
   return v;
 }
 int64_t ia3_launch_count(void) { return g_launches.load(); }
+int ia3_debug_stats(char* buf, int cap) {
+  int off = 0;
+  const int n = g_nstats.load();
+  for (int i = 0; i < n && off < cap - 96; ++i)
+    off += snprintf(buf + off, cap - off, "%-24s calls %8lld  total %10.2f ms\n", g_stats[i].name, g_stats[i].calls.load(),
+                    g_stats[i].ns.load() * 1e-6);
+  return off;
+}
 
 int ia3_timer_start(void) {
   if (ensure_device()) return -1;
@@ -232,6 +273,7 @@ static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
 }
 
 int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack** out) {
+  IA3_STAT("ia3_stack_create");
   if (ensure_device()) return -1;
   if (!im || !out) { set_error("null argument"); return -1; }
   ia3_stack* s = new ia3_stack();
@@ -245,6 +287,7 @@ int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack**
 }
 
 int ia3_stack_wrap_device(const void* d_im, int dtype, int Z, int X, int Y, ia3_stack** out) {
+  IA3_STAT("ia3_stack_wrap_device");
   if (ensure_device()) return -1;
   if (!d_im || !out) { set_error("null argument"); return -1; }
   ia3_stack* s = new ia3_stack();
@@ -256,6 +299,7 @@ int ia3_stack_wrap_device(const void* d_im, int dtype, int Z, int X, int Y, ia3_
 }
 
 int ia3_stack_destroy(ia3_stack* s) {
+  IA3_STAT("ia3_stack_destroy");
   if (!s) return 0;
   if (g_device >= 0) cudaSetDevice(g_device);
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -266,6 +310,29 @@ int ia3_stack_destroy(ia3_stack* s) {
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   release_stream(s->stream);
   delete s;
+  return 0;
+}
+
+int ia3_stack_trim(ia3_stack* s, int what) {
+  IA3_STAT("ia3_stack_trim");
+  if (!s) return 0;
+  if (ensure_device()) return -1;
+  IA3_CUDA(cudaStreamSynchronize(s->stream));
+  if (what & 1) {
+    dev_free(s->fg); dev_free(s->bg); dev_free(s->scratch);
+    dev_free(s->bits); dev_free(s->counts); dev_free(s->offsets);
+    dev_free(s->cand_zxy); dev_free(s->cand_h);
+    s->fg = s->bg = s->scratch = nullptr;
+    s->bits = nullptr; s->counts = nullptr; s->offsets = nullptr;
+    s->cand_zxy = nullptr; s->cand_h = nullptr;
+    s->fg_final = s->bg_final = nullptr;
+    s->n_cand = 0;
+  }
+  if ((what & 2) && s->owns) {
+    dev_free(s->d_im);
+    s->d_im = nullptr;
+    s->owns = false;
+  }
   return 0;
 }
 
@@ -343,8 +410,10 @@ static int seed_run_t(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidat
 extern "C" {
 
 int ia3_seed_run(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, ia3_seed_timing* t) {
+  IA3_STAT("ia3_seed_run");
   if (ensure_device()) return -1;
   if (!s || !cfg) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   if (s->dtype == IA3_DTYPE_U16) return seed_run_t<uint16_t>(s, cfg, n_candidates, t);
   if (s->dtype == IA3_DTYPE_F32) return seed_run_t<float>(s, cfg, n_candidates, t);
   set_error("seed stage supports uint16 and float32 stacks");
@@ -352,6 +421,7 @@ int ia3_seed_run(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, i
 }
 
 int ia3_seed_fetch(ia3_stack* s, int32_t* zxy, float* h, int64_t cap) {
+  IA3_STAT("ia3_seed_fetch");
   if (ensure_device()) return -1;
   if (!s) { set_error("null argument"); return -1; }
   const int64_t n = std::min<int64_t>(cap, s->n_cand);
@@ -378,8 +448,10 @@ static inline long long cell_key(long long a, long long b, long long c) {
 }
 
 int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_fit_cfg* cfg, ia3_fit** out) {
+  IA3_STAT("ia3_fit_create");
   if (ensure_device()) return -1;
   if (!s || !cfg || !out || (n > 0 && !centers_zxy)) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   if (cfg->radius < 1 || cfg->radius > 7) { set_error("radius_fit must be in 1..7 (window of at most 2048 voxels)"); return -1; }
   if (cfg->personality != 3 && cfg->personality != 4) { set_error("personality must be 3 or 4"); return -1; }
   for (int64_t i = 0; i < 3 * n; ++i)
@@ -447,7 +519,34 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
       dev_alloc((void**)&f->d_praw, nn * NP * 8) || dev_alloc((void**)&f->d_succ, nn) ||
       dev_alloc((void**)&f->d_nfev, nn * 4) || dev_alloc((void**)&f->d_info, nn * 4) ||
       dev_alloc((void**)&f->d_rec, nn * K * 8) || dev_alloc((void**)&f->d_snap, nn * K * 8) ||
-      dev_alloc((void**)&f->d_vol, s->nvox * 8) || dev_alloc((void**)&f->d_tie_count, 256)) { ia3_fit_destroy(f); return -1; }
+      dev_alloc((void**)&f->d_tie_count, 256)) { ia3_fit_destroy(f); return -1; }
+  // sparse float64 work volume: the 8x8x8 bricks touched by some seed's (clipped) window
+  const int nbz = (s->Z + 7) / 8, nbx = (s->X + 7) / 8, nby = (s->Y + 7) / 8;
+  {
+    std::vector<int> tab((size_t)nbz * nbx * nby, -1);
+    int next = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      int lo[3], hi[3];
+      const int dims[3] = {s->Z, s->X, s->Y};
+      bool empty = false;
+      for (int a = 0; a < 3; ++a) {
+        const int ic = (int)f->centers[3 * i + a];
+        lo[a] = std::max(ic - r, 0);
+        hi[a] = std::min(ic + r - 1, dims[a] - 1);
+        if (lo[a] > hi[a]) empty = true;
+      }
+      if (empty) continue;
+      for (int bz = lo[0] >> 3; bz <= hi[0] >> 3; ++bz)
+        for (int bx = lo[1] >> 3; bx <= hi[1] >> 3; ++bx)
+          for (int by = lo[2] >> 3; by <= hi[2] >> 3; ++by) {
+            int& t = tab[((size_t)bz * nbx + bx) * nby + by];
+            if (t < 0) t = next++;
+          }
+    }
+    f->n_bricks = next;
+    if (upload(&f->d_brick_tab, tab, st) || dev_alloc((void**)&f->d_vol, (size_t)std::max(next, 1) * 512 * 8)) { ia3_fit_destroy(f); return -1; }
+    IA3_CUDA(cudaStreamSynchronize(st));           // tab is a local
+  }
   IA3_CUDA(cudaMemsetAsync(f->d_succ, 0, nn, st));
   IA3_CUDA(cudaMemsetAsync(f->d_rec, 0, nn * K * 8, st));
   IA3_CUDA(cudaEventCreate(&f->e0));
@@ -455,7 +554,7 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
 
   FitDev& d = f->d;
   memset(&d, 0, sizeof(d));
-  d.im = s->d_im; d.im_dtype = s->dtype; d.vol = f->d_vol;
+  d.im = s->d_im; d.im_dtype = s->dtype; d.vol = f->d_vol; d.brick_tab = f->d_brick_tab; d.nbx = nbx; d.nby = nby;
   d.Z = s->Z; d.X = s->X; d.Y = s->Y;
   d.n = n; d.centers = f->d_centers; d.own_id = f->d_own; d.nbr_start = f->d_nbr_start; d.nbr_idx = f->d_nbr_idx;
   d.K = K; d.KW = KW; d.offs = f->d_offs; d.mask = f->d_mask;
@@ -474,12 +573,13 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
 }
 
 int ia3_fit_destroy(ia3_fit* f) {
+  IA3_STAT("ia3_fit_destroy");
   if (!f) return 0;
   if (g_device >= 0) cudaSetDevice(g_device);
   if (f->s && f->s->stream) cudaStreamSynchronize(f->s->stream);
   void* ptrs[] = {f->d_centers, f->d_own, f->d_nbr_start, f->d_nbr_idx, f->d_offs, f->d_mask, f->d_tie_count,
                   f->d_tie_spot, f->d_tie_k, f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info, f->d_rec,
-                  f->d_snap, f->d_vol, f->d_work};
+                  f->d_snap, f->d_vol, f->d_work, f->d_brick_tab};
   for (void* p : ptrs) dev_free(p);
   if (f->e0) cudaEventDestroy(f->e0);
   if (f->e1) cudaEventDestroy(f->e1);
@@ -488,6 +588,7 @@ int ia3_fit_destroy(ia3_fit* f) {
 }
 
 int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
+  IA3_STAT("ia3_fit_first_prepare");
   if (ensure_device()) return -1;
   if (!f) { set_error("null argument"); return -1; }
   cudaStream_t st = f->s->stream;
@@ -516,6 +617,7 @@ int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
 }
 
 int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
+  IA3_STAT("ia3_fit_first_ties");
   if (ensure_device()) return -1;
   if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
   const int64_t n = std::min<int64_t>(cap, f->n_ties);
@@ -533,6 +635,7 @@ int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
 }
 
 int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
+  IA3_STAT("ia3_fit_first_resolve");
   if (ensure_device()) return -1;
   if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
   n = std::min<int64_t>(n, f->n_ties);
@@ -583,8 +686,10 @@ static int build_work(ia3_fit* f, const uint8_t* active, std::vector<int>& bound
 
 int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw, uint8_t* success, int32_t* nfev,
                       int32_t* info) {
+  IA3_STAT("ia3_fit_first_run");
   if (ensure_device()) return -1;
   if (!f) { set_error("null argument"); return -1; }
+  if (!f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   if (!f->prepared && ia3_fit_first_prepare(f, nullptr)) return -1;
   cudaStream_t st = f->s->stream;
   f->d.fp.delta = delta_center;
@@ -605,6 +710,7 @@ int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw,
 
 int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active, float* ps, double* p_raw,
                          uint8_t* success, int32_t* nfev, int32_t* info) {
+  IA3_STAT("ia3_fit_repeat_sweep");
   if (ensure_device()) return -1;
   if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
   cudaStream_t st = f->s->stream;
@@ -623,6 +729,7 @@ int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active,
 int ia3_fit_get_volume(ia3_fit* f, int which, double* out) {
   if (ensure_device()) return -1;
   if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
+  if (!f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   cudaStream_t st = f->s->stream;
   double* tmp = nullptr;
   if (dev_alloc((void**)&tmp, f->s->nvox * 8)) return -1;

@@ -96,6 +96,11 @@ struct WarpExec {
   }
 };
 
+__device__ __forceinline__ long long vol_index(const FitDev& d, int z, int x, int y) {
+  const int b = __ldg(d.brick_tab + ((long long)(z >> 3) * d.nbx + (x >> 3)) * d.nby + (y >> 3));
+  return (long long)b * 512 + (((z & 7) << 6) | ((x & 7) << 3) | (y & 7));
+}
+
 __device__ __forceinline__ double load_im(const void* im, int dtype, long long idx) {
   if (dtype == 0) return (double)reinterpret_cast<const uint16_t*>(im)[idx];
   if (dtype == 1) return (double)reinterpret_cast<const float*>(im)[idx];
@@ -132,7 +137,7 @@ __global__ void k_init_window(FitDev d) {
   const int y = (int)d.centers[3 * s + 2] + d.offs[3 * k + 2];
   if (z < 0 || z >= d.Z || x < 0 || x >= d.X || y < 0 || y >= d.Y) return;
   const long long idx = ((long long)z * d.X + x) * d.Y + y;
-  d.vol[idx] = load_im(d.im, d.im_dtype, idx);   // overlapping windows write the same value
+  d.vol[vol_index(d, z, x, y)] = load_im(d.im, d.im_dtype, idx);   // overlapping windows write the same value
 }
 
 // squared distance exactly as scipy's sqeuclidean_distance_double for 3 components:
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) k_fit(FitDev d, int mode, cons
       const int pos = m + __popc(bal & ((1u << lane) - 1u));
       double v;
       if (mode == 0) v = load_im(d.im, d.im_dtype, idx);
-      else { v = d.vol[idx]; if (had_rec) v = d.rec[s * K + k] + v; }   // im_ = im_rec + im_  (:662)
+      else { v = d.vol[vol_index(d, ic[0] + dz, ic[1] + dx, ic[2] + dy)]; if (had_rec) v = d.rec[s * K + k] + v; }   // im_ = im_rec + im_  (:662)
       dv[pos] = v;
       pk[pos] = pack_vox(dz, dx, dy, k);
     }
@@ -288,9 +293,8 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) k_fit(FitDev d, int mode, cons
       const int dz = (int)(p & 63u) - 32, dx = (int)((p >> 6) & 63u) - 32, dy = (int)((p >> 12) & 63u) - 32;
       const int k = (int)(p >> 18);
       const double f0 = eval_f0<double>(vcd, (double)dz, (double)dx, (double)dy);
-      const long long idx = ((long long)(ic[0] + dz) * d.X + (ic[1] + dx)) * d.Y + (ic[2] + dy);
       d.rec[s * K + k] = f0;
-      d.vol[idx] = dv[pos] - f0;
+      d.vol[vol_index(d, ic[0] + dz, ic[1] + dx, ic[2] + dy)] = dv[pos] - f0;
     }
   }
 }
@@ -318,9 +322,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_subtract(FitDev d, const int* __
     const int z = ic[0] + dz, x = ic[1] + dx, y = ic[2] + dy;
     if (z < 0 || z >= d.Z || x < 0 || x >= d.X || y < 0 || y >= d.Y) continue;
     const double f0 = eval_f0<double>(vcd, (double)dz, (double)dx, (double)dy);
-    const long long idx = ((long long)z * d.X + x) * d.Y + y;
     d.rec[s * d.K + k] = f0;
-    d.vol[idx] -= f0;
+    d.vol[vol_index(d, z, x, y)] -= f0;
   }
 }
 
@@ -462,8 +465,8 @@ __global__ void k_window_copy(FitDev d, double* snap, double* vol_out, int dir) 
   const int y = (int)d.centers[3 * s + 2] + d.offs[3 * k + 2];
   if (z < 0 || z >= d.Z || x < 0 || x >= d.X || y < 0 || y >= d.Y) return;
   const long long idx = ((long long)z * d.X + x) * d.Y + y;
-  if (dir == 0) snap[t] = d.vol[idx];
-  else vol_out[idx] = snap[t];
+  if (dir == 0) snap[t] = d.vol[vol_index(d, z, x, y)];
+  else vol_out[idx] = snap[t];          // vol_out is a dense (Z, X, Y) volume
 }
 int launch_window_copy(const FitDev& d, double* snap, double* vol_out, int dir, cudaStream_t st) {
   const long long total = d.n * d.K;

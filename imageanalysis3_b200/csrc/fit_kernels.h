@@ -10,7 +10,12 @@ namespace ia3 {
 struct FitDev {
   // image / volumes
   const void* im; int im_dtype;       // original stack (u16 / f32 / f64)
-  double* vol;                        // float64 work volume (im_subtr -> im_add); only window voxels are initialised
+  // float64 work volume (im_subtr -> im_add), stored sparsely: only 8x8x8 bricks touched by some
+  // seed's window exist.  brick_tab[(bz * nbx + bx) * nby + by] = brick number (or -1); a brick is
+  // 512 doubles at vol + 512 * number.  A dense copy would be 1.7 GB per 50x2048x2048 stack.
+  double* vol;
+  const int* brick_tab;
+  int nbx, nby;
   int Z, X, Y;
   // seeds
   long long n;

@@ -204,6 +204,8 @@ def fit_fov_image(im, channel, seeds=None,
         _seeds = np.array(seeds)[:, :len(np.shape(im))]
         if verbose:
             print(f"{len(_seeds)} given, ", end='')
+    if stack is not None:
+        stack.trim(1)          # the seed stage's work volumes go back to the other stacks in flight
     if len(_seeds) == 0:
         return np.array([])
     if seed_mask is not None:
@@ -215,6 +217,8 @@ def fit_fov_image(im, channel, seeds=None,
 
     fitter = Fitting_v4.iter_fit_seed_points(im, _seeds.T, radius_fit=fit_radius, _stack=stack, **fitting_args)
     fitter.firstfit()
+    if stack is not None:
+        stack.trim(2)          # repeatfit only touches the sparse work volume, not the image
     fitter.repeatfit()
     _spots = np.array(fitter.ps)
     _spots = _spots[np.sum(np.isnan(_spots), axis=1) == 0]

@@ -33,6 +33,9 @@ int ia3_version(void);
 int ia3_device_sm_count(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 int64_t ia3_launch_count(void);
+/* wall-clock time spent inside the entry points so far (text table; only filled when the process was
+ * started with IA3_STATS=1) */
+int ia3_debug_stats(char* buf, int cap);
 /* CUDA-event stopwatch on the library's stream (all kernels and copies of this process are issued
  * on it): start records an event after a device sync, stop returns the elapsed device time. */
 int ia3_timer_start(void);
@@ -46,6 +49,11 @@ int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack**
 /* Wrap a stack that is already in device memory (no copy, not owned). */
 int ia3_stack_wrap_device(const void* d_im, int dtype, int Z, int X, int Y, ia3_stack** out);
 int ia3_stack_destroy(ia3_stack* s);
+/* Give device memory back early (to the library's allocation cache, i.e. to the other stacks in
+ * flight): what & 1 = the seed stage's work volumes and candidate list (after ia3_seed_fetch);
+ * what & 2 = the library's own copy of the image (after ia3_fit_first_run: repeat sweeps only touch
+ * the sparse work volume).  A later call that needs what was released fails with an error. */
+int ia3_stack_trim(ia3_stack* s, int what);
 
 /* ---- seed stage ------------------------------------------------------------------------ */
 typedef struct {

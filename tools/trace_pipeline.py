@@ -17,6 +17,8 @@ from imageanalysis3_b200.synth import synth_torch
 
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+MODE = sys.argv[3] if len(sys.argv) > 3 else "both"      # both | seed | fit
+QUIET = len(sys.argv) > 4
 SHAPE = (50, 2048, 2048)
 _lib.init(0)
 dev = torch.device("cuda", 0)
@@ -36,17 +38,28 @@ def step(i):
         ev.append((name, 1e3 * (t0 - T0), 1e3 * (time.perf_counter() - T0)))
     t = time.perf_counter()
     st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
-    seeds = fitting.get_seeds(host, max_num_seeds=None, th_seed=300.0, _stack=st)
+    if MODE in ("fit", "first"):
+        seeds = SEEDS[i % len(stacks)]
+    else:
+        seeds = fitting.get_seeds(host, max_num_seeds=None, th_seed=300.0, _stack=st)
+        st.trim(1)
     mark("seed", t); t = time.perf_counter()
+    if MODE == "seed":
+        trace.append((i, threading.get_ident() % 1000, ev))
+        return len(seeds)
     f = Fitting_v4.iter_fit_seed_points(host, seeds.T, _stack=st)
     f.firstfit()
     mark("first", t); t = time.perf_counter()
+    if MODE == "first":
+        trace.append((i, threading.get_ident() % 1000, ev))
+        return len(seeds)
     f.repeatfit()
     mark(f"repeat x{f.n_iter}", t)
     trace.append((i, threading.get_ident() % 1000, ev))
     return len(seeds)
 
 
+SEEDS = [fitting.get_seeds(h, max_num_seeds=None, th_seed=300.0) for _, h in stacks]
 pool = ThreadPoolExecutor(D)
 list(pool.map(step, range(D)))       # warm-up
 trace.clear()
@@ -54,5 +67,8 @@ T0 = time.perf_counter()
 list(pool.map(step, range(K)))
 total = 1e3 * (time.perf_counter() - T0)
 for i, tid, ev in sorted(trace):
+    if QUIET:
+        break
     print(f"step {i} thr {tid:3d}: " + "  ".join(f"{n} {a:7.1f}-{b:7.1f}" for n, a, b in ev))
-print(f"D={D} K={K} total {total:.1f} ms -> {total / K:.1f} ms/step")
+print(_lib.debug_stats())
+print(f"mode={MODE} D={D} K={K} total {total:.1f} ms -> {total / K:.1f} ms/step")
