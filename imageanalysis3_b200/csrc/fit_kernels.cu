@@ -43,6 +43,7 @@ struct WarpExec {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
   }
+  __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(FULL, v, src); }
   __device__ __forceinline__ double allmax(double v) const {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));

@@ -18,6 +18,7 @@ struct SpotShared {
   LMState st;
   VoxConsts<T> vc;
   double Ag[NTRI + NP];   // J^T J (packed upper triangle) followed by J^T f
+  double etab[NEXP];      // exp table of the parameter transforms (one slot per lane)
   double x0[NP];
   double small10[10], large10[10];
 };
@@ -193,34 +194,36 @@ struct FitResult {
   int nfev, njev, info;
 };
 
+// Per-voxel constants at x, by the whole warp: the 19 FP64 exps one per lane, the rest (divisions,
+// square roots, the 36 quadratic-form coefficients) by lane 0.  Always with the Jacobian constants:
+// an accepted trial point is the next Jacobian point, so lmder's pair "f(x + p), then J(x + p)" costs
+// one call instead of two.
+template <typename T, typename Exec>
+IA3_HD void build_consts_par(Exec& ex, const FitParams& fp, const double* cen_est, const double* origin,
+                             const double* x, SpotShared<T>& sh) {
+  for (int i = ex.lane(); i < NEXP; i += Exec::W) sh.etab[i] = (i == 1) ? 0.0 : exp(exp_slot_arg(fp, x, i));
+  ex.sync();
+  if (ex.lane() == 0) finish_consts<T>(fp, cen_est, origin, x, sh.etab, true, sh.vc);
+  ex.sync();
+}
+
 // Runs leastsq from sh.x0.  Every lane must call this; results are in sh.st (shared) after return.
 template <typename T, typename Exec, typename Vox>
 IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen_est,
                    const double* origin, const Vox& vox, SpotShared<T>& sh) {
   LMState& st = sh.st;
-  // f(x0)
-  if (ex.lane() == 0) {
-    build_consts<T>(fp, cen_est, origin, sh.x0, false, sh.vc);
-  }
-  ex.sync();
+  build_consts_par<T>(ex, fp, cen_est, origin, sh.x0, sh);        // f(x0); the constants also serve J(x0)
   const double fn0 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
   lm_init(ex, st, sh.x0, fn0);
   for (;;) {
-    // Jacobian at st.x
-    if (ex.lane() == 0) {
-      build_consts<T>(fp, cen_est, origin, st.x, true, sh.vc);
-    }
-    ex.sync();
+    // Jacobian at st.x: sh.vc already holds the constants of st.x (x0, or the accepted trial point)
     pass_jacobian<T>(ex, sh.vc, vox, sh.Ag);
     ex.sync();
     if (!lm_outer(ex, st, cfg, sh.Ag, sh.Ag + NTRI)) break;
     int action;
     for (;;) {
       lm_propose(ex, st);
-      if (ex.lane() == 0) {
-        build_consts<T>(fp, cen_est, origin, st.xt, false, sh.vc);
-      }
-      ex.sync();
+      build_consts_par<T>(ex, fp, cen_est, origin, st.xt, sh);
       const double fn1 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
       action = lm_judge(ex, st, cfg, fn1);
       if (action != LM_RETRY) break;

@@ -47,56 +47,70 @@ struct ModelConsts {
 // ~20 call sites and an inlined exp is ~60 instructions.
 IA3_HDN double exp_s(double v) { return exp(v); }
 
-IA3_HD double v4_sigmoid_guarded(double a, double lo_val, double hi_val, double num, double off) {
-  // value = num/(1+exp(a)) + off with the reference's saturation guards at |a| >= log(DBL_MAX)
+// ---- the transcendental part of the parameter transforms, one exp per slot -------------------
+// All FP64 exps a model_consts call needs, as a table so that a warp evaluates them in parallel
+// (one slot per lane, fit_spot.h: build_consts_par) instead of one lane evaluating 19 in a row:
+//   0 exp(bk) as used by calc_f (v4: bk clipped)   2..4 exp(xp|yp|zp) (v3: exp(-xp) ...)
+//   5..7 exp(w1..w3)   8 exp(pp)   9 exp(tp)        10 exp(bk) unclipped (calc_jac f1)
+//   11..13 exp(-|xp|..)   14..16 exp(-|w1|..)   17 exp(-|pp|/2)   18 exp(-|tp|/2)       (1 unused)
+constexpr int NEXP = 19;
+
+IA3_HD double exp_slot_arg(const FitParams& fp, const double* x, int i) {
+  const bool v4 = (fp.personality == 4);
+  if (i == 0) {
+    const double bk = x[0];
+    if (!v4) return bk;
+    return bk < -709.78 ? -709.78 : (bk > 709.78 ? 709.78 : bk);      // np.clip, Fitting_v4.py:287 (NaN passes)
+  }
+  if (i < 10) return (!v4 && i >= 2 && i <= 4) ? -x[i] : x[i];
+  if (i == 10) return x[0];
+  const double a = -fabs(x[i - 9]);
+  return (i >= 17) ? a / 2 : a;
+}
+
+IA3_HD double v4_sigmoid_guarded(double a, double ea, double lo_val, double hi_val, double num, double off) {
+  // value = num/(1+exp(a)) + off with the reference's saturation guards at |a| >= log(DBL_MAX); ea = exp(a)
   const double LOGMAX = 709.782712893384;  // np.log(np.finfo(np.float64).max)
   if (a >= LOGMAX) return lo_val;
   if (a <= -LOGMAX) return hi_val;
-  return num / (1.0 + exp_s(a)) + off;
+  return num / (1.0 + ea) + off;
 }
 
-IA3_HD double norm_w_fn(double w, double minw, double maxw) {
+IA3_HD double norm_w_fn(double w, double e /* exp(-|w|) */, double minw, double maxw) {
   // Fitting_v4.py:369-375 / Fitting_v3.py:232-238
-  if (w > 0) {
-    double e = exp_s(-w);
-    double d = maxw * e + minw;
-    return 0.5 * (maxw - minw) * e / (d * d);
-  } else {
-    double e = exp_s(w);
-    double d = minw * e + maxw;
-    return 0.5 * (maxw - minw) * e / (d * d);
-  }
+  const double d = (w > 0) ? maxw * e + minw : minw * e + maxw;
+  return 0.5 * (maxw - minw) * e / (d * d);
 }
 
-// want_jac = false skips the Jacobian-only constants.
-IA3_HD void model_consts(const FitParams& fp, const double* cen_est, const double* x, bool want_jac,
-                         ModelConsts& mc) {
-  const double bk = x[0], h = x[1], xp = x[2], yp = x[3], zp = x[4];
+// want_jac = false skips the Jacobian-only constants.  e[NEXP]: exp table at x (exp_slot_arg).
+IA3_HD void model_consts_e(const FitParams& fp, const double* cen_est, const double* x, const double* e, bool want_jac,
+                           ModelConsts& mc) {
+  const double h = x[1], xp = x[2], yp = x[3], zp = x[4];
   const double w1 = x[5], w2 = x[6], w3 = x[7], pp = x[8], tp = x[9];
   const bool v4 = (fp.personality == 4);
   const double d = fp.delta, minw = fp.min_w2, maxw = fp.max_w2, dws = maxw - minw;
   double t, p, ws1, ws2, ws3;
   if (v4) {
-    t = v4_sigmoid_guarded(tp, -1.0, 1.0, 2.0, -1.0);
-    p = v4_sigmoid_guarded(pp, -1.0, 1.0, 2.0, -1.0);
-    ws1 = v4_sigmoid_guarded(w1, minw, dws + minw, dws, minw);
-    ws2 = v4_sigmoid_guarded(w2, minw, dws + minw, dws, minw);
-    ws3 = v4_sigmoid_guarded(w3, minw, dws + minw, dws, minw);
+    t = v4_sigmoid_guarded(tp, e[9], -1.0, 1.0, 2.0, -1.0);
+    p = v4_sigmoid_guarded(pp, e[8], -1.0, 1.0, 2.0, -1.0);
+    ws1 = v4_sigmoid_guarded(w1, e[5], minw, dws + minw, dws, minw);
+    ws2 = v4_sigmoid_guarded(w2, e[6], minw, dws + minw, dws, minw);
+    ws3 = v4_sigmoid_guarded(w3, e[7], minw, dws + minw, dws, minw);
     // c = 2*delta/(1+exp(c_)) - delta + center_est   (left-to-right as written, :198)
     const double LOGMAX = 709.782712893384;
     const double raw[3] = {xp, yp, zp};
     for (int i = 0; i < 3; ++i) {
       if (raw[i] >= LOGMAX) mc.c[i] = -d + cen_est[i];
       else if (raw[i] <= -LOGMAX) mc.c[i] = d + cen_est[i];
-      else mc.c[i] = 2.0 * d / (1.0 + exp_s(raw[i])) - d + cen_est[i];
+      else mc.c[i] = 2.0 * d / (1.0 + e[2 + i]) - d + cen_est[i];
     }
   } else {
-    t = 2.0 / (1.0 + exp_s(tp)) - 1.0;
-    p = 2.0 / (1.0 + exp_s(pp)) - 1.0;
-    ws1 = dws / (1.0 + exp_s(w1)) + minw;
-    ws2 = dws / (1.0 + exp_s(w2)) + minw;
-    ws3 = dws / (1.0 + exp_s(w3)) + minw;
-    const double e0 = exp_s(-xp), e1 = exp_s(-yp), e2 = exp_s(-zp);
+    t = 2.0 / (1.0 + e[9]) - 1.0;
+    p = 2.0 / (1.0 + e[8]) - 1.0;
+    ws1 = dws / (1.0 + e[5]) + minw;
+    ws2 = dws / (1.0 + e[6]) + minw;
+    ws3 = dws / (1.0 + e[7]) + minw;
+    const double e0 = e[2], e1 = e[3], e2 = e[4];             // exp(-xp), exp(-yp), exp(-zp)
     mc.c[0] = 2.0 * d * e0 / (1.0 + e0) - d + cen_est[0];
     mc.c[1] = 2.0 * d * e1 / (1.0 + e1) - d + cen_est[1];
     mc.c[2] = 2.0 * d * e1 / (1.0 + e2) - d + cen_est[2];   // Fitting_v3.py:86 (sic)
@@ -111,28 +125,23 @@ IA3_HD void model_consts(const FitParams& fp, const double* cen_est, const doubl
   mc.q[4] = 2 * p * pc * tc * (s3 - s1);
   mc.q[5] = 2 * p * pc * t * (s3 - s1);
   mc.h = h;
-  if (v4) {
-    double bkc = bk < -709.78 ? -709.78 : (bk > 709.78 ? 709.78 : bk);  // np.clip, :287 (NaN passes through)
-    mc.ebk_f = exp_s(bkc);
-  } else {
-    mc.ebk_f = exp_s(bk);
-  }
+  mc.ebk_f = e[0];
   mc.pen = 0.0;
   if (!v4 && fp.weight_sigma > 0) {
     const double d0 = fp.init_wt[0] - w1, d1 = fp.init_wt[1] - w2, d2 = fp.init_wt[2] - w3;
     mc.pen = fp.weight_sigma * sqrt(d0 * d0 + d1 * d1 + d2 * d2);
   }
   if (!want_jac) return;
-  mc.ebk_j = exp_s(bk);
+  mc.ebk_j = e[10];
   {
-    const double ex = exp_s(-fabs(xp)), ey = exp_s(-fabs(yp)), ez = exp_s(-fabs(zp));
+    const double ex = e[11], ey = e[12], ez = e[13];
     mc.ncen[0] = -d * ex / ((1 + ex) * (1 + ex));
     mc.ncen[1] = -d * ey / ((1 + ey) * (1 + ey));
     mc.ncen[2] = -d * ez / ((1 + ez) * (1 + ez));
   }
-  const double nw1 = norm_w_fn(w1, minw, maxw), nw2 = norm_w_fn(w2, minw, maxw), nw3 = norm_w_fn(w3, minw, maxw);
-  const double e_p = exp_s(-fabs(pp) / 2), norm_p = e_p / (1 + e_p * e_p);
-  const double e_t = exp_s(-fabs(tp) / 2), norm_t = e_t / (1 + e_t * e_t);
+  const double nw1 = norm_w_fn(w1, e[14], minw, maxw), nw2 = norm_w_fn(w2, e[15], minw, maxw), nw3 = norm_w_fn(w3, e[16], minw, maxw);
+  const double e_p = e[17], norm_p = e_p / (1 + e_p * e_p);
+  const double e_t = e[18], norm_t = e_t / (1 + e_t * e_t);
   // order of the six monomials: xt2, yt2, zt2, xtyt, xtzt, ytzt
   // f6 (Fitting_v4.py:355)
   mc.a6[0] = -pc2 * tc2 * nw1; mc.a6[1] = -pc2 * t2 * nw1; mc.a6[2] = -p2 * nw1;
@@ -164,6 +173,15 @@ IA3_HD void model_consts(const FitParams& fp, const double* cen_est, const doubl
   }
 }
 
+
+// serial convenience form (every exp evaluated here)
+IA3_HD void model_consts(const FitParams& fp, const double* cen_est, const double* x, bool want_jac, ModelConsts& mc) {
+  double e[NEXP];
+  const int n = want_jac ? NEXP : 10;
+  for (int i = 0; i < n; ++i) e[i] = (i == 1) ? 0.0 : exp_s(exp_slot_arg(fp, x, i));
+  model_consts_e(fp, cen_est, x, e, want_jac, mc);
+}
+
 // Per-voxel constants narrowed to the evaluation type, with the centre expressed relative to
 // an integer origin so that the float mode keeps sub-pixel accuracy at x,y ~ 2000.
 template <typename T>
@@ -193,6 +211,15 @@ IA3_HDN void build_consts(const FitParams& fp, const double* cen_est, const doub
                           bool want_jac, VoxConsts<T>& vc) {
   ModelConsts mc;
   model_consts(fp, cen_est, x, want_jac, mc);
+  narrow_consts<T>(mc, origin, want_jac, vc);
+}
+
+// the non-transcendental rest of build_consts, given the exp table (shared memory) of a warp
+template <typename T>
+IA3_HDN void finish_consts(const FitParams& fp, const double* cen_est, const double* origin, const double* x,
+                           const double* e, bool want_jac, VoxConsts<T>& vc) {
+  ModelConsts mc;
+  model_consts_e(fp, cen_est, x, e, want_jac, mc);
   narrow_consts<T>(mc, origin, want_jac, vc);
 }
 
@@ -244,9 +271,9 @@ IA3_HDN void natural_params(const FitParams& fp, const double* cen_est, const do
   const double minw = fp.min_w2, dws = fp.max_w2 - fp.min_w2;
   double ws[3], t, p;
   if (v4) {
-    for (int i = 0; i < 3; ++i) ws[i] = v4_sigmoid_guarded(x[5 + i], minw, dws + minw, dws, minw);
-    t = v4_sigmoid_guarded(x[9], -1.0, 1.0, 2.0, -1.0);
-    p = v4_sigmoid_guarded(x[8], -1.0, 1.0, 2.0, -1.0);
+    for (int i = 0; i < 3; ++i) ws[i] = v4_sigmoid_guarded(x[5 + i], exp_s(x[5 + i]), minw, dws + minw, dws, minw);
+    t = v4_sigmoid_guarded(x[9], exp_s(x[9]), -1.0, 1.0, 2.0, -1.0);
+    p = v4_sigmoid_guarded(x[8], exp_s(x[8]), -1.0, 1.0, 2.0, -1.0);
   } else {
     for (int i = 0; i < 3; ++i) ws[i] = dws / (1.0 + exp_s(x[5 + i])) + minw;
     t = 2.0 / (1.0 + exp_s(x[9])) - 1.0;

@@ -42,8 +42,10 @@ struct LMState {
   double acn[NP];      // column norms of J                      (qrfac acnorm / lmder wa2)
   double qtf[NP];      // first n entries of Q^T f
   double R[NP][NP];    // upper triangle: R (pivoted order)
-  double B0[NTRI];     // R^T R, packed upper triangle (pivoted order)
-  double S[NTRI];      // Cholesky factor of R^T R + par D^2, packed upper triangle
+  double B0[NP][NP];   // R^T R, upper triangle (pivoted order)
+  double S[NP][NP];    // Cholesky factor of R^T R + par D^2, upper triangle
+  double rinv[NP];     // 1 / R[j][j] (0 where the pivot is 0)
+  double sinv[NP];     // 1 / S[j][j]
   double rq[NP];       // R^T qtf (pivoted order)
   double rd[NP], gp[NP], y[NP];
   double w1[NP], w2[NP], w3[NP];
@@ -58,29 +60,32 @@ IA3_HD double enorm_n(const double* v, int n) {
   return sqrt(s);
 }
 
-// B0 = R^T R and rq = R^T qtf (both in pivoted order) from st.R / st.qtf
+// B0 = R^T R, rq = R^T qtf (both in pivoted order) and rinv from st.R / st.qtf
 template <typename Ex>
 IA3_HDN void lm_post_factor(Ex& ex, LMState& st) {
-  for (int e = ex.lane(); e < NTRI + NP; e += Ex::W) {
-    if (e < NTRI) {
-      int a = 0, rem = e;
-      while (rem >= NP - a) { rem -= NP - a; ++a; }
-      const int b = a + rem;                     // entry (a, b), a <= b
+  for (int e = ex.lane(); e < NP * NP + NP; e += Ex::W) {
+    if (e < NP * NP) {
+      const int a = e / NP, b = e - a * NP;
+      if (b < a) continue;                          // upper triangle only
       double s = 0.0;
       for (int i = 0; i <= a; ++i) s += st.R[i][a] * st.R[i][b];
-      st.B0[e] = s;
+      st.B0[a][b] = s;
     } else {
-      const int j = e - NTRI;
+      const int j = e - NP * NP;
       double s = 0.0;
       for (int i = 0; i <= j; ++i) s += st.R[i][j] * st.qtf[i];
       st.rq[j] = s;
+      const double rjj = st.R[j][j];
+      st.rinv[j] = (rjj != 0.0) ? 1.0 / rjj : 0.0;
     }
   }
   ex.sync();
 }
 
 // Pivoted Cholesky of the packed symmetric A (55 entries) with MINPACK qrfac's pivoting.
-// Outputs st.R (upper), st.ipvt, st.acn, st.qtf = R^-T (g permuted), st.B0 = R^T R, st.rq = R^T qtf.
+// Outputs st.R (upper), st.ipvt, st.acn, st.qtf = R^-T (g permuted), and lm_post_factor's products.
+// Step j: lane k - j forms the entry (j, k) of the Schur complement (lane 0 the pivot itself), the
+// pivot's reciprocal square root is broadcast, one barrier per step.
 template <typename Ex>
 IA3_HDN void lm_factor(Ex& ex, LMState& st, const double* A, const double* g) {
   const int ln = ex.lane();
@@ -93,11 +98,12 @@ IA3_HDN void lm_factor(Ex& ex, LMState& st, const double* A, const double* g) {
     for (int j = 0; j < NP; ++j) st.R[i][j] = 0.0;
   }
   ex.sync();
+#pragma unroll 1
   for (int j = 0; j < NP; ++j) {
     int kmax = j;
     for (int k = j + 1; k < NP; ++k) if (st.rd[k] > st.rd[kmax]) kmax = k;
-    ex.sync();                                   // everybody has read rd[] before it is permuted
     if (kmax != j) {
+      ex.sync();                                 // everybody has read rd[] before it is permuted
       for (int i = ln; i < j; i += Ex::W) { const double t = st.R[i][j]; st.R[i][j] = st.R[i][kmax]; st.R[i][kmax] = t; }
       if (ln == 0) {
         { const double t = st.rd[j]; st.rd[j] = st.rd[kmax]; st.rd[kmax] = t; }
@@ -113,13 +119,14 @@ IA3_HDN void lm_factor(Ex& ex, LMState& st, const double* A, const double* g) {
       continue;
     }
     const double rjj = sqrt(d);
+    const double inv = 1.0 / rjj;
     const int pj = st.ipvt[j];
     for (int k = j + ln; k < NP; k += Ex::W) {
       if (k == j) { st.R[j][j] = rjj; continue; }
       const int pk = st.ipvt[k];
       double s = A[pj < pk ? tri(pj, pk) : tri(pk, pj)];
       for (int i = 0; i < j; ++i) s -= st.R[i][j] * st.R[i][k];
-      const double r = s / rjj;
+      const double r = s * inv;
       st.R[j][k] = r;
       st.rd[k] -= r * r;
     }
@@ -128,6 +135,7 @@ IA3_HDN void lm_factor(Ex& ex, LMState& st, const double* A, const double* g) {
   // qtf = R^-T gp (forward substitution in axpy form; rows with zero pivot give 0)
   for (int k = ln; k < NP; k += Ex::W) st.w1[k] = st.gp[k];
   ex.sync();
+#pragma unroll 1
   for (int j = 0; j < NP; ++j) {
     const double rjj = st.R[j][j];
     const double q = (rjj != 0.0) ? st.w1[j] / rjj : 0.0;
@@ -139,40 +147,51 @@ IA3_HDN void lm_factor(Ex& ex, LMState& st, const double* A, const double* g) {
 }
 
 // Solve min |R P^T x - qtf|^2 + par |D x|^2 (MINPACK qrsolv's job): S = chol(R^T R + par D^2),
-// z = S^-1 S^-T rq, x[ipvt[j]] = z[j].  Leaves S in st.S; x in xout (unpermuted); uses st.w3, st.y.
+// z = S^-1 S^-T rq, x[ipvt[j]] = z[j].  Leaves S / sinv in st; x in xout (unpermuted); uses st.w3, st.y.
 template <typename Ex>
 IA3_HDN void lm_damped_solve(Ex& ex, LMState& st, double par, double* xout) {
   const int ln = ex.lane();
-  // left-looking Cholesky: at step j every lane forms the pivot itself, lane k-j the entry (j, k)
+  // left-looking Cholesky: at step j lane k - j forms entry (j, k) (lane 0 the pivot), the reciprocal
+  // of the pivot's square root is broadcast from lane 0
+#pragma unroll 1
   for (int j = 0; j < NP; ++j) {
-    const double dj = st.diag[st.ipvt[j]];
-    double d = st.B0[tri(j, j)] + par * (dj * dj);
-    for (int i = 0; i < j; ++i) { const double v = st.S[tri(i, j)]; d -= v * v; }
-    const double sjj = (d > 0.0) ? sqrt(d) : 0.0;
-    for (int k = j + ln; k < NP; k += Ex::W) {
-      if (k == j) { st.S[tri(j, j)] = sjj; continue; }
-      double v = st.B0[tri(j, k)];
-      for (int i = 0; i < j; ++i) v -= st.S[tri(i, j)] * st.S[tri(i, k)];
-      st.S[tri(j, k)] = (sjj != 0.0) ? v / sjj : 0.0;
+    const int k0 = j + ln;
+    double v = 0.0;
+    if (k0 < NP) {
+      v = st.B0[j][k0];
+      if (ln == 0) { const double dj = st.diag[st.ipvt[j]]; v += par * (dj * dj); }
+      for (int i = 0; i < j; ++i) v -= st.S[i][j] * st.S[i][k0];
+    }
+    double sjj = 0.0, inv = 0.0;
+    if (ln == 0) { sjj = (v > 0.0) ? sqrt(v) : 0.0; inv = (sjj != 0.0) ? 1.0 / sjj : 0.0; }
+    inv = ex.bcast(inv, 0);
+    if (k0 < NP) {
+      if (ln == 0) { st.S[j][j] = sjj; st.sinv[j] = inv; }
+      else st.S[j][k0] = v * inv;
+    }
+    for (int k = k0 + Ex::W; k < NP; k += Ex::W) {        // executors narrower than NP lanes (host: W = 1)
+      double v2 = st.B0[j][k];
+      for (int i = 0; i < j; ++i) v2 -= st.S[i][j] * st.S[i][k];
+      st.S[j][k] = v2 * inv;
     }
     ex.sync();
   }
   // forward: S^T y = rq  (axpy form)
   for (int k = ln; k < NP; k += Ex::W) st.w3[k] = st.rq[k];
   ex.sync();
+#pragma unroll 1
   for (int j = 0; j < NP; ++j) {
-    const double sjj = st.S[tri(j, j)];
-    const double y = (sjj != 0.0) ? st.w3[j] / sjj : 0.0;
+    const double y = st.w3[j] * st.sinv[j];
     if (ln == 0) st.y[j] = y;
-    for (int k = j + 1 + ln; k < NP; k += Ex::W) st.w3[k] -= st.S[tri(j, k)] * y;
+    for (int k = j + 1 + ln; k < NP; k += Ex::W) st.w3[k] -= st.S[j][k] * y;
     ex.sync();
   }
   // backward: S z = y
+#pragma unroll 1
   for (int j = NP - 1; j >= 0; --j) {
-    const double sjj = st.S[tri(j, j)];
-    const double z = (sjj != 0.0) ? st.y[j] / sjj : 0.0;
+    const double z = st.y[j] * st.sinv[j];
     if (ln == 0) xout[st.ipvt[j]] = z;
-    for (int i = ln; i < j; i += Ex::W) st.y[i] -= st.S[tri(i, j)] * z;
+    for (int i = ln; i < j; i += Ex::W) st.y[i] -= st.S[i][j] * z;
     ex.sync();
   }
 }
@@ -194,9 +213,10 @@ IA3_HDN void lm_lmpar(Ex& ex, LMState& st, double* xout) {
   }
   ex.sync();
   // Gauss-Newton direction: back substitution with the non-singular leading block of R
+#pragma unroll 1
   for (int k = 0; k < nsing; ++k) {
     const int j = nsing - 1 - k;
-    const double temp = wa1[j] / r[j][j];
+    const double temp = wa1[j] * st.rinv[j];
     if (ln == 0) xout[st.ipvt[j]] = temp;
     for (int i = ln; i < j; i += Ex::W) wa1[i] -= r[i][j] * temp;
     ex.sync();
@@ -213,8 +233,9 @@ IA3_HDN void lm_lmpar(Ex& ex, LMState& st, double* xout) {
     for (int j = ln; j < NP; j += Ex::W) { const int l = st.ipvt[j]; wa1[j] = st.diag[l] * (wa2[l] / dxnorm); }
     ex.sync();
     double n2 = 0.0;
+#pragma unroll 1
     for (int j = 0; j < NP; ++j) {               // R^T w = wa1, axpy form; only |w| is needed
-      const double t = wa1[j] / r[j][j];
+      const double t = wa1[j] * st.rinv[j];
       n2 += t * t;
       for (int k = j + 1 + ln; k < NP; k += Ex::W) wa1[k] -= r[j][k] * t;
       ex.sync();
@@ -247,10 +268,11 @@ IA3_HDN void lm_lmpar(Ex& ex, LMState& st, double* xout) {
     for (int j = ln; j < NP; j += Ex::W) { const int l = st.ipvt[j]; wa1[j] = st.diag[l] * (wa2[l] / dxnorm); }
     ex.sync();
     double n2 = 0.0;
+#pragma unroll 1
     for (int j = 0; j < NP; ++j) {               // S^T w = wa1, axpy form; only |w| is needed
-      const double t = wa1[j] / st.S[tri(j, j)];
+      const double t = wa1[j] * st.sinv[j];
       n2 += t * t;
-      for (int k = j + 1 + ln; k < NP; k += Ex::W) wa1[k] -= st.S[tri(j, k)] * t;
+      for (int k = j + 1 + ln; k < NP; k += Ex::W) wa1[k] -= st.S[j][k] * t;
       ex.sync();
     }
     temp = sqrt(n2);

@@ -17,6 +17,7 @@ struct SerialExec {
   double allsum(double v) const { return v; }
   int allsum_int(int v) const { return v; }
   double allmax(double v) const { return v; }
+  double bcast(double v, int) const { return v; }
   void argmin(double&, int&) const {}
   struct TakenMask {
     std::vector<bool> bits;
