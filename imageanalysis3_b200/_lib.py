@@ -117,7 +117,10 @@ def timer_stop():
     return float(ms.value)
 
 
-def debug_stats():
+def debug_stats(reset=False):
+    if reset:
+        load().ia3_debug_stats(None, 0)
+        return ""
     buf = C.create_string_buffer(8192)
     load().ia3_debug_stats(buf, 8192)
     return buf.value.decode()

@@ -44,6 +44,55 @@ static int global_stream(cudaStream_t* out) {
   *out = g_stream;
   return 0;
 }
+// Events and pinned staging buffers are pooled like streams and device blocks: in steady state a stack
+// in flight makes no call that creates or destroys a driver object (those calls wait for the device
+// while other stacks' kernels run, and every other host thread then queues behind them).
+static std::vector<cudaEvent_t> g_event_pool;
+static int acquire_event(cudaEvent_t* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_event_pool.empty()) { *out = g_event_pool.back(); g_event_pool.pop_back(); return 0; }
+  }
+  IA3_CUDA(cudaEventCreate(out));
+  return 0;
+}
+static void release_event(cudaEvent_t e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_event_pool.push_back(e);
+}
+static std::multimap<size_t, void*> g_host_free;
+static std::unordered_map<void*, size_t> g_host_sizes;
+static int host_alloc(void** p, size_t bytes) {
+  size_t cls = 4096;
+  while (cls < bytes) cls <<= 1;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_host_free.find(cls);
+    if (it != g_host_free.end()) { *p = it->second; g_host_free.erase(it); return 0; }
+  }
+  IA3_CUDA(cudaMallocHost(p, cls));
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_host_sizes[*p] = cls;
+  return 0;
+}
+static void host_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_host_sizes.find(p);
+  if (it != g_host_sizes.end()) g_host_free.emplace(it->second, p);
+}
+static int reserve_pinned(void** buf, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  host_free(*buf);
+  *buf = nullptr; *cap = 0;
+  if (host_alloc(buf, bytes)) return -1;
+  size_t cls = 4096;
+  while (cls < bytes) cls <<= 1;
+  *cap = cls;
+  return 0;
+}
+
 static void release_stream(cudaStream_t st) {
   if (!st) return;
   std::lock_guard<std::mutex> lk(g_mu);
@@ -87,14 +136,27 @@ static std::unordered_map<void*, size_t> g_sizes;
 static size_t g_cached_bytes = 0;
 static const size_t kCacheLimit = (size_t)150 << 30;
 
+// Request sizes are rounded up to size classes (powers of two up to 1 MiB, then eight classes per
+// octave: at most 12.5 % over-allocation), and a freed block is reused only for its own class.  After
+// a warm-up every allocation of a stack in flight is a cache hit: cudaMalloc while other stacks'
+// kernels are running was measured at ~150 ms per call (it waits for the device), which throttled the
+// whole pipeline.
+static size_t size_class(size_t bytes) {
+  if (bytes < 256) bytes = 256;
+  size_t p2 = 256;
+  while (p2 < bytes) p2 <<= 1;
+  if (p2 <= ((size_t)1 << 20)) return p2;
+  const size_t step = p2 >> 4;                   // p2/2 < bytes <= p2: eight steps of p2/16 above p2/2
+  return (bytes + step - 1) / step * step;
+}
+
 int dev_alloc(void** p, size_t bytes) {
   IA3_STAT("dev_alloc");
-  if (bytes == 0) bytes = 256;
-  bytes = (bytes + 255) / 256 * 256;
+  bytes = size_class(bytes);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_free.lower_bound(bytes);
-    if (it != g_free.end() && it->first <= bytes + bytes / 4 + (1 << 20)) {
+    auto it = g_free.lower_bound(bytes);         // best fit, at most twice the class (or 1 MiB for small ones)
+    if (it != g_free.end() && it->first <= std::max<size_t>(2 * bytes, (size_t)1 << 20)) {
       *p = it->second;
       g_cached_bytes -= it->first;
       g_free.erase(it);
@@ -210,6 +272,9 @@ struct ia3_fit {
   double* d_rec = nullptr; double* d_snap = nullptr; double* d_vol = nullptr; int* d_brick_tab = nullptr;
   int64_t n_bricks = 0;
   int* d_work = nullptr; size_t work_cap = 0;
+  void* h_stage = nullptr; size_t stage_cap = 0;      // pinned staging, device -> host (results, ties)
+  void* h_up = nullptr; size_t up_cap = 0;            // pinned staging, host -> device (inputs, work lists)
+  uint8_t* d_keep = nullptr; size_t keep_cap = 0;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   float last_ms = 0.f;
 };
@@ -235,6 +300,10 @@ int ia3_device_sm_count(void) {
 }
 int64_t ia3_launch_count(void) { return g_launches.load(); }
 int ia3_debug_stats(char* buf, int cap) {
+  if (!buf || cap <= 0) {                        // reset
+    for (int i = 0; i < g_nstats.load(); ++i) { g_stats[i].ns = 0; g_stats[i].calls = 0; }
+    return 0;
+  }
   int off = 0;
   const int n = g_nstats.load();
   for (int i = 0; i < n && off < cap - 96; ++i)
@@ -268,7 +337,7 @@ static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
   s->dtype = dtype; s->Z = Z; s->X = X; s->Y = Y;
   s->nvox = (size_t)Z * X * Y;
   if (acquire_stream(&s->stream)) return -1;
-  for (auto& e : s->ev) IA3_CUDA(cudaEventCreate(&e));
+  for (auto& e : s->ev) if (acquire_event(&e)) return -1;
   return 0;
 }
 
@@ -307,7 +376,7 @@ int ia3_stack_destroy(ia3_stack* s) {
   dev_free(s->fg); dev_free(s->bg); dev_free(s->scratch);
   dev_free(s->bits); dev_free(s->counts); dev_free(s->offsets);
   dev_free(s->cand_zxy); dev_free(s->cand_h);
-  for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : s->ev) release_event(e);
   release_stream(s->stream);
   delete s;
   return 0;
@@ -512,8 +581,27 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   }
   f->n_levels = n_levels;
 
-  if (upload(&f->d_centers, f->centers, st) || upload(&f->d_own, own, st) || upload(&f->d_nbr_start, nbr_start, st) ||
-      upload(&f->d_nbr_idx, nbr_idx, st) || upload(&f->d_offs, f->offs, st)) { ia3_fit_destroy(f); return -1; }
+  // inputs go through one pinned arena (no pageable copies), the brick table included
+  const int nbz = (s->Z + 7) / 8, nbx = (s->X + 7) / 8, nby = (s->Y + 7) / 8;
+  const size_t tab_n = (size_t)nbz * nbx * nby;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t up_total = al(f->centers.size() * 8) + al(own.size() * 4) + al(nbr_start.size() * 4) + al(nbr_idx.size() * 4) +
+                          al(f->offs.size()) + al(tab_n * 4) + al((size_t)std::max<int64_t>(n, 1) * 4);
+  if (reserve_pinned(&f->h_up, &f->up_cap, up_total)) { ia3_fit_destroy(f); return -1; }
+  size_t up_off = 0;
+  auto put = [&](void** d, const void* src, size_t bytes) -> int {
+    if (dev_alloc(d, bytes)) return -1;
+    if (bytes) {
+      char* h = static_cast<char*>(f->h_up) + up_off;
+      memcpy(h, src, bytes);
+      if (cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("cudaMemcpyAsync (inputs) failed"); return -1; }
+      up_off += (bytes + 255) / 256 * 256;
+    }
+    return 0;
+  };
+  if (put((void**)&f->d_centers, f->centers.data(), f->centers.size() * 8) || put((void**)&f->d_own, own.data(), own.size() * 4) ||
+      put((void**)&f->d_nbr_start, nbr_start.data(), nbr_start.size() * 4) || put((void**)&f->d_nbr_idx, nbr_idx.data(), nbr_idx.size() * 4) ||
+      put((void**)&f->d_offs, f->offs.data(), f->offs.size())) { ia3_fit_destroy(f); return -1; }
   const size_t nn = (size_t)std::max<int64_t>(n, 1);
   if (dev_alloc((void**)&f->d_mask, nn * KW * 4) || dev_alloc((void**)&f->d_ps, nn * NOUT * 4) ||
       dev_alloc((void**)&f->d_praw, nn * NP * 8) || dev_alloc((void**)&f->d_succ, nn) ||
@@ -521,9 +609,8 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
       dev_alloc((void**)&f->d_rec, nn * K * 8) || dev_alloc((void**)&f->d_snap, nn * K * 8) ||
       dev_alloc((void**)&f->d_tie_count, 256)) { ia3_fit_destroy(f); return -1; }
   // sparse float64 work volume: the 8x8x8 bricks touched by some seed's (clipped) window
-  const int nbz = (s->Z + 7) / 8, nbx = (s->X + 7) / 8, nby = (s->Y + 7) / 8;
   {
-    std::vector<int> tab((size_t)nbz * nbx * nby, -1);
+    std::vector<int> tab(tab_n, -1);
     int next = 0;
     for (int64_t i = 0; i < n; ++i) {
       int lo[3], hi[3];
@@ -544,13 +631,11 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
           }
     }
     f->n_bricks = next;
-    if (upload(&f->d_brick_tab, tab, st) || dev_alloc((void**)&f->d_vol, (size_t)std::max(next, 1) * 512 * 8)) { ia3_fit_destroy(f); return -1; }
-    IA3_CUDA(cudaStreamSynchronize(st));           // tab is a local
+    if (put((void**)&f->d_brick_tab, tab.data(), tab_n * 4) || dev_alloc((void**)&f->d_vol, (size_t)std::max(next, 1) * 512 * 8)) { ia3_fit_destroy(f); return -1; }
   }
   IA3_CUDA(cudaMemsetAsync(f->d_succ, 0, nn, st));
   IA3_CUDA(cudaMemsetAsync(f->d_rec, 0, nn * K * 8, st));
-  IA3_CUDA(cudaEventCreate(&f->e0));
-  IA3_CUDA(cudaEventCreate(&f->e1));
+  if (acquire_event(&f->e0) || acquire_event(&f->e1)) { ia3_fit_destroy(f); return -1; }
 
   FitDev& d = f->d;
   memset(&d, 0, sizeof(d));
@@ -581,8 +666,11 @@ int ia3_fit_destroy(ia3_fit* f) {
                   f->d_tie_spot, f->d_tie_k, f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info, f->d_rec,
                   f->d_snap, f->d_vol, f->d_work, f->d_brick_tab};
   for (void* p : ptrs) dev_free(p);
-  if (f->e0) cudaEventDestroy(f->e0);
-  if (f->e1) cudaEventDestroy(f->e1);
+  release_event(f->e0);
+  release_event(f->e1);
+  host_free(f->h_stage);
+  host_free(f->h_up);
+  dev_free(f->d_keep);
   delete f;
   return 0;
 }
@@ -603,10 +691,10 @@ int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
     f->d.tie_cap = f->tie_cap; f->d.tie_spot = f->d_tie_spot; f->d.tie_k = f->d_tie_k;
     IA3_CUDA(cudaMemsetAsync(f->d_tie_count, 0, sizeof(int), st));
     if (launch_voronoi(f->d, st)) return -1;
-    int cnt = 0;
-    IA3_DRAIN(st);
-    IA3_CUDA(cudaMemcpyAsync(&cnt, f->d_tie_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (reserve_pinned(&f->h_stage, &f->stage_cap, 256)) return -1;
+    IA3_CUDA(cudaMemcpyAsync(f->h_stage, f->d_tie_count, sizeof(int), cudaMemcpyDeviceToHost, st));
     IA3_CUDA(cudaStreamSynchronize(st));
+    const int cnt = *static_cast<int*>(f->h_stage);
     f->n_ties = cnt;
     if (cnt <= f->tie_cap) break;
     cap = cnt;
@@ -622,9 +710,11 @@ int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
   if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
   const int64_t n = std::min<int64_t>(cap, f->n_ties);
   if (n <= 0) return 0;
-  std::vector<int> sp(n), kk(n);
-  IA3_CUDA(cudaMemcpyAsync(sp.data(), f->d_tie_spot, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
-  IA3_CUDA(cudaMemcpyAsync(kk.data(), f->d_tie_k, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
+  if (reserve_pinned(&f->h_stage, &f->stage_cap, 2 * sizeof(int) * (size_t)n)) return -1;
+  int* sp = static_cast<int*>(f->h_stage);
+  int* kk = sp + n;
+  IA3_CUDA(cudaMemcpyAsync(sp, f->d_tie_spot, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
+  IA3_CUDA(cudaMemcpyAsync(kk, f->d_tie_k, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
   IA3_CUDA(cudaStreamSynchronize(f->s->stream));
   for (int64_t i = 0; i < n; ++i) {
     const int sidx = sp[i], k = kk[i];
@@ -640,32 +730,43 @@ int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
   if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
   n = std::min<int64_t>(n, f->n_ties);
   if (n <= 0) return 0;
-  uint8_t* d_keep = nullptr;
-  if (dev_alloc((void**)&d_keep, (size_t)n)) return -1;
+  if ((size_t)n > f->keep_cap) {
+    dev_free(f->d_keep);
+    f->d_keep = nullptr;
+    if (dev_alloc((void**)&f->d_keep, (size_t)n)) return -1;
+    f->keep_cap = (size_t)n;
+  }
   cudaStream_t st = f->s->stream;
-  IA3_CUDA(cudaMemcpyAsync(d_keep, keep, (size_t)n, cudaMemcpyHostToDevice, st));
-  if (launch_apply_ties(f->d_mask, f->d.KW, f->d_tie_spot, f->d_tie_k, d_keep, (int)n, st)) return -1;
-  IA3_CUDA(cudaStreamSynchronize(st));
-  dev_free(d_keep);
-  return 0;
+  if (reserve_pinned(&f->h_up, &f->up_cap, (size_t)n)) return -1;
+  memcpy(f->h_up, keep, (size_t)n);
+  IA3_CUDA(cudaMemcpyAsync(f->d_keep, f->h_up, (size_t)n, cudaMemcpyHostToDevice, st));
+  if (launch_apply_ties(f->d_mask, f->d.KW, f->d_tie_spot, f->d_tie_k, f->d_keep, (int)n, st)) return -1;
+  return 0;        // stream-ordered before first_run; the arena is next touched after first_run's synchronisation
 }
 
 static int fetch_results(ia3_fit* f, float* ps, double* p_raw, uint8_t* success, int32_t* nfev, int32_t* info) {
   cudaStream_t st = f->s->stream;
   const size_t n = (size_t)f->n;
   if (n == 0) return 0;
-  IA3_DRAIN(st);
-  if (ps) IA3_CUDA(cudaMemcpyAsync(ps, f->d_ps, n * NOUT * 4, cudaMemcpyDeviceToHost, st));
-  if (p_raw) IA3_CUDA(cudaMemcpyAsync(p_raw, f->d_praw, n * NP * 8, cudaMemcpyDeviceToHost, st));
-  if (success) IA3_CUDA(cudaMemcpyAsync(success, f->d_succ, n, cudaMemcpyDeviceToHost, st));
-  if (nfev) IA3_CUDA(cudaMemcpyAsync(nfev, f->d_nfev, n * 4, cudaMemcpyDeviceToHost, st));
-  if (info) IA3_CUDA(cudaMemcpyAsync(info, f->d_info, n * 4, cudaMemcpyDeviceToHost, st));
-  IA3_CUDA(cudaStreamSynchronize(st));
+  // device -> pinned staging (asynchronous copies queued behind the kernels), one wait, then plain
+  // memcpy into the caller's arrays: no pageable-memory copy ever enters the driver
+  const size_t sz[5] = {n * NOUT * 4, n * NP * 8, n, n * 4, n * 4};
+  const void* src[5] = {f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info};
+  void* dst[5] = {ps, p_raw, success, nfev, info};
+  size_t off[5], total = 0;
+  for (int i = 0; i < 5; ++i) { off[i] = total; total += (sz[i] + 255) / 256 * 256; }
+  if (reserve_pinned(&f->h_stage, &f->stage_cap, total)) return -1;
+  char* h = static_cast<char*>(f->h_stage);
+  for (int i = 0; i < 5; ++i)
+    if (dst[i]) IA3_CUDA(cudaMemcpyAsync(h + off[i], src[i], sz[i], cudaMemcpyDeviceToHost, st));
+  { IA3_STAT("  fetch: wait for stream"); IA3_DRAIN(st); }
+  for (int i = 0; i < 5; ++i) if (dst[i]) memcpy(dst[i], h + off[i], sz[i]);
   return 0;
 }
 
 // builds per-level work lists of the selected seeds; returns level boundaries
 static int build_work(ia3_fit* f, const uint8_t* active, std::vector<int>& bounds) {
+  IA3_STAT("  build_work");
   std::vector<std::vector<int>> per(f->n_levels);
   for (int64_t i = 0; i < f->n; ++i)
     if (!active || active[i]) per[f->level[i]].push_back((int)i);
@@ -678,9 +779,12 @@ static int build_work(ia3_fit* f, const uint8_t* active, std::vector<int>& bound
     if (dev_alloc((void**)&f->d_work, sizeof(int) * std::max<size_t>(flat.size(), (size_t)f->n))) return -1;
     f->work_cap = std::max<size_t>(flat.size(), (size_t)f->n);
   }
-  if (!flat.empty())
-    IA3_CUDA(cudaMemcpyAsync(f->d_work, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, f->s->stream));
-  IA3_CUDA(cudaStreamSynchronize(f->s->stream));   // flat is a local
+  if (!flat.empty()) {
+    // the previous call on this handle ended with a stream synchronisation, so the arena is free
+    if (reserve_pinned(&f->h_up, &f->up_cap, sizeof(int) * flat.size())) return -1;
+    memcpy(f->h_up, flat.data(), sizeof(int) * flat.size());
+    IA3_CUDA(cudaMemcpyAsync(f->d_work, f->h_up, sizeof(int) * flat.size(), cudaMemcpyHostToDevice, f->s->stream));
+  }
   return 0;
 }
 

@@ -63,6 +63,7 @@ SEEDS = [fitting.get_seeds(h, max_num_seeds=None, th_seed=300.0) for _, h in sta
 pool = ThreadPoolExecutor(D)
 list(pool.map(step, range(D)))       # warm-up
 trace.clear()
+_lib.debug_stats(reset=True)
 T0 = time.perf_counter()
 list(pool.map(step, range(K)))
 total = 1e3 * (time.perf_counter() - T0)
