@@ -13,7 +13,8 @@ line on rank 0.
   value      spots fitted per second, stack already resident in HBM when the timed region starts
   e2e        same metric through the public API (fit_fov_image on a pinned host stack): the H2D copy
              of the stack and the D2H reads of candidates / results are inside the timed region
-  roofline   dominant kernel = one 61-tap exact Gaussian axis pass (k_gauss_axis<30>)
+  roofline   the seed stage's dominant kernel, one 61-tap exact Gaussian axis pass (k_gauss_strided<30>),
+             against the measured HBM copy peak; roofline_fit = the fit stage against the FP pipes
   cpu_baseline  the oracle port (same scipy calls as the reference) on a bounded sample, 1 core
 Multi-GPU: one process per GPU (torchrun), every rank processes its own stacks (weak scaling), no
 data-path collective; the barrier / max-over-ranks reduction uses torch.distributed (NCCL).
@@ -163,13 +164,12 @@ def run_ours(args):
     _lib.init(local)
     dev = torch.device("cuda", local)
 
-    from concurrent.futures import ThreadPoolExecutor
+    from imageanalysis3_b200 import sharding
     D = max(1, args.inflight)
     n_stacks = max(2, min(D, 4))   # distinct stacks, cycled (each 419 MB > 126 MB L2)
-    pool = ThreadPoolExecutor(max_workers=D)
 
     def run_steps(fn, first, count):
-        return sum(pool.map(fn, range(first, first + count)))
+        return sum(sharding.map_stacks(fn, range(first, first + count), inflight=D))
     host, devt = [], []
     for i in range(n_stacks):
         d = synth_torch(SHAPE, N_PLANTED, 1 + rank * 16 + i, dev)
@@ -268,7 +268,8 @@ def run_ours(args):
     achieved = alg_bytes / (bg_launch_ms * 1e-3) / 1e9
     seed_ms_med = float(np.median(stage["seed_total"]))
     stage_bytes = 2.0 * vox + 16.0 * float(np.median(stage["n_cand"]))
-    fp64_flop = 91.0 * vox                                  # 30 pair adds + 31 mul + 30 adds, not fused
+    fp64_inst = 36.0 * vox                                  # 31 DFMA + 5 FP64 adds (offset, guards) per voxel
+    fit_flops_per_spot = 1.67e6                             # model / Jacobian / normal equations per spot
     line = {
         "metric": "spots_fitted_per_s", "value": n_spots / (ms_dev * 1e-3), "unit": "spots/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
@@ -285,15 +286,21 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps, "stacks_per_s": world * args.steps / (ms_e2e * 1e-3)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "k_gauss_axis<30> (one 61-tap exact axis pass, 3 launches per stack)",
+                     "kernel": "k_gauss_strided<30> / k_gauss_contig<30> (one 61-tap bit-exact axis pass; 3 launches per stack, mean)",
                      "launch_ms": bg_launch_ms, "peak_source": peak_src,
-                     "fp64_gflops_nonfused": fp64_flop / (bg_launch_ms * 1e-3) / 1e9,
+                     "note": "exact uint16 semantics make this pass FP64-pipe bound, not HBM bound: 36 FP64 instructions per voxel",
+                     "fp64_inst_per_s": fp64_inst / (bg_launch_ms * 1e-3),
+                     "fp64_pipe_frac": fp64_inst / (bg_launch_ms * 1e-3) / (148 * 64 * 1.965e9),
                      "seed_stage": {"ms": seed_ms_med, "algorithmic_bytes": stage_bytes,
                                     "achieved_GBps": stage_bytes / (seed_ms_med * 1e-3) / 1e9,
                                     "frac": stage_bytes / (seed_ms_med * 1e-3) / 1e9 / peak,
                                     "ms_gauss_fg": float(np.median(stage["gauss_fg"])), "ms_gauss_bg": float(np.median(stage["gauss_bg"])),
                                     "ms_rank": float(np.median(stage["rank"])), "ms_compact": float(np.median(stage["compact"]))},
                      "fit_stage": {"firstfit_ms": first_ms, "repeatfit_wall_ms": repeat_wall * 1e3}},
+        "roofline_fit": {"bound": "fp64/fp32 pipes (latency bound: one warp per spot runs MINPACK's serial iterations)",
+                         "achieved": fit_flops_per_spot * n_spots / (ms_dev * 1e-3) / 1e12, "unit": "TFLOP/s",
+                         "peak_fp32": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_fp64": 148 * 64 * 2 * 1.965e9 / 1e12,
+                         "algorithmic_flops_per_spot": fit_flops_per_spot},
         "wall_ms_per_step": 1e3 * wall / args.steps,
     }
     if not args.no_cpu:
@@ -310,11 +317,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=32, help="stacks in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--inflight", type=int, default=64, help="stacks in flight per GPU (host threads / CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

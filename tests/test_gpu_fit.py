@@ -150,3 +150,38 @@ def test_medium_fov_against_oracle(lib):
     cmp_ok = fit_oracle.fit_fov_image_oracle.last_comparable
     assert cmp_ok.mean() > 0.95
     assert_spots_close(got, want, "medium fov", cmp_ok)
+
+
+def test_concurrent_stacks_match_sequential(lib):
+    """several stacks in flight (host threads, one CUDA stream per stack) give exactly the results
+    of running them one after the other"""
+    from imageanalysis3_b200 import sharding
+    from imageanalysis3_b200.spot_tools.fitting import fit_fov_image
+    from imageanalysis3_b200.synth import synth
+    ims = [synth((20, 96, 104), 40, 50 + i) for i in range(6)]
+    run = lambda im: fit_fov_image(im, '647', th_seed=300, max_num_seeds=None, verbose=False)
+    seq = [run(im) for im in ims]
+    par = sharding.map_stacks(run, ims * 3, inflight=6)
+    for i, got in enumerate(par):
+        want = seq[i % len(ims)]
+        assert got.shape == want.shape and np.array_equal(got, want, equal_nan=True)
+
+
+def test_trim_releases_and_guards(lib, golden_fits):
+    from imageanalysis3_b200.External import Fitting_v4
+    g = golden_fits
+    st = lib.Stack(g["im"])
+    from imageanalysis3_b200.spot_tools.fitting import get_seeds
+    seeds = get_seeds(g["im"], th_seed=300, _stack=st)
+    st.trim(1)                                   # seed buffers gone, image still there
+    with pytest.raises(lib.IA3Error):
+        st.seed_volume(0)
+    f = Fitting_v4.iter_fit_seed_points(g["im"], seeds.T, _stack=st)
+    f.firstfit()
+    st.trim(2)                                   # the library's image copy gone: repeatfit still works
+    f.repeatfit()
+    assert_spots_close(f.ps, g["v4_final"], "after trim")
+    with pytest.raises(lib.IA3Error):
+        f.im_subtr
+    with pytest.raises(lib.IA3Error):
+        get_seeds(g["im"], th_seed=300, _stack=st)
