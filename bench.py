@@ -188,7 +188,7 @@ def run_ours(args):
         f = Fitting_v4.iter_fit_seed_points(host[i % n_stacks], seeds.T, _stack=st)
         f.firstfit()
         f.repeatfit()
-        spots = np.array(f.ps)
+        spots = f._ps_array()
         spots = spots[np.sum(np.isnan(spots), axis=1) == 0]
         return len(spots)
 
@@ -210,9 +210,11 @@ def run_ours(args):
     l0 = _lib.launch_count()
     _lib.timer_start()
     t0 = time.perf_counter()
+    cpu0 = time.process_time()
     n_spots = run_steps(step_resident, args.warmup, args.steps)
     ms_dev = _lib.timer_stop()
     wall = time.perf_counter() - t0
+    cpu_ms_per_step = 1e3 * (time.process_time() - cpu0) / args.steps
     launches = _lib.launch_count() - l0
     barrier()
     clocks = sampler.stop()
@@ -279,6 +281,7 @@ def run_ours(args):
                                "5000 planted spots; seed stage + Fitting_v4 firstfit + repeatfit",
                    "l2": f"inputs larger than L2 (419 MB per stack, {n_stacks} stacks cycled)",
                    "inflight": D, "latency_ms_one_stack_alone": ms_latency,
+                   "host_cpu_ms_per_step": cpu_ms_per_step, "host_cores": os.cpu_count(),
                    "spots_per_stack": n_spots / (world * args.steps), "fit_levels": n_levels, "repeat_sweeps": n_iter},
         "clocks": clocks,
         "e2e": {"value": n_e2e / (ms_e2e * 1e-3), "unit": "spots/s",

@@ -157,6 +157,16 @@ class IterFitBase:
             raise AttributeError(f"'{type(self).__name__}' object has no attribute 'im_add'")
         return self._h.volume(1)
 
+    def _ps_array(self):
+        """np.array(self.ps) without building 10^4 python objects: float32 (n, 11) if every row holds a
+        fit, float64 with NaN rows otherwise (the reference's dtype trap)."""
+        ok = self._ever_ok()
+        if ok.all():
+            return self._ps.copy()
+        out = self._ps.astype(np.float64)
+        out[~ok] = np.nan
+        return out
+
     def _centers_fit_array(self):
         """np.array(self.centers_fit): float32 if every row is a fit, float64 otherwise."""
         ok = self._ever_ok()

@@ -45,7 +45,7 @@ EXPORTS = [
     "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count", "ia3_debug_stats",
     "ia3_timer_start", "ia3_timer_stop",
     "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
-    "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume",
+    "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_box_background",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
     "ia3_fit_first_resolve", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_get_volume",
     "ia3_fit_get_rec", "ia3_fit_num_levels", "ia3_fit_last_ms", "ia3_gaussfit_batch", "ia3_gauss_eval",
@@ -81,6 +81,7 @@ def load():
     lib.ia3_seed_run.argtypes = [vp, P(SeedCfg), P(i64), P(SeedTiming)]
     lib.ia3_seed_fetch.argtypes = [vp, vp, vp, i64]
     lib.ia3_seed_fetch_volume.argtypes = [vp, i32, vp]
+    lib.ia3_box_background.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp]
     lib.ia3_fit_create.argtypes = [vp, vp, i64, P(FitCfg), P(vp)]
     lib.ia3_fit_destroy.argtypes = [vp]
     lib.ia3_fit_first_prepare.argtypes = [vp, P(i64)]
@@ -207,6 +208,15 @@ class Stack:
             _check(lib.ia3_seed_fetch(self._h, _ptr(zxy), _ptr(h), n))
         COPIED["d2h"] += zxy.nbytes + h.nbytes + 8
         return zxy, h, t
+
+    def box_background(self, boxes, first, last, bin_size, max_iter):
+        """find_image_background (io_tools/load.py:642-686) of n boxes (n, 6) int32 [z0, z1, x0, x1, y0, y1)"""
+        boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 6)
+        out = np.empty(len(boxes), dtype=np.float64)
+        _check(load().ia3_box_background(self._h, _ptr(boxes), len(boxes), int(first), int(last), int(bin_size), int(max_iter), _ptr(out)))
+        COPIED["h2d"] += boxes.nbytes
+        COPIED["d2h"] += out.nbytes
+        return out
 
     def seed_volume(self, which):
         out = np.empty(self.shape, dtype=self.dtype)

@@ -511,6 +511,46 @@ int ia3_seed_fetch_volume(ia3_stack* s, int which, void* out) {
   return 0;
 }
 
+int ia3_box_background(ia3_stack* s, const int32_t* boxes, int64_t n, int first, int last, int bin_size, int max_iter,
+                       double* out) {
+  IA3_STAT("ia3_box_background");
+  if (ensure_device()) return -1;
+  if (!s || (n > 0 && (!boxes || !out))) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (s->dtype != IA3_DTYPE_U16) { set_error("ia3_box_background supports uint16 stacks"); return -1; }
+  if (bin_size < 1 || last <= first) { set_error("bad histogram range"); return -1; }
+  if (n <= 0) return 0;
+  // np.arange(first, last, bin_size) has ceil((last - first) / bin_size) edges -> one bin fewer
+  const int nedges = (last - first + bin_size - 1) / bin_size;
+  const int nbins = nedges - 1;
+  if (nbins < 1) { set_error("bad histogram range"); return -1; }
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t* b = boxes + 6 * i;
+    if (b[0] < 0 || b[1] > s->Z || b[2] < 0 || b[3] > s->X || b[4] < 0 || b[5] > s->Y) { set_error("box outside the stack"); return -1; }
+  }
+  cudaStream_t st = s->stream;
+  void* h = nullptr;
+  int* d_boxes = nullptr;
+  double* d_out = nullptr;
+  const size_t bb = (size_t)n * 6 * 4, ob = (size_t)n * 8;
+  if (host_alloc(&h, bb + ob + 256) || dev_alloc((void**)&d_boxes, bb) || dev_alloc((void**)&d_out, ob)) return -1;
+  memcpy(h, boxes, bb);
+  char* ho = static_cast<char*>(h) + (bb + 255) / 256 * 256;
+  IA3_CUDA(cudaMemcpyAsync(d_boxes, h, bb, cudaMemcpyHostToDevice, st));
+  const bool whole = (n == 1 && boxes[0] == 0 && boxes[1] == s->Z && boxes[2] == 0 && boxes[3] == s->X && boxes[4] == 0 && boxes[5] == s->Y);
+  unsigned* d_ghist = nullptr;
+  if (whole) {
+    if (dev_alloc((void**)&d_ghist, (size_t)nbins * 4)) return -1;
+    if (volume_background(reinterpret_cast<const uint16_t*>(s->d_im), s->Z, s->X, s->Y, d_boxes, first, bin_size, nbins, max_iter,
+                          d_ghist, d_out, st)) return -1;
+  } else if (box_background(reinterpret_cast<const uint16_t*>(s->d_im), s->X, s->Y, d_boxes, n, first, bin_size, nbins, max_iter, d_out, st)) return -1;
+  IA3_CUDA(cudaMemcpyAsync(ho, d_out, ob, cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, ho, ob);
+  host_free(h); dev_free(d_boxes); dev_free(d_out); dev_free(d_ghist);
+  return 0;
+}
+
 // ---- fit stage ------------------------------------------------------------------------------
 static inline long long cell_key(long long a, long long b, long long c) {
   return ((a + (1LL << 20)) << 42) | ((b + (1LL << 20)) << 21) | (c + (1LL << 20));

@@ -947,3 +947,172 @@ template int seed_emit<float>(const float*, const float*, const SeedDims&, int, 
 int seed_flag_threads() { return FLAG_THREADS; }
 
 }  // namespace ia3
+
+// ------------------------------------------------------------------------------------------
+// Local background of a box of a uint16 stack = mode of its intensity histogram
+// (io_tools/load.py:642-686 find_image_background, called per spot by fit_fov_image's
+// normalize_local, spot_tools/fitting.py:246-258, on a (2*fit_radius*2+1)^3 crop).
+//   counts  np.histogram(crop, bins=arange(first, last, bin)): bin b = [first + b*bin, first + (b+1)*bin),
+//           the last bin also holds its right edge, values beyond it are dropped
+//   peaks   scipy.signal.find_peaks = strict local maxima, plateaus reported at their midpoint, never the
+//           first / last sample; the loop `height = size/50 / 2^k, k = 1..` accepts the first k <= max_iter
+//           with a peak of that height, i.e. succeeds iff the highest peak >= size/50/2^max_iter, and then
+//           takes the highest peak (lowest index among equals) -> centre of its bin
+//   else    np.nanmedian(crop)
+// One CTA per box; the histogram lives in shared memory.
+// ------------------------------------------------------------------------------------------
+namespace ia3 {
+
+constexpr int BG_THREADS = 256;
+
+__device__ __forceinline__ void block_reduce_best(unsigned long long& key, unsigned long long* sh) {
+  // max over the block of a packed (height << 32 | ~index) key
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, key, o); if (v > key) key = v; }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long v = (threadIdx.x < BG_THREADS / 32) ? sh[threadIdx.x] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); if (w > v) v = w; }
+    if (threadIdx.x == 0) sh[0] = v;
+  }
+  __syncthreads();
+  key = sh[0];
+  __syncthreads();
+}
+
+// k-th smallest (0-based) value of the box by two 256-bin radix passes; every thread returns it
+__device__ unsigned box_select(const uint16_t* __restrict__ im, int X, int Y, const int* b, long long nvox, long long k,
+                               unsigned* cnt /*256, shared*/) {
+  const int ex = b[3] - b[2], ey = b[5] - b[4];
+  unsigned prefix = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = threadIdx.x; i < 256; i += BG_THREADS) cnt[i] = 0;
+    __syncthreads();
+    for (long long t = threadIdx.x; t < nvox; t += BG_THREADS) {
+      const int dy = (int)(t % ey), dx = (int)((t / ey) % ex), dz = (int)(t / ((long long)ey * ex));
+      const unsigned v = im[((long long)(b[0] + dz) * X + (b[2] + dx)) * Y + (b[4] + dy)];
+      if (pass == 0) atomicAdd(&cnt[v >> 8], 1u);
+      else if ((v >> 8) == prefix) atomicAdd(&cnt[v & 255u], 1u);
+    }
+    __syncthreads();
+    unsigned digit = 0;
+    long long acc = 0;
+    for (int i = 0; i < 256; ++i) {          // every thread scans the same 256 counters
+      if (acc + cnt[i] > k) { digit = i; break; }
+      acc += cnt[i];
+    }
+    k -= acc;
+    prefix = (pass == 0) ? digit : ((prefix << 8) | digit);
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// whole-volume histogram for one large box (normalize_background): many CTAs, shared-memory
+// histograms flushed into a global one; k_box_background then starts from that histogram
+__global__ void __launch_bounds__(BG_THREADS)
+k_hist_accum(const uint16_t* __restrict__ im, long long nvox, int first, int bin, int nbins, unsigned* __restrict__ ghist) {
+  extern __shared__ unsigned hist[];
+  for (int i = threadIdx.x; i < nbins; i += BG_THREADS) hist[i] = 0;
+  __syncthreads();
+  const int last_edge = first + nbins * bin;
+  const long long stride = (long long)gridDim.x * BG_THREADS;
+  for (long long t = (long long)blockIdx.x * BG_THREADS + threadIdx.x; t < nvox; t += stride) {
+    const int v = im[t];
+    if (v < first || v > last_edge) continue;
+    atomicAdd(&hist[(v == last_edge) ? nbins - 1 : (v - first) / bin], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += BG_THREADS) if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+}
+
+__global__ void __launch_bounds__(BG_THREADS)
+k_box_background(const uint16_t* __restrict__ im, int X, int Y, const int* __restrict__ boxes, int first, int bin, int nbins,
+                 int max_iter, const unsigned* __restrict__ ghist, double* __restrict__ out) {
+  extern __shared__ unsigned hist[];                 // nbins counters
+  __shared__ unsigned long long red[BG_THREADS / 32];
+  __shared__ unsigned cnt256[256];
+  const int* b = boxes + 6 * (long long)blockIdx.x;  // z0 z1 x0 x1 y0 y1 (half open)
+  const int ez = b[1] - b[0], ex = b[3] - b[2], ey = b[5] - b[4];
+  const long long nvox = (ez > 0 && ex > 0 && ey > 0) ? (long long)ez * ex * ey : 0;
+  for (int i = threadIdx.x; i < nbins; i += BG_THREADS) hist[i] = ghist ? ghist[i] : 0u;
+  __syncthreads();
+  const int last_edge = first + nbins * bin;
+  if (!ghist) {
+    for (long long t = threadIdx.x; t < nvox; t += BG_THREADS) {
+      const int dy = (int)(t % ey), dx = (int)((t / ey) % ex), dz = (int)(t / ((long long)ey * ex));
+      const int v = im[((long long)(b[0] + dz) * X + (b[2] + dx)) * Y + (b[4] + dy)];
+      if (v < first || v > last_edge) continue;
+      const int bi = (v == last_edge) ? nbins - 1 : (v - first) / bin;
+      atomicAdd(&hist[bi], 1u);
+    }
+    __syncthreads();
+  }
+  // local maxima with plateaus (scipy _local_maxima_1d)
+  unsigned long long best = 0ull;
+  for (int i = 1 + threadIdx.x; i < nbins - 1; i += BG_THREADS) {
+    const unsigned h = hist[i];
+    if (h == 0 || !(hist[i - 1] < h)) continue;
+    int j = i + 1;
+    while (j < nbins - 1 && hist[j] == h) ++j;
+    if (hist[j] < h) {
+      const unsigned mid = (unsigned)((i + j - 1) / 2);
+      const unsigned long long key = ((unsigned long long)h << 32) | (unsigned long long)(0xffffffffu - mid);
+      if (key > best) best = key;
+    }
+  }
+  block_reduce_best(best, red);
+  const unsigned hmax = (unsigned)(best >> 32);
+  double hmin = (double)nvox / 50.0;
+  for (int k = 0; k < max_iter; ++k) hmin *= 0.5;   // the last height tried that still counts
+  double result;
+  if (best != 0ull && (double)hmax >= hmin) {
+    const unsigned p = 0xffffffffu - (unsigned)(best & 0xffffffffull);
+    result = (double)((long long)first * 2 + (2ll * p + 1) * bin) / 2.0;     // (bins[p] + bins[p+1]) / 2
+  } else if (nvox == 0) {
+    result = nan("");
+  } else {
+    const unsigned lo = box_select(im, X, Y, b, nvox, (nvox - 1) / 2, cnt256);
+    const unsigned hi = (nvox % 2) ? lo : box_select(im, X, Y, b, nvox, nvox / 2, cnt256);
+    result = ((double)lo + (double)hi) / 2.0;                                  // np.nanmedian
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = result;
+}
+
+int box_background(const uint16_t* im, int X, int Y, const int* d_boxes, long long n, int first, int bin, int nbins, int max_iter,
+                   double* d_out, cudaStream_t st) {
+  if (n == 0) return 0;
+  const size_t smem = (size_t)nbins * sizeof(unsigned);
+  if (smem > 200 * 1024) { set_error("background histogram does not fit in shared memory (bin_size too small)"); return -1; }
+  static std::once_flag once;
+  static cudaError_t once_err = cudaSuccess;
+  std::call_once(once, [] { once_err = cudaFuncSetAttribute(k_box_background, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  IA3_CUDA(once_err);
+  k_box_background<<<(unsigned)n, BG_THREADS, smem, st>>>(im, X, Y, d_boxes, first, bin, nbins, max_iter, nullptr, d_out);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+// one box covering the whole (Z, X, Y) volume
+int volume_background(const uint16_t* im, int Z, int X, int Y, const int* d_box, int first, int bin, int nbins, int max_iter,
+                      unsigned* d_ghist, double* d_out, cudaStream_t st) {
+  const size_t smem = (size_t)nbins * sizeof(unsigned);
+  if (smem > 200 * 1024) { set_error("background histogram does not fit in shared memory (bin_size too small)"); return -1; }
+  static std::once_flag once;
+  static cudaError_t once_err = cudaSuccess;
+  std::call_once(once, [] {
+    once_err = cudaFuncSetAttribute(k_hist_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (once_err == cudaSuccess) once_err = cudaFuncSetAttribute(k_box_background, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  IA3_CUDA(once_err);
+  IA3_CUDA(cudaMemsetAsync(d_ghist, 0, smem, st));
+  k_hist_accum<<<148 * 4, BG_THREADS, smem, st>>>(im, (long long)Z * X * Y, first, bin, nbins, d_ghist);
+  IA3_LAUNCH_CHECK();
+  k_box_background<<<1, BG_THREADS, smem, st>>>(im, X, Y, d_box, first, bin, nbins, max_iter, d_ghist, d_out);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia3

@@ -33,3 +33,11 @@ int seed_emit(const Tin* fg, const Tin* bg, const SeedDims& d, int variant, cons
 int seed_flag_threads();
 
 }  // namespace ia3
+
+namespace ia3 {
+// mode-of-histogram background of n boxes (z0 z1 x0 x1 y0 y1, half open) of a uint16 stack
+int box_background(const uint16_t* im, int X, int Y, const int* d_boxes, long long n, int first, int bin, int nbins, int max_iter,
+                   double* d_out, cudaStream_t st);
+int volume_background(const uint16_t* im, int Z, int X, int Y, const int* d_box, int first, int bin, int nbins, int max_iter,
+                      unsigned* d_ghist, double* d_out, cudaStream_t st);
+}  // namespace ia3

@@ -157,6 +157,42 @@ def _find_image_background(im, dtype=np.uint16, bin_size=10, max_iter=10):
     return (bins[sel] + bins[sel + 1]) / 2
 
 
+def _neighbor_boxes(coords, crop_size, shape):
+    """generate_neighboring_crop (io_tools/crop.py:59-88, sub_pixel_precision=False) for all spots at once:
+    (M, 3) centres -> (M, 6) int32 [z0, z1, x0, x1, y0, y1) (np.round = half to even, on float64)"""
+    c = np.asarray(coords)[:, :len(shape)].astype(np.float64)
+    size = np.ones(len(shape), dtype=np.int32) * crop_size
+    lo = np.maximum(np.round(c - size), 0.0)
+    hi = np.minimum(np.round(c + size + 1), np.array(shape, dtype=np.int32))
+    out = np.empty((len(c), 2 * len(shape)), dtype=np.int32)
+    out[:, 0::2] = lo.astype(np.int32)
+    out[:, 1::2] = hi.astype(np.int32)
+    return out
+
+
+def _image_backgrounds(im, stack, boxes, dtype='uint16', bin_size=10, make_plot=False, max_iter=10):
+    """find_image_background (io_tools/load.py:642-686) for every box of ``im``.  uint16 stacks that are
+    resident on the device are histogrammed there (one CTA per box); anything else (float images, other
+    ``dtype`` arguments) keeps the reference's own numpy/scipy expressions."""
+    boxes = np.asarray(boxes, dtype=np.int32).reshape(-1, 6)
+    if dtype is None:
+        dtype = im.dtype
+    on_device = (stack is not None and im.dtype == np.uint16 and np.dtype(dtype).kind in "ui"
+                 and float(bin_size) == int(bin_size) and int(bin_size) >= 1)
+    if on_device:
+        info = np.iinfo(dtype)
+        first, last = int(info.min), int(info.max)
+        if first >= 0 and last <= 65535:
+            empty = (boxes[:, 1] <= boxes[:, 0]) | (boxes[:, 3] <= boxes[:, 2]) | (boxes[:, 5] <= boxes[:, 4])
+            safe = boxes.copy()
+            safe[empty] = 0
+            out = stack.box_background(safe, first, last, int(bin_size), int(max_iter))
+            out[empty] = np.nan
+            return out
+    return np.array([_find_image_background(im[b[0]:b[1], b[2]:b[3], b[4]:b[5]], dtype=dtype, bin_size=bin_size, max_iter=max_iter)
+                     for b in boxes])
+
+
 def _neighbor_slices(coord, crop_size, shape):
     """io_tools/crop.py:59-88 (sub_pixel_precision=False) -> tuple of slices"""
     coord = np.array(coord)[:len(shape)]
@@ -217,24 +253,22 @@ def fit_fov_image(im, channel, seeds=None,
 
     fitter = Fitting_v4.iter_fit_seed_points(im, _seeds.T, radius_fit=fit_radius, _stack=stack, **fitting_args)
     fitter.firstfit()
-    if stack is not None:
+    _need_image = normalize_local or normalize_background
+    if stack is not None and not _need_image:
         stack.trim(2)          # repeatfit only touches the sparse work volume, not the image
     fitter.repeatfit()
-    _spots = np.array(fitter.ps)
+    _spots = fitter._ps_array()                 # == np.array(fitter.ps)
     _spots = _spots[np.sum(np.isnan(_spots), axis=1) == 0]
     if remove_boundary_points:
         inside = (_spots[:, 1:4] > np.zeros(3)).all(1) * (_spots[:, 1:4] < np.array(np.shape(im))).all(1)
         _spots = _spots[np.where(inside)[0]]
     if normalize_background and not normalize_local:
-        back = _find_image_background(im, **background_args)
+        back = _image_backgrounds(im, stack, np.array([[0, im.shape[0], 0, im.shape[1], 0, im.shape[2]]]), **background_args)[0]
         if verbose:
             print(f"normalize total background:{back:.2f}, ", end='')
         _spots[:, 0] = _spots[:, 0] / back
     elif normalize_local:
-        backs = []
-        for pt in _spots:
-            sl = _neighbor_slices(pt[1:4], fit_radius * 2, np.array(np.shape(im)))
-            backs.append(_find_image_background(im[sl], **background_args))
+        backs = _image_backgrounds(im, stack, _neighbor_boxes(_spots[:, 1:4], fit_radius * 2, np.shape(im)), **background_args)
         if verbose:
             print(f"normalize local background for each spot, ", end='')
         _spots[:, 0] = _spots[:, 0] / np.array(backs)
@@ -268,9 +302,9 @@ def get_centers(im, seeds=None, th_seed=150,
     fitter = Fitting_v4.iter_fit_seed_points(im, seeds.T, radius_fit=fit_radius)
     fitter.firstfit()
     fitter.repeatfit()
-    pfits = fitter.ps
+    pfits = fitter._ps_array()                  # == np.array(fitter.ps)
     if len(pfits) > 0:
-        centers = np.array(pfits)[:, 1:4]
+        centers = pfits[:, 1:4]
         if verbose:
             print(f"-- fitting {len(pfits)} points.")
         if remove_close_pts:

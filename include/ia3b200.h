@@ -87,6 +87,15 @@ int ia3_seed_fetch(ia3_stack* s, int32_t* zxy, float* h, int64_t cap);
  * 1 = background blur), same dtype as the stack. */
 int ia3_seed_fetch_volume(ia3_stack* s, int which, void* out);
 
+/* ---- local background (fit_fov_image's normalize_local / normalize_background) ------------ */
+/* find_image_background (io_tools/load.py:642-686) for n boxes of a uint16 stack: mode of the
+ * histogram with bins arange(first, last, bin_size) found with scipy.signal.find_peaks' rule and the
+ * reference's height loop, np.nanmedian of the box if that loop fails.  boxes is n x 6 int32
+ * (z0, z1, x0, x1, y0, y1; half open, as the slices of generate_neighboring_crop,
+ * io_tools/crop.py:59-88); out receives n float64. */
+int ia3_box_background(ia3_stack* s, const int32_t* boxes, int64_t n, int first, int last, int bin_size, int max_iter,
+                       double* out);
+
 /* ---- fit stage ------------------------------------------------------------------------- */
 typedef struct {
   int personality;      /* 4: External/Fitting_v4.py GaussianFit; 3: External/Fitting_v3.py */

@@ -331,9 +331,43 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
     return out
 
 
+def image_background(im, dtype='uint16', bin_size=10, max_iter=10):
+    """io_tools/load.py:642-686 find_image_background: mode of the intensity histogram."""
+    from scipy.signal import find_peaks
+    if dtype is None:
+        dtype = im.dtype
+    cts, bins = np.histogram(im, bins=np.arange(np.iinfo(dtype).min, np.iinfo(dtype).max, bin_size))
+    peaks, height, it = [], np.size(im) / 50, 0
+    while len(peaks) == 0:
+        height = height / 2
+        peaks, props = find_peaks(cts, height=height)
+        it += 1
+        if it > max_iter:
+            break
+    if it > max_iter:
+        return np.nanmedian(im)
+    p = peaks[np.argmax(props['peak_heights'])]
+    return (bins[p] + bins[p + 1]) / 2
+
+
+def local_backgrounds(im, spots, fit_radius=5, **background_args):
+    """spot_tools/fitting.py:246-258 + io_tools/crop.py:59-88: background of the crop around every spot."""
+    out = []
+    shape = np.array(np.shape(im), dtype=np.int32)
+    for pt in spots:
+        c = np.array(pt[1:4])[:3]
+        size = np.ones(3, dtype=np.int32) * (fit_radius * 2)
+        lo = np.max([np.round(c - size), np.zeros(3)], axis=0)
+        hi = np.min([np.round(c + size + 1), shape], axis=0)
+        lim = np.array(np.array([lo, hi]).transpose(), dtype=np.int32)
+        out.append(image_background(im[tuple(slice(a, b) for a, b in lim)], **background_args))
+    return np.array(out)
+
+
 def fit_fov_image_oracle(im, th_seed=300, max_num_seeds=500, fit_radius=5, remove_boundary_points=True,
-                         seed_backend="scipy", seeds=None, **seed_kw):
-    """spot_tools/fitting.py:169-262 without the optional intensity normalisation."""
+                         seed_backend="scipy", seeds=None, normalize_background=False, normalize_local=False,
+                         background_args={}, **seed_kw):
+    """spot_tools/fitting.py:169-262."""
     if seeds is None:
         seeds = seed_oracle.get_seeds_oracle(im, max_num_seeds=max_num_seeds, th_seed=float(th_seed),
                                              backend=seed_backend, **seed_kw)
@@ -347,4 +381,8 @@ def fit_fov_image_oracle(im, th_seed=300, max_num_seeds=500, fit_radius=5, remov
         inside = (spots[:, 1:4] > np.zeros(3)).all(1) * (spots[:, 1:4] < np.array(im.shape)).all(1)
         spots, cmp_ok = spots[np.where(inside)[0]], cmp_ok[np.where(inside)[0]]
     fit_fov_image_oracle.last_comparable = cmp_ok
+    if normalize_background and not normalize_local:
+        spots[:, 0] = spots[:, 0] / image_background(im, **background_args)
+    elif normalize_local:
+        spots[:, 0] = spots[:, 0] / local_backgrounds(im, spots, fit_radius, **background_args)
     return spots, seeds

@@ -87,6 +87,19 @@ def main():
     sp, _ = fit_oracle.fit_fov_image_oracle(im, th_seed=300, max_num_seeds=20)
     assert np.array_equal(sp, out["fov_spots_top20"])
     out["fov_spots_top20_comparable"] = fit_oracle.fit_fov_image_oracle.last_comparable
+    # intensity normalisation (find_image_background per spot crop / on the whole stack); a second stack
+    # with a background ramp so that the local backgrounds differ from spot to spot
+    for tag, kw in (("local", dict(normalize_local=True)), ("global", dict(normalize_background=True)),
+                    ("local_bin4", dict(normalize_local=True, background_args=dict(bin_size=4)))):
+        out[f"fov_spots_norm_{tag}"] = ns.fitting.fit_fov_image(im, '647', th_seed=300, max_num_seeds=None, verbose=False, **kw)
+        sp, _ = fit_oracle.fit_fov_image_oracle(im, th_seed=300, max_num_seeds=None, **kw)
+        assert np.array_equal(sp, out[f"fov_spots_norm_{tag}"])
+    ramp = (im.astype(np.int64) + (np.arange(im.shape[2])[None, None, :] * 9) + (np.arange(im.shape[1])[None, :, None] * 5)).astype(np.uint16)
+    out["im_ramp"] = ramp
+    out["ramp_spots_norm_local"] = ns.fitting.fit_fov_image(ramp, '647', th_seed=300, max_num_seeds=None, normalize_local=True, verbose=False)
+    sp, _ = fit_oracle.fit_fov_image_oracle(ramp, th_seed=300, max_num_seeds=None, normalize_local=True)
+    assert np.array_equal(sp, out["ramp_spots_norm_local"])
+    out["ramp_comparable"] = fit_oracle.fit_fov_image_oracle.last_comparable
     out["centers"] = ns.fitting.get_centers(im, th_seed=300)
     out["std_centers"] = ns.visual.get_STD_centers(im, th_seed=300)
     # seeds at the border: windows clipped by the image, one seed with < 10 voxels -> NaN row

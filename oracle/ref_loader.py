@@ -108,6 +108,7 @@ def load():
     sys.modules[_PKG + ".visual_tools"] = vt
     root.visual_tools = vt
 
+    _lift_io(root)
     v3 = _load(_PKG + ".External.Fitting_v3", "External/Fitting_v3.py")
     v4 = _load(_PKG + ".External.Fitting_v4", "External/Fitting_v4.py")
     ext.Fitting_v3 = v3
@@ -117,6 +118,42 @@ def load():
     ns = types.SimpleNamespace(Fitting_v3=v3, Fitting_v4=v4, fitting=fitting, visual=_lift_visual(v3, sigma_zxy))
     _cache["ns"] = ns
     return ns
+
+
+def _lift_nodes(relpath, names, env, kinds=(ast.FunctionDef, ast.ClassDef)):
+    with open(os.path.join(REF_ROOT, relpath), "r", encoding="utf-8", errors="replace") as fh:
+        tree = ast.parse(fh.read())
+    nodes = [n for n in tree.body if isinstance(n, kinds) and n.name in names]
+    code = compile(ast.Module(body=nodes, type_ignores=[]), f"<reference {relpath} (lifted)>", "exec")
+    exec(code, env)
+    return env
+
+
+def _lift_io(root):
+    """fit_fov_image(normalize_local=True) imports io_tools.load.find_image_background
+    (io_tools/load.py:642-686) and io_tools.crop.generate_neighboring_crop (io_tools/crop.py:59-88, which
+    needs classes.preprocess.ImageCrop, classes/preprocess.py:17-93).  Those packages do not import here
+    (h5py, skimage, ...): lift the three definitions by AST into stand-in modules."""
+    import scipy
+    import scipy.signal
+    pre = types.ModuleType(_PKG + ".classes.preprocess")
+    _lift_nodes("classes/preprocess.py", {"ImageCrop"}, pre.__dict__.update(np=np, _image_size=root._image_size) or pre.__dict__)
+    classes = types.ModuleType(_PKG + ".classes")
+    classes.__path__ = []
+    classes.preprocess = pre
+    load_m = types.ModuleType(_PKG + ".io_tools.load")
+    load_m.__dict__.update(np=np, scipy=scipy, _image_dtype="uint16")
+    _lift_nodes("io_tools/load.py", {"find_image_background"}, load_m.__dict__)
+    crop_m = types.ModuleType(_PKG + ".io_tools.crop")
+    crop_m.__package__ = _PKG + ".io_tools"
+    crop_m.__dict__.update(np=np, _image_size=root._image_size)
+    _lift_nodes("io_tools/crop.py", {"generate_neighboring_crop"}, crop_m.__dict__)
+    io = types.ModuleType(_PKG + ".io_tools")
+    io.__path__ = []
+    io.load, io.crop = load_m, crop_m
+    sys.modules.update({_PKG + ".classes": classes, _PKG + ".classes.preprocess": pre, _PKG + ".io_tools": io,
+                        _PKG + ".io_tools.load": load_m, _PKG + ".io_tools.crop": crop_m})
+    root.classes, root.io_tools = classes, io
 
 
 def _lift_visual(v3, sigma_zxy):
