@@ -29,3 +29,41 @@ class iter_fit_seed_points(IterFitBase):
             self._firstfit_device()
         else:
             raise ValueError(f"{len(self.centers)} points have been seeded, exit.")
+
+
+def get_seed_points_base(im, gfilt_size_min=1, gfilt_size_max=3, filt_size=3, th_seed=0., max_num=None,
+                         use_snr=False, hot_pix_th=0, return_h=False):
+    """Legacy seeder of Fitting_v3 (External/Fitting_v3.py:261-306): local maxima of the raw image that are
+    not local minima, height = blur(gfilt_size_min) - blur(gfilt_size_max) at those voxels, in the image's
+    own dtype (on a uint16 image the subtraction wraps around, exactly as in the reference).  The rank
+    filters and both Gaussian blurs run on the device; the bookkeeping below is the reference's numpy."""
+    from .. import _lib
+    from ..spot_tools.fitting import _device_image, _gauss_half_kernel
+    im_plt = np.array(im)
+    st = _lib.Stack(_device_image(im_plt))
+    zxy, _, _ = st.seed_candidates(None, None, int(filt_size), 0, 0.0, -1e300)       # (max == im) & (min != im)
+    z, x, y = (zxy[:, a].astype(np.int64) for a in range(3))
+    st.seed_candidates(_gauss_half_kernel(gfilt_size_min), _gauss_half_kernel(gfilt_size_max), int(filt_size), 0, 0.0, 1e300)
+    g_filt_sm, g_filt = st.seed_volume(0).astype(im_plt.dtype, copy=False), st.seed_volume(1).astype(im_plt.dtype, copy=False)
+    st.close()
+    with np.errstate(all='ignore'):
+        h = g_filt_sm[z, x, y] - g_filt[z, x, y]
+        snr = 1. * g_filt_sm[z, x, y] / g_filt[z, x, y]
+    keep = snr > th_seed if use_snr else h > th_seed
+    x, y, z = x[keep], y[keep], z[keep]
+    h, snr = h[keep], snr[keep]
+    if hot_pix_th > 0 and len(x) > 0:
+        xy = y * np.max(x) + x
+        xy_, cts_ = np.unique(xy, return_counts=True)
+        bad_xy = xy_[cts_ > hot_pix_th]
+        keep = ~np.isin(xy, bad_xy)
+        x, y, z = x[keep], y[keep], z[keep]
+        snr = snr[keep]
+        h = h[keep]
+    ind = np.argsort(snr)[::-1] if use_snr else np.argsort(h)[::-1]
+    centers = np.array([z[ind], x[ind], y[ind]])
+    if return_h:
+        centers = np.array([z, x, y, h])
+    if max_num is not None:
+        centers = centers[:, :max_num]
+    return centers

@@ -188,6 +188,42 @@ IA3_HD void pass_jacobian(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, doub
   ex.template reduce_store<NTRI + NP>(acc, Ag_out);
 }
 
+// Residual norm AND normal equations at the same point in one sweep over the voxels.  lmder evaluates
+// f(x + p) and, if the step is accepted, J(x + p): same point, same exp per voxel.  Doing both at once
+// saves a voxel sweep per accepted step (most steps are) at the price of a discarded Jacobian per
+// rejected one.  Residuals that are inf / NaN / huge go through pass_residual's enorm-faithful path
+// (the step is then rejected and the sums are never used).
+template <typename T, typename Exec, typename Vox>
+IA3_HD double pass_fused(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* Ag_out) {
+  const double agiant = 1.304e19 / (double)vox.m;
+  double acc[NTRI + NP];
+#pragma unroll
+  for (int i = 0; i < NTRI + NP; ++i) acc[i] = 0.0;
+  double s2 = 0.0;
+  int nbad = 0;
+  for (int k = ex.lane(); k < vox.m; k += Exec::W) {
+    T X0, X1, X2, d, res;
+    float J[NP];
+    vox.get(k, X0, X1, X2, d);
+    eval_jac<T>(vc, X0, X1, X2, d, res, J);
+    const double r = (double)res;
+    if (fabs(r) < agiant) s2 += r * r; else nbad += 1;
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const double ji = (double)J[i];
+      acc[NTRI + i] += ji * r;
+#pragma unroll
+      for (int j = i; j < NP; ++j) { acc[idx] += ji * (double)J[j]; ++idx; }
+    }
+  }
+  ex.template reduce_store<NTRI + NP>(acc, Ag_out);
+  s2 = ex.allsum(s2);
+  nbad = ex.allsum_int(nbad);
+  if (nbad == 0) return sqrt(s2);
+  return pass_residual<T>(ex, vc, vox, (double*)0);
+}
+
 struct FitResult {
   double p_raw[NP];
   float ps[NOUT];
@@ -212,19 +248,18 @@ template <typename T, typename Exec, typename Vox>
 IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen_est,
                    const double* origin, const Vox& vox, SpotShared<T>& sh) {
   LMState& st = sh.st;
-  build_consts_par<T>(ex, fp, cen_est, origin, sh.x0, sh);        // f(x0); the constants also serve J(x0)
-  const double fn0 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
+  build_consts_par<T>(ex, fp, cen_est, origin, sh.x0, sh);
+  const double fn0 = pass_fused<T>(ex, sh.vc, vox, sh.Ag);       // f(x0) and J(x0)
   lm_init(ex, st, sh.x0, fn0);
   for (;;) {
-    // Jacobian at st.x: sh.vc already holds the constants of st.x (x0, or the accepted trial point)
-    pass_jacobian<T>(ex, sh.vc, vox, sh.Ag);
+    // sh.Ag holds J^T J, J^T f at st.x (x0, or the trial point that was just accepted)
     ex.sync();
     if (!lm_outer(ex, st, cfg, sh.Ag, sh.Ag + NTRI)) break;
     int action;
     for (;;) {
       lm_propose(ex, st);
       build_consts_par<T>(ex, fp, cen_est, origin, st.xt, sh);
-      const double fn1 = pass_residual<T>(ex, sh.vc, vox, (double*)0);
+      const double fn1 = pass_fused<T>(ex, sh.vc, vox, sh.Ag);   // lm_outer has consumed the old sums
       action = lm_judge(ex, st, cfg, fn1);
       if (action != LM_RETRY) break;
     }

@@ -328,12 +328,13 @@ IA3_HDN bool lm_outer(Ex& ex, LMState& st, const LMConfig& cfg, const double* A,
   double gnorm = 0.0;
   const double fnorm = st.fnorm;
   if (fnorm != 0.0) {
+    for (int j = ln; j < NP; j += Ex::W) st.y[j] = st.qtf[j] / fnorm;     // lmder divides every term
+    ex.sync();
     for (int j = ln; j < NP; j += Ex::W) {
       const int l = st.ipvt[j];
       if (st.acn[l] != 0.0) {
-        // sum_{i<=j} R[i][j] * (qtf[i] / fnorm), as lmder does
         double sum = 0.0;
-        for (int i = 0; i <= j; ++i) sum += st.R[i][j] * (st.qtf[i] / fnorm);
+        for (int i = 0; i <= j; ++i) sum += st.R[i][j] * st.y[i];
         gnorm = fmax(gnorm, fabs(sum / st.acn[l]));
       }
     }

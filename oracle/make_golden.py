@@ -51,6 +51,11 @@ def main():
     out["legacy_base"] = ns.visual.get_seed_points_base(im, th_seed=200, hot_pix_th=3, return_h=True)
     imf = (im.astype(np.float32) / np.float32(301.7))
     out["seeds_f32"] = ns.fitting.get_seeds(imf, th_seed=1.0)
+    # Fitting_v3's own seeder (a11): float input (as intended) and uint16 input (wrap-around heights)
+    out["v3base_f32"] = ns.Fitting_v3.get_seed_points_base(imf, th_seed=0.4, hot_pix_th=3)
+    out["v3base_f32_h"] = ns.Fitting_v3.get_seed_points_base(imf, th_seed=0.4, return_h=True, max_num=50)
+    out["v3base_f32_snr"] = ns.Fitting_v3.get_seed_points_base(imf, th_seed=1.3, use_snr=True)
+    out["v3base_u16"] = ns.Fitting_v3.get_seed_points_base(im, th_seed=200, max_num=300)
     np.savez_compressed(os.path.join(OUT, "seeds_small.npz"), **out)
 
     # ---- fits --------------------------------------------------------------------------------

@@ -142,3 +142,18 @@ def test_full_size_stack_properties(lib):
     bg = st.seed_volume(1)[:, 900:1100, 500:740]
     assert np.array_equal(fg[:, 4:-4, 4:-4], seed_oracle.gaussian_filter_c(sub, 0.75)[:, 4:-4, 4:-4])
     assert np.array_equal(bg[:, 31:-31, 31:-31], seed_oracle.gaussian_filter_c(sub, 7.5)[:, 31:-31, 31:-31])
+
+
+def test_fitting_v3_seeder_matches_reference_fixture(lib, golden_seeds):
+    """External/Fitting_v3.py:261-306 get_seed_points_base (a11): float input and the uint16 wrap-around"""
+    from imageanalysis3_b200.External import Fitting_v3
+    g = golden_seeds
+    im = g["im"]
+    imf = im.astype(np.float32) / np.float32(301.7)
+    for name, arr, kw in (("v3base_f32", imf, dict(th_seed=0.4, hot_pix_th=3)),
+                          ("v3base_f32_h", imf, dict(th_seed=0.4, return_h=True, max_num=50)),
+                          ("v3base_f32_snr", imf, dict(th_seed=1.3, use_snr=True)),
+                          ("v3base_u16", im, dict(th_seed=200, max_num=300))):
+        got = Fitting_v3.get_seed_points_base(arr, **kw)
+        want = g[name]
+        assert got.shape == want.shape and got.dtype == want.dtype and np.array_equal(got, want), name
