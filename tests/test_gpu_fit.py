@@ -260,3 +260,21 @@ def test_box_background_against_oracle(lib):
         want = np.array([fit_oracle.image_background(im[b[0]:b[1], b[2]:b[3], b[4]:b[5]], bin_size=bin_size, max_iter=max_iter)
                          for b in boxes])
         assert np.array_equal(got, want), (bin_size, np.nonzero(got != want)[0][:5], got[got != want][:5], want[got != want][:5])
+
+
+def test_c4_density_crop_against_oracle(lib):
+    """BASELINE config C4 (dense RNA-FISH: 50 000 spots in 60 x 2048 x 2048) at the same density on a
+    60 x 256 x 256 crop: overlapping windows, several dependency levels, Voronoi ties"""
+    from imageanalysis3_b200.External import Fitting_v4
+    from imageanalysis3_b200.spot_tools.fitting import fit_fov_image, get_seeds
+    from imageanalysis3_b200.synth import synth
+    im = synth((60, 256, 256), 780, 4, h_range=(400.0, 3000.0))
+    want, seeds = fit_oracle.fit_fov_image_oracle(im, th_seed=300, max_num_seeds=None, seed_backend="c")
+    assert np.array_equal(get_seeds(im, th_seed=300.0), seeds) and len(seeds) > 600
+    got = fit_fov_image(im, '647', th_seed=300, max_num_seeds=None, verbose=False)
+    cmp_ok = fit_oracle.fit_fov_image_oracle.last_comparable
+    assert cmp_ok.mean() > 0.9
+    assert_spots_close(got, want, "C4-density crop", cmp_ok)
+    f = Fitting_v4.iter_fit_seed_points(im, seeds.T)
+    f.firstfit()
+    assert f._h.num_levels >= 2 and f.n_tie_voxels > 0

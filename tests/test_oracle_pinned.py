@@ -129,7 +129,8 @@ def test_well_posed_statistics(golden_fits):
     im = synth((24, 96, 96), 220, 31, h_range=(500.0, 3000.0))     # crowded: merged / overlapping spots
     seeds = seed_oracle.get_seeds_oracle(im, th_seed=200, backend="c")
     d = fit_oracle.iter_fit(im, seeds.T, version=4)
-    assert len(seeds) > 90 and d["cond_max"].max() < 50 and d["comparable"].all()
+    assert len(seeds) > 90 and d["cond_max"].max() < 50
+    assert d["well_posed"].mean() > 0.9          # a few slow crawls (widths on their bound) fail the sensitivity probe
 
 
 def test_comparable_mask_taints_window_overlap_components():
@@ -154,3 +155,18 @@ def test_background_normalisation_oracle_matches_golden(golden_fits):
     # the height loop's quirk: a peak found only at the 11th halving still falls back to the median
     flat = np.full((4, 5, 6), 7, dtype=np.uint16)             # single bin at the left edge: never a peak
     assert fit_oracle.image_background(flat) == 7.0
+
+
+def test_reference_sensitivity_probe_flags_slow_crawls():
+    """A spot whose width sits on its bound makes MINPACK crawl (> 100 evaluations on a well-conditioned
+    Jacobian); raising 1 % of its float32 voxel values by one ulp moves scipy's own answer by more than
+    the parity tolerance.  The oracle's probe must flag it (and only a handful of seeds like it)."""
+    from imageanalysis3_b200.synth import synth
+    im = synth((60, 256, 256), 780, 4, h_range=(400.0, 3000.0))
+    seeds = seed_oracle.get_seeds_oracle(im, th_seed=300.0, backend="c")
+    o = fit_oracle.iter_fit(im, seeds.T, version=4)
+    assert (o["cond_max"] < fit_oracle.COND_WELL_POSED).all()
+    assert 1 <= o["unstable"].sum() <= 5 and o["nfev_max"][o["unstable"]].min() > fit_oracle.NFEV_PROBE
+    sig = np.array([np.asarray(r, float) for r in o["ps"]])[o["unstable"], 5:8]
+    assert (np.abs(sig - 4.0) < 1e-3).any(1).all()          # every flagged row has a width on the bound
+    assert o["comparable"].mean() > 0.98
