@@ -34,6 +34,10 @@ class SeedTiming(C.Structure):
                 ("ms_compact", C.c_float), ("ms_total", C.c_float)]
 
 
+class MomentCfg(C.Structure):
+    _fields_ = [("radius", C.c_int), ("avoid_neighbors", C.c_int), ("recenter", C.c_int), ("bk_f", C.c_double)]
+
+
 class FitCfg(C.Structure):
     _fields_ = [("personality", C.c_int), ("radius", C.c_int),
                 ("min_w", C.c_double), ("max_w", C.c_double),
@@ -48,7 +52,7 @@ EXPORTS = [
     "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_box_background",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
     "ia3_fit_first_resolve", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_get_volume",
-    "ia3_fit_get_rec", "ia3_fit_num_levels", "ia3_fit_last_ms", "ia3_gaussfit_batch", "ia3_gauss_eval",
+    "ia3_fit_get_rec", "ia3_fit_num_levels", "ia3_fit_last_ms", "ia3_gaussfit_batch", "ia3_gauss_eval", "ia3_moment_fit",
 ]
 
 _lib = None
@@ -95,6 +99,7 @@ def load():
     lib.ia3_fit_last_ms.argtypes = [vp]
     lib.ia3_gaussfit_batch.argtypes = [P(FitCfg), dbl, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.ia3_gauss_eval.argtypes = [P(FitCfg), dbl, vp, vp, vp, i64, vp]
+    lib.ia3_moment_fit.argtypes = [vp, vp, i64, P(MomentCfg), vp]
     _lib = lib
     return lib
 
@@ -215,6 +220,16 @@ class Stack:
         out = np.empty(len(boxes), dtype=np.float64)
         _check(load().ia3_box_background(self._h, _ptr(boxes), len(boxes), int(first), int(last), int(bin_size), int(max_iter), _ptr(out)))
         COPIED["h2d"] += boxes.nbytes
+        COPIED["d2h"] += out.nbytes
+        return out
+
+    def moment_fit(self, centers_nx3, radius, avoid_neighbors=True, recenter=False, bk_f=0.1):
+        """gfit_fast for every seed (Fitting_v4.py:433-447, 494-556) -> (n, 12) float64"""
+        cen = np.ascontiguousarray(centers_nx3, dtype=np.float64).reshape(-1, 3)
+        out = np.empty((len(cen), 12), dtype=np.float64)
+        cfg = MomentCfg(int(radius), int(bool(avoid_neighbors)), int(bool(recenter)), float(bk_f))
+        _check(load().ia3_moment_fit(self._h, _ptr(cen), len(cen), C.byref(cfg), _ptr(out)))
+        COPIED["h2d"] += cen.nbytes
         COPIED["d2h"] += out.nbytes
         return out
 

@@ -963,6 +963,81 @@ int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_pr
   return 0;
 }
 
+int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_moment_cfg* cfg, double* out) {
+  IA3_STAT("ia3_moment_fit");
+  if (ensure_device()) return -1;
+  if (!s || !cfg || (n > 0 && (!centers_zxy || !out))) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (cfg->radius < 1 || cfg->radius > 7) { set_error("radius_fit must be in 1..7"); return -1; }
+  if (n <= 0) return 0;
+  for (int64_t i = 0; i < 3 * n; ++i)
+    if (!(std::fabs(centers_zxy[i]) < 1e6)) { set_error("seed coordinates must be finite and |c| < 1e6"); return -1; }
+  const int r = cfg->radius;
+  std::vector<int8_t> offs;
+  for (int a = -r; a < r; ++a) for (int b = -r; b < r; ++b) for (int c = -r; c < r; ++c)
+    if (a * a + b * b + c * c <= r * r) { offs.push_back((int8_t)a); offs.push_back((int8_t)b); offs.push_back((int8_t)c); }
+  const int K = (int)(offs.size() / 3);
+  // cKDTree.query_ball_tree(tree, 2r): seeds within 2r (inclusive), ascending, self included
+  std::vector<int> nbr_start(n + 1, 0), nbr_idx;
+  if (cfg->avoid_neighbors) {
+    const double reach = 2.0 * r, cs = reach;
+    std::unordered_map<long long, std::vector<int>> cells;
+    cells.reserve((size_t)n * 2 + 16);
+    auto cellc = [&](double v) { return (long long)std::floor(v / cs); };
+    for (int64_t i = 0; i < n; ++i) {
+      const double* c = centers_zxy + 3 * i;
+      cells[cell_key(cellc(c[0]), cellc(c[1]), cellc(c[2]))].push_back((int)i);
+    }
+    for (int64_t i = 0; i < n; ++i) {
+      const double* c = centers_zxy + 3 * i;
+      const long long a = cellc(c[0]), b = cellc(c[1]), cc = cellc(c[2]);
+      const size_t begin = nbr_idx.size();
+      for (long long da = -1; da <= 1; ++da) for (long long db = -1; db <= 1; ++db) for (long long dc = -1; dc <= 1; ++dc) {
+        auto it = cells.find(cell_key(a + da, b + db, cc + dc));
+        if (it == cells.end()) continue;
+        for (int j : it->second) {
+          const double* q = centers_zxy + 3 * (size_t)j;
+          const double d0 = q[0] - c[0], d1 = q[1] - c[1], d2 = q[2] - c[2];
+          if (std::sqrt(d0 * d0 + d1 * d1 + d2 * d2) <= reach) nbr_idx.push_back(j);
+        }
+      }
+      std::sort(nbr_idx.begin() + begin, nbr_idx.end());
+      nbr_start[i + 1] = (int)nbr_idx.size();
+    }
+  }
+  cudaStream_t st = s->stream;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_cen = (size_t)n * 24, b_ns = (size_t)(n + 1) * 4, b_ni = std::max<size_t>(nbr_idx.size(), 1) * 4, b_off = offs.size(), b_out = (size_t)n * 96;
+  void* h = nullptr;
+  if (host_alloc(&h, al(b_cen) + al(b_ns) + al(b_ni) + al(b_off) + al(b_out))) return -1;
+  double* d_cen = nullptr; int* d_ns = nullptr; int* d_ni = nullptr; int8_t* d_off = nullptr; double* d_out = nullptr;
+  if (dev_alloc((void**)&d_cen, b_cen) || dev_alloc((void**)&d_ns, b_ns) || dev_alloc((void**)&d_ni, b_ni) ||
+      dev_alloc((void**)&d_off, b_off) || dev_alloc((void**)&d_out, b_out)) return -1;
+  char* hp = static_cast<char*>(h);
+  size_t off = 0;
+  auto put = [&](void* d, const void* src, size_t bytes) -> int {
+    memcpy(hp + off, src, bytes);
+    if (cudaMemcpyAsync(d, hp + off, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("cudaMemcpyAsync failed"); return -1; }
+    off += (bytes + 255) / 256 * 256;
+    return 0;
+  };
+  if (put(d_cen, centers_zxy, b_cen) || put(d_ns, nbr_start.data(), b_ns) || (nbr_idx.size() && put(d_ni, nbr_idx.data(), nbr_idx.size() * 4)) ||
+      put(d_off, offs.data(), b_off)) return -1;
+  MomentDev d;
+  memset(&d, 0, sizeof(d));
+  d.im = s->d_im; d.im_dtype = s->dtype; d.Z = s->Z; d.X = s->X; d.Y = s->Y; d.n = n; d.centers = d_cen;
+  d.nbr_start = d_ns; d.nbr_idx = d_ni; d.K = K; d.offs = d_off; d.avoid = cfg->avoid_neighbors ? 1 : 0;
+  d.recenter = cfg->recenter ? 1 : 0; d.bk_f = cfg->bk_f; d.out = d_out;
+  if (launch_moment_fit(d, st)) return -1;
+  char* ho = hp + off;
+  IA3_CUDA(cudaMemcpyAsync(ho, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  IA3_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, ho, b_out);
+  host_free(h);
+  dev_free(d_cen); dev_free(d_ns); dev_free(d_ni); dev_free(d_off); dev_free(d_out);
+  return 0;
+}
+
 int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_raw, const double* center,
                    const float* coords, int64_t m, double* out) {
   if (ensure_device()) return -1;

@@ -440,6 +440,161 @@ int launch_generic_fit(const GenericFitDev& d, cudaStream_t st) {
 
 }  // namespace ia3
 
+// ------------------------------------------------------------------------------------------
+// Moment ("fast") fit of Fitting_v4: fast_fit_big_image + gfit_fast (External/Fitting_v4.py:433-447,
+// 494-556), default path (better_fit=False): per seed, the ball voxels that are closer to this seed
+// than to any seed within 2r (argmin of cdist, first index wins), optional recentring on the brightest
+// voxel, background = the int(n * bk_f)-th smallest value, weights = (values - background) clipped at 0
+// IN THE IMAGE'S DTYPE (a uint16 image wraps around, as in the reference), then weighted mean and
+// covariance of the voxel coordinates.  One warp per seed.
+// ------------------------------------------------------------------------------------------
+namespace ia3 {
+
+__global__ void __launch_bounds__(WARPS * 32) k_moment_fit(MomentDev d) {
+  extern __shared__ __align__(16) unsigned char msm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long s = (long long)blockIdx.x * WARPS + warp;
+  if (s >= d.n) return;
+  const int K = d.K;
+  const size_t per_warp = ((size_t)K * 12 + 15) / 16 * 16;
+  double* vals = reinterpret_cast<double*>(msm + per_warp * warp);
+  uint32_t* pk = reinterpret_cast<uint32_t*>(vals + K);
+  const double c[3] = {d.centers[3 * s], d.centers[3 * s + 1], d.centers[3 * s + 2]};
+  int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
+  const int nb0 = d.nbr_start[s], nb1 = d.nbr_start[s + 1];
+  double* out = d.out + 12 * s;
+
+  for (int pass = 0; pass < (d.recenter ? 2 : 1); ++pass) {
+    // gather the member voxels that are inside the image, in offset order
+    int m = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      bool use = false;
+      int dz = 0, dx = 0, dy = 0;
+      long long idx = 0;
+      if (k < K) {
+        dz = d.offs[3 * k]; dx = d.offs[3 * k + 1]; dy = d.offs[3 * k + 2];
+        use = true;
+        if (d.avoid) {
+          // np.argmin(cdist(centers[common] - centre, offsets), 0) == position of this seed in common
+          double best = 0.0; int bj = -1;
+          for (int e = nb0; e < nb1; ++e) {
+            const int j = d.nbr_idx[e];
+            const double r[3] = {d.centers[3 * j] - c[0], d.centers[3 * j + 1] - c[1], d.centers[3 * j + 2] - c[2]};
+            const double dist = sqrt(sqdist3((double)dz, (double)dx, (double)dy, r));
+            if (bj < 0 || dist < best) { best = dist; bj = j; }
+          }
+          use = (bj == (int)s);
+        }
+        const int z = ic[0] + dz, x = ic[1] + dx, y = ic[2] + dy;
+        use = use && (z >= 0 && z < d.Z && x >= 0 && x < d.X && y >= 0 && y < d.Y);
+        idx = ((long long)z * d.X + x) * d.Y + y;
+      }
+      const unsigned bal = __ballot_sync(FULL, use);
+      if (use) {
+        const int pos = m + __popc(bal & ((1u << lane) - 1u));
+        vals[pos] = load_im(d.im, d.im_dtype, idx);
+        pk[pos] = pack_vox(dz, dx, dy, 0);
+      }
+      m += __popc(bal);
+    }
+    __syncwarp();
+    if (m == 0) {
+      if (lane < 12) out[lane] = NAN;
+      return;
+    }
+    if (d.recenter && pass == 0) {
+      // zc, xc, yc = coordinates of the brightest member voxel (first maximum), same offsets again
+      double bv = -INFINITY; int bp = 0x7fffffff;
+      for (int p = lane; p < m; p += 32) if (vals[p] > bv) { bv = vals[p]; bp = p; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, bv, o);
+        const int op = __shfl_xor_sync(FULL, bp, o);
+        if (ov > bv || (ov == bv && op < bp)) { bv = ov; bp = op; }
+      }
+      const uint32_t p = pk[bp];
+      ic[0] += (int)(p & 63u) - 32; ic[1] += (int)((p >> 6) & 63u) - 32; ic[2] += (int)((p >> 12) & 63u) - 32;
+      __syncwarp();
+      continue;
+    }
+    // background: the kth smallest value, kth = int(m * bk_f)
+    const int kth = (int)((double)m * d.bk_f);
+    double bk = 0.0;
+    for (int p = lane; p < m; p += 32) {
+      const double v = vals[p];
+      int less = 0, eq_before = 0;
+      for (int q = 0; q < m; ++q) { const double u = vals[q]; less += (u < v); eq_before += (u == v && q < p); }
+      if (less + eq_before == kth) bk = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bk += __shfl_xor_sync(FULL, bk, o);      // exactly one lane holds it
+    // weights in the image's dtype
+    double hmax = 0.0, wsum = 0.0;
+    for (int p = lane; p < m; p += 32) {
+      double w = vals[p] - bk;
+      if (d.im_dtype == 0) w = (double)(uint16_t)(int)w;        // uint16 - uint16 wraps around
+      else if (w < 0) w = 0.0;
+      if (d.im_dtype == 1) w = (double)(float)w;                // float32 arithmetic
+      vals[p] = w;
+      hmax = fmax(hmax, w);
+      wsum += w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { hmax = fmax(hmax, __shfl_xor_sync(FULL, hmax, o)); wsum += __shfl_xor_sync(FULL, wsum, o); }
+    __syncwarp();
+    double mu[3] = {0, 0, 0};
+    for (int p = lane; p < m; p += 32) {
+      const double w = vals[p] / wsum;
+      vals[p] = w;
+      const uint32_t q = pk[p];
+      mu[0] += (double)(ic[0] + (int)(q & 63u) - 32) * w;
+      mu[1] += (double)(ic[1] + (int)((q >> 6) & 63u) - 32) * w;
+      mu[2] += (double)(ic[2] + (int)((q >> 12) & 63u) - 32) * w;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mu[a] += __shfl_xor_sync(FULL, mu[a], o);
+    __syncwarp();
+    double cv[6] = {0, 0, 0, 0, 0, 0};     // a b c d e f = zz xx yy zx zy xy
+    for (int p = lane; p < m; p += 32) {
+      const double w = vals[p];
+      const uint32_t q = pk[p];
+      const double z = (double)(ic[0] + (int)(q & 63u) - 32) - mu[0];
+      const double x = (double)(ic[1] + (int)((q >> 6) & 63u) - 32) - mu[1];
+      const double y = (double)(ic[2] + (int)((q >> 12) & 63u) - 32) - mu[2];
+      cv[0] += z * z * w; cv[1] += x * x * w; cv[2] += y * y * w; cv[3] += z * x * w; cv[4] += z * y * w; cv[5] += x * y * w;
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cv[a] += __shfl_xor_sync(FULL, cv[a], o);
+    if (lane == 0) {
+      out[0] = hmax; out[1] = mu[0]; out[2] = mu[1]; out[3] = mu[2]; out[4] = bk;
+      for (int a = 0; a < 6; ++a) out[5 + a] = cv[a];
+      out[11] = NAN;
+    }
+    return;
+  }
+}
+
+int launch_moment_fit(const MomentDev& d, cudaStream_t st) {
+  if (d.n == 0) return 0;
+  const size_t per_warp = ((size_t)d.K * 12 + 15) / 16 * 16;
+  const size_t smem = per_warp * WARPS;
+  if (smem > 200 * 1024) { set_error("radius_fit too large for the moment fit"); return -1; }
+  static std::once_flag once;
+  static cudaError_t once_err = cudaSuccess;
+  std::call_once(once, [] { once_err = cudaFuncSetAttribute(k_moment_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  IA3_CUDA(once_err);
+  k_moment_fit<<<(unsigned)((d.n + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(d);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia3
+
 // ---- small helper kernels used by the C ABI ---------------------------------------------------
 namespace ia3 {
 

@@ -44,6 +44,20 @@ int launch_voronoi(const FitDev& d, cudaStream_t st);
 int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, bool fp32, cudaStream_t st);
 int launch_subtract(const FitDev& d, const int* work, long long n_work, cudaStream_t st);
 
+struct MomentDev {                    // fast_fit_big_image / gfit_fast (Fitting_v4.py:433-556)
+  const void* im; int im_dtype;
+  int Z, X, Y;
+  long long n;
+  const double* centers;              // n x 3
+  const int* nbr_start;               // seeds within 2r (inclusive, ascending, self included)
+  const int* nbr_idx;
+  int K; const int8_t* offs;
+  int avoid, recenter;
+  double bk_f;
+  double* out;                        // n x 12
+};
+int launch_moment_fit(const MomentDev& d, cudaStream_t st);
+
 struct GenericFitDev {
   long long n; const long long* off;
   const double* values; const float* coords; const double* centers;

@@ -147,6 +147,20 @@ int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_pr
                        const double* values, const float* coords, const double* centers,
                        float* ps, double* p_raw, uint8_t* success, int32_t* nfev, int32_t* info, double* rec);
 
+/* Fitting_v4.fast_fit_big_image with better_fit=False (External/Fitting_v4.py:494-556) = gfit_fast
+ * (:433-447) for every seed: weighted-moment estimate [h, z, x, y, background, cov_zz, cov_xx, cov_yy,
+ * cov_zx, cov_zy, cov_xy, nan] over the seed's ball (offsets -r..r-1, d^2 <= r^2), restricted to the
+ * voxels nearer to it than to any other seed within 2r when avoid_neighbors != 0, recentred on the
+ * brightest voxel when recenter != 0.  centers is n x 3 float64, out n x 12 float64 (NaN rows for
+ * empty windows).  Weights are formed in the image's dtype like the reference does (uint16 wraps). */
+typedef struct {
+  int radius;            /* radius_fit (4) */
+  int avoid_neighbors;   /* avoid_neigbors (sic) */
+  int recenter;
+  double bk_f;           /* background quantile (0.1) */
+} ia3_moment_cfg;
+int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_moment_cfg* cfg, double* out);
+
 /* GaussianFit.get_im() (Fitting_v4.py:394-396): Gaussian part exp(h - q/2) of the model with raw
  * parameters p_raw (10) on m coordinates (m x 3 float32). */
 int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_raw, const double* center,

@@ -427,3 +427,57 @@ def fit_fov_image_oracle(im, th_seed=300, max_num_seeds=500, fit_radius=5, remov
     elif normalize_local:
         spots[:, 0] = spots[:, 0] / local_backgrounds(im, spots, fit_radius, **background_args)
     return spots, seeds
+
+
+def fast_fit_big_image_oracle(im, centers_zxy, radius_fit=4, avoid_neigbors=True, recenter=False, better_fit=False):
+    """External/Fitting_v4.py:433-447 (gfit_fast, reconstruct=False) + :494-556 (fast_fit_big_image)."""
+    ps = []
+    centers_zxy = np.asarray(centers_zxy)
+    if len(centers_zxy) > 0:
+        if avoid_neigbors:
+            tree = cKDTree(centers_zxy)
+            inters = tree.query_ball_tree(tree, radius_fit * 2)
+        g = window(radius_fit)
+        zb, xb, yb = g
+        X_c = g.T
+        sz, sx, sy = im.shape
+
+        def inside(z, x, y):
+            k = (z >= 0) & (z < sz) & (x >= 0) & (x < sx) & (y >= 0) & (y < sy)
+            return z[k], x[k], y[k]
+        for ic, (zc, xc, yc) in enumerate(centers_zxy):
+            if avoid_neigbors:
+                common = inters[ic]
+                rel = centers_zxy[common] - [zc, xc, yc]
+                zb_, xb_, yb_ = X_c[np.argmin(cdist(rel, X_c), 0) == common.index(ic)].T
+            else:
+                zb_, xb_, yb_ = zb, xb, yb
+            z, x, y = inside(int(zc) + zb_, int(xc) + xb_, int(yc) + yb_)
+            X_ = np.array([z, x, y]).T
+            im_ = im[z, x, y]
+            if recenter and len(im_) > 0:
+                k = np.argmax(im_)
+                zc, xc, yc = z[k], x[k], y[k]
+                z, x, y = inside(int(zc) + zb_, int(xc) + xb_, int(yc) + yb_)
+                X_ = np.array([z, x, y]).T
+                im_ = im[z, x, y]
+            if not better_fit:
+                p = np.array([np.nan] * 12)
+                if len(im_) > 0:
+                    X = X_.T
+                    bk = np.sort(im_)[int(len(im_) * 0.1)]
+                    w = im_ - bk
+                    w[w < 0] = 0
+                    h = np.max(w)
+                    w = w / np.sum(w)
+                    mu = np.sum(X * w, -1)
+                    Xc = X.T - mu
+                    cov = np.sum(np.array([[Xc[:, i] * Xc[:, j] for i in range(3)] for j in range(3)]) * w, -1)
+                    [[a, d, e], [d, b, f], [e, f, c]] = cov
+                    p = np.array([h, mu[0], mu[1], mu[2], bk, a, b, c, d, e, f, np.nan])
+            else:
+                p = np.array([np.nan] * 11)
+                if len(im_) > 0:
+                    p = gaussian_fit(im_, X_.T, center=X_[np.argmax(im_)], version=4, delta_center=2.5)["p"]
+            ps.append(p)
+    return np.array(ps)

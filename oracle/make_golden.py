@@ -118,6 +118,21 @@ def main():
     assert np.array_equal(_rows(o["ps"]), out["edge_final"], equal_nan=True)
     out["edge_comparable"] = o["comparable"]
     out["edge_cond_max"], out["edge_nfev_max"] = o["cond_max"], o["nfev_max"]
+    # Fitting_v4's moment fit (a13): float64 / uint16 / float32 images, neighbours avoided or not, recentring
+    ff = ns.Fitting_v4.fast_fit_big_image
+    imd = im.astype(np.float64)
+    jit = seeds + np.random.default_rng(3).uniform(-0.4, 0.4, size=seeds.shape)
+    close = np.concatenate([seeds, seeds[:5] + [1, 2, -2], edge_seeds[:4]])
+    for tag, (arr, cen, kw) in {"f64": (imd, seeds, {}), "f64_noavoid_r5": (imd, seeds, dict(avoid_neigbors=False, radius_fit=5)),
+                                "f64_close_recenter": (imd, close, dict(recenter=True)), "f64_jitter": (imd, jit, {}),
+                                "u16": (im, close, {}), "f32": (im.astype(np.float32), close, {})}.items():
+        out["fastfit_" + tag] = ff(arr, cen, verbose=False, **kw)
+        o2 = fit_oracle.fast_fit_big_image_oracle(arr, cen, **kw)
+        assert np.array_equal(o2, out["fastfit_" + tag], equal_nan=True), tag
+    out["fastfit_close"], out["fastfit_jitter"] = close, jit
+    out["fastfit_better"] = ff(imd, close[:12], verbose=False, better_fit=True)
+    o2 = fit_oracle.fast_fit_big_image_oracle(imd, close[:12], better_fit=True)
+    assert np.array_equal(o2, out["fastfit_better"], equal_nan=True)
     # single GaussianFit problems
     zb, xb, yb = f.zb, f.xb, f.yb
     c = seeds[0]

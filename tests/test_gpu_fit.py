@@ -278,3 +278,28 @@ def test_c4_density_crop_against_oracle(lib):
     f = Fitting_v4.iter_fit_seed_points(im, seeds.T)
     f.firstfit()
     assert f._h.num_levels >= 2 and f.n_tie_voxels > 0
+
+
+def test_fast_fit_big_image_matches_fixture(lib, golden_fits):
+    """Fitting_v4.fast_fit_big_image / gfit_fast (a13): weighted-moment fits on the device against the
+    unmodified reference, incl. the uint16 wrap-around of the weights and the GaussianFit variant"""
+    from imageanalysis3_b200.External import Fitting_v4
+    g = golden_fits
+    im = g["im"]
+    imd = im.astype(np.float64)
+    cases = {"f64": (imd, g["seeds"], {}, 1e-10), "f64_noavoid_r5": (imd, g["seeds"], dict(avoid_neigbors=False, radius_fit=5), 1e-10),
+             "f64_close_recenter": (imd, g["fastfit_close"], dict(recenter=True), 1e-10),
+             "f64_jitter": (imd, g["fastfit_jitter"], {}, 1e-10),
+             "u16": (im, g["fastfit_close"], {}, 1e-10), "f32": (im.astype(np.float32), g["fastfit_close"], {}, 2e-5)}
+    for tag, (arr, cen, kw, tol) in cases.items():
+        got = Fitting_v4.fast_fit_big_image(arr, cen, verbose=False, **kw)
+        want = g["fastfit_" + tag]
+        assert got.shape == want.shape and got.dtype == want.dtype, tag
+        assert np.array_equal(np.isnan(got), np.isnan(want)), tag
+        ok = ~np.isnan(want)
+        scale = np.maximum(np.abs(want[ok]), 1.0)
+        assert (np.abs(got[ok] - want[ok]) / scale).max() <= tol, (tag, (np.abs(got[ok] - want[ok]) / scale).max())
+    got = Fitting_v4.fast_fit_big_image(imd, g["fastfit_close"][:12], verbose=False, better_fit=True)
+    assert got.shape == g["fastfit_better"].shape
+    assert_spots_close(got, g["fastfit_better"], "fast_fit_big_image(better_fit=True)")
+    assert Fitting_v4.fast_fit_big_image(imd, np.zeros((0, 3)), verbose=False).shape == (0,)

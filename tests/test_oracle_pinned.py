@@ -170,3 +170,15 @@ def test_reference_sensitivity_probe_flags_slow_crawls():
     sig = np.array([np.asarray(r, float) for r in o["ps"]])[o["unstable"], 5:8]
     assert (np.abs(sig - 4.0) < 1e-3).any(1).all()          # every flagged row has a width on the bound
     assert o["comparable"].mean() > 0.98
+
+
+def test_fast_fit_oracle_matches_golden(golden_fits):
+    g = golden_fits
+    imd = g["im"].astype(np.float64)
+    for tag, (arr, cen, kw) in {"f64": (imd, g["seeds"], {}), "f64_noavoid_r5": (imd, g["seeds"], dict(avoid_neigbors=False, radius_fit=5)),
+                                "f64_close_recenter": (imd, g["fastfit_close"], dict(recenter=True)),
+                                "u16": (g["im"], g["fastfit_close"], {})}.items():
+        got = fit_oracle.fast_fit_big_image_oracle(arr, cen, **kw)
+        assert np.array_equal(got, g["fastfit_" + tag], equal_nan=True), tag
+    got = fit_oracle.fast_fit_big_image_oracle(imd, g["fastfit_close"][:12], better_fit=True)
+    assert np.array_equal(got, g["fastfit_better"], equal_nan=True)
