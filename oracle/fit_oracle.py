@@ -172,12 +172,24 @@ class _Problem:
     def solve(self):
         """-> (ok, natural parameters float32 (11), raw parameters float64 (10), nfev, ier)"""
         self.cond = np.inf
+        self.last_step_px = self.last_step_rel = 0.0
         if len(self.p0) > len(self.data):
             return False, None, None, 0, 0
         with np.errstate(all='ignore'):
             kw = dict(maxfev=1000) if self.version == 4 else {}
-            q, _, info, _, ier = leastsq(self.residual, self.p0, Dfun=self.jacobian, full_output=True, **kw)
+            jac_at = []                                   # lmder evaluates the Jacobian at every accepted iterate
+
+            def jac(x):
+                jac_at.append(np.array(x, dtype=np.float64))
+                return self.jacobian(x)
+            q, _, info, _, ier = leastsq(self.residual, self.p0, Dfun=jac, full_output=True, **kw)
             self.cond = jacobian_condition(self.jacobian(q)) if ier in (1, 2, 3, 4) else np.inf
+            # size of MINPACK's last accepted step in natural parameters: where its ftol test fires is
+            # uncertain by one iteration, so this is the reference's own stopping uncertainty
+            nat, prev = self.natural(q), self.natural(jac_at[-1])
+            self.last_step_px = float(np.abs(nat[1:4].astype(np.float64) - prev[1:4]).max())
+            cols = [0, 4, 5, 6, 7]
+            self.last_step_rel = float((np.abs(nat[cols].astype(np.float64) - prev[cols]) / np.abs(nat[cols].astype(np.float64))).max())
             return True, self.natural(q), q, info['nfev'], ier
 
 
@@ -201,10 +213,22 @@ COND_WELL_POSED = 1.0e3
 # which its ftol test (1.49e-8) first fires moves with the last bits of the data.  Measured on such a
 # fit: raising 1 % of the float32 voxel values by ONE ulp changes scipy's own answer by 4e-4 px and
 # 4e-4 relative (nfev 136 -> 81).  So every seed whose slowest fit needed more than NFEV_PROBE
-# evaluations (real spots: 6 .. 30) is probed exactly like that, and is ill-posed if the reference moves
-# by more than half the parity tolerance under the perturbation.
-NFEV_PROBE = 40
+# evaluations (real spots: 6 .. 30), or ended with a width on one of its bounds, is probed exactly like
+# that, and is ill-posed if the reference moves by more than half the parity tolerance under the
+# perturbation.
+NFEV_PROBE = 20
+# ... and, cheaper and sharper: MINPACK stops at the first iterate whose actual and predicted relative
+# reductions are both below ftol; a last-bit difference in those two numbers moves the stop by one
+# iteration.  If the reference's own LAST accepted step is larger than the tolerance in natural
+# parameters, an implementation that follows the same trajectory to 1e-13 can still land one step away,
+# outside the tolerance.  Real spots converge quadratically (last step ~1e-6 px); crawls do not.
 PROBE_TOL_PX, PROBE_TOL_REL = 5.0e-4, 5.0e-5
+LAST_STEP_PX, LAST_STEP_REL = 1.0e-3, 1.0e-4       # the parity tolerance itself
+
+
+def _on_bound(nat, min_w, max_w):
+    sig = np.asarray(nat[5:8], dtype=np.float64)
+    return bool((np.abs(sig - max_w) < 1e-3 * max_w).any() or (np.abs(sig - min_w) < 1e-3 * max_w).any())
 
 
 def reference_is_unstable(problem, base_nat):
@@ -294,6 +318,7 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
     tree = cKDTree(cen) if version == 4 else None
     mk = lambda v, X, c, d: _Problem(v, X, c, version, d, min_w, max_w, init_w, weight_sigma)
     ps, cfit, ok_l, recs, nfevs, conds = [], [], [], [], [], []
+    coarse = np.zeros(n, dtype=bool)               # a fit of this seed ended with a last step > the tolerance
     slowest = {}                                   # seed -> (problem, natural parameters) of its longest fit
 
     def ball(c):
@@ -314,8 +339,10 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
         ok_l.append(ok)
         nfevs.append(nfev)
         conds.append(pr.cond if ok else 0.0)
-        if ok and nfev > NFEV_PROBE:
+        if ok and (nfev > NFEV_PROBE or _on_bound(nat, min_w, max_w)):
             slowest[i] = (pr, nat)
+        if ok and (pr.last_step_px > LAST_STEP_PX or pr.last_step_rel > LAST_STEP_REL):
+            coarse[i] = True
         if ok:
             rec = pr.gauss(q, full)
             work[full[0], full[1], full[2]] -= rec
@@ -342,11 +369,13 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
             ok, nat, q, nfev, _ = pr.solve()
             ok_l[i] = ok
             nfev_rep.append(nfev)
-            if ok and nfev > NFEV_PROBE and nfev >= nfev_max[i]:
+            if ok and (nfev > NFEV_PROBE or _on_bound(nat, min_w, max_w)) and (nfev >= nfev_max[i] or i not in slowest):
                 slowest[i] = (pr, nat)
             nfev_max[i] = max(nfev_max[i], nfev)
             if ok:
                 cond_max[i] = max(cond_max[i], pr.cond)
+                if pr.last_step_px > LAST_STEP_PX or pr.last_step_rel > LAST_STEP_REL:
+                    coarse[i] = True
             if ok:
                 rec = pr.gauss(q)
                 ps[i], cfit[i], recs[i] = nat, nat[1:4], rec
@@ -358,9 +387,9 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
         n_iter += 1
         stop = np.all(done) or (n_iter > n_max_iter)
     well = cond_max <= COND_WELL_POSED       # (a fit that ran into maxfev has cond = inf)
-    unstable = np.zeros(n, dtype=bool)
+    unstable = coarse.copy()
     for i, (pr, nat) in slowest.items():
-        if well[i]:
+        if well[i] and not unstable[i]:
             unstable[i] = reference_is_unstable(pr, nat)
     gross = ~well                                # cond / maxfev: the answer is off by 1e-2 .. 1 px between runs
     well &= ~unstable
