@@ -42,6 +42,16 @@ FIT_KW = dict(th_seed=TH_SEED, max_num_seeds=None, verbose=False)
 CPU_CROP = (50, 448, 448)      # bounded CPU sample: a crop of the same stack (same spot density)
 
 
+def _traffic():
+    """dram__bytes_read + dram__bytes_write of the 61-tap pass from the committed ncu capture (per launch)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            t = json.load(fh)["k_gauss_61tap_pass"]
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -288,7 +298,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": (c1["h2d"] - c0["h2d"]) / args.steps, "d2h_bytes_per_step": (c1["d2h"] - c0["d2h"]) / args.steps,
                 "ms_per_step": ms_e2e / args.steps, "stacks_per_s": world * args.steps / (ms_e2e * 1e-3)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(),
                      "kernel": "k_gauss_strided<30> / k_gauss_contig<30> (one 61-tap bit-exact axis pass; 3 launches per stack, mean)",
                      "launch_ms": bg_launch_ms, "peak_source": peak_src,
                      "note": "exact uint16 semantics make this pass FP64-pipe bound, not HBM bound: 36 FP64 instructions per voxel",
