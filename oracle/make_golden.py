@@ -105,6 +105,17 @@ def main():
     sp, _ = fit_oracle.fit_fov_image_oracle(ramp, th_seed=300, max_num_seeds=None, normalize_local=True)
     assert np.array_equal(sp, out["ramp_spots_norm_local"])
     out["ramp_comparable"] = fit_oracle.fit_fov_image_oracle.last_comparable
+    # the remaining argument paths of fit_fov_image / get_centers: given seeds, seed mask, float32 image, crop
+    mask = np.zeros(im.shape, dtype=np.uint8)
+    mask[:, :40, :] = 1
+    out["fov_given_seeds"] = ns.fitting.fit_fov_image(im, '647', seeds=np.concatenate([seeds[:15], np.ones((15, 1))], axis=1), verbose=False)
+    out["fov_seed_mask"] = ns.fitting.fit_fov_image(im, '647', th_seed=300, max_num_seeds=None, seed_mask=mask, verbose=False)
+    imf32 = im.astype(np.float32) / np.float32(2.5)
+    out["fov_f32"] = ns.fitting.fit_fov_image(imf32, '647', th_seed=120, max_num_seeds=None, verbose=False)
+    out["fov_noboundary_r4"] = ns.fitting.fit_fov_image(im, '647', th_seed=300, max_num_seeds=25, fit_radius=4,
+                                                        remove_boundary_points=False, verbose=False)
+    out["centers_crop"] = ns.fitting.get_centers(im, th_seed=300, sel_center=[10, 36, 40], seed_radius=25)
+    out["centers_noclose"] = ns.fitting.get_centers(im, th_seed=300, remove_close_pts=False, max_num_seeds=12)
     out["centers"] = ns.fitting.get_centers(im, th_seed=300)
     out["std_centers"] = ns.visual.get_STD_centers(im, th_seed=300)
     # seeds at the border: windows clipped by the image, one seed with < 10 voxels -> NaN row

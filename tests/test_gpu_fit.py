@@ -303,3 +303,27 @@ def test_fast_fit_big_image_matches_fixture(lib, golden_fits):
     assert got.shape == g["fastfit_better"].shape
     assert_spots_close(got, g["fastfit_better"], "fast_fit_big_image(better_fit=True)")
     assert Fitting_v4.fast_fit_big_image(imd, np.zeros((0, 3)), verbose=False).shape == (0,)
+
+
+def test_remaining_argument_paths_match_fixture(lib, golden_fits):
+    """fit_fov_image with given seeds / a seed mask / a float32 image / another radius without the boundary
+    filter, get_centers with a crop and without the duplicate filter -- against the unmodified reference"""
+    from imageanalysis3_b200.spot_tools.fitting import fit_fov_image, get_centers
+    g = golden_fits
+    im, seeds = g["im"], g["seeds"]
+    got = fit_fov_image(im, '647', seeds=np.concatenate([seeds[:15], np.ones((15, 1))], axis=1), verbose=False)
+    assert_spots_close(got, g["fov_given_seeds"], "given seeds")
+    mask = np.zeros(im.shape, dtype=np.uint8)
+    mask[:, :40, :] = 1
+    got = fit_fov_image(im, '647', th_seed=300, max_num_seeds=None, seed_mask=mask, verbose=False)
+    assert_spots_close(got, g["fov_seed_mask"], "seed mask")
+    imf32 = im.astype(np.float32) / np.float32(2.5)
+    got = fit_fov_image(imf32, '647', th_seed=120, max_num_seeds=None, verbose=False)
+    assert got.dtype == g["fov_f32"].dtype
+    assert_spots_close(got, g["fov_f32"], "float32 image")
+    got = fit_fov_image(im, '647', th_seed=300, max_num_seeds=25, fit_radius=4, remove_boundary_points=False, verbose=False)
+    assert_spots_close(got, g["fov_noboundary_r4"], "radius 4, no boundary filter")
+    c = get_centers(im, th_seed=300, sel_center=[10, 36, 40], seed_radius=25)
+    assert c.shape == g["centers_crop"].shape and np.abs(c - g["centers_crop"]).max() <= 1e-3
+    c = get_centers(im, th_seed=300, remove_close_pts=False, max_num_seeds=12)
+    assert c.shape == g["centers_noclose"].shape and np.abs(c - g["centers_noclose"]).max() <= 1e-3
