@@ -165,7 +165,11 @@ def run_ours(args):
     if use_dist:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        backend = os.environ.get("IA3_BENCH_BACKEND", "nccl")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
     from imageanalysis3_b200 import _lib
     from imageanalysis3_b200.External import Fitting_v4
     from imageanalysis3_b200.spot_tools import fitting
@@ -262,7 +266,10 @@ def run_ours(args):
     step_e2e(0)
     ms_latency = _lib.timer_stop()
 
-    t_val = torch.tensor([ms_dev, ms_e2e, float(n_spots), float(n_e2e), float(launches)], dtype=torch.float64, device=dev)
+    t_val = torch.tensor([ms_dev, ms_e2e, float(n_spots), float(n_e2e), float(launches)], dtype=torch.float64,
+                         device=dev if (not use_dist or dist.get_backend() == "nccl") else "cpu")
+    if use_dist and os.environ.get("IA3_BENCH_VERBOSE"):
+        print(f"rank {rank}: {ms_dev / args.steps:.2f} ms/step resident, {ms_e2e / args.steps:.2f} ms/step e2e", file=sys.stderr, flush=True)
     if use_dist:
         tmax = t_val.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t_val.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)

@@ -199,14 +199,19 @@ void dev_cache_clear() {
   g_cached_bytes = 0;
 }
 
-static int ensure_device() {
-  static std::once_flag flags_once;
-  std::call_once(flags_once, [] {
-    // host threads that wait for a stack's stream should sleep, not spin: many stacks are in flight
-    // per GPU (one host thread each).  Takes effect if this process has not created the device's
-    // primary context yet; otherwise the call fails harmlessly.
-    if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError();
+// Host threads that wait for a stack's stream should sleep, not spin: dozens of stacks are in flight
+// per GPU (one host thread each), and spinning threads starve each other and the other ranks of the
+// box.  The scheduling flag belongs to the device's primary context, so it has to be set for THAT device
+// (cudaSetDeviceFlags would act on the calling thread's current device, i.e. device 0) and before the
+// context exists; if the application created the context first the call fails harmlessly.
+static void init_device_flags(int dev) {
+  static std::once_flag once;
+  std::call_once(once, [dev] {
+    if (cudaInitDevice(dev, cudaDeviceScheduleBlockingSync, cudaInitDeviceFlagsAreValid) != cudaSuccess) cudaGetLastError();
   });
+}
+
+static int ensure_device() {
   if (g_device >= 0) { IA3_CUDA(cudaSetDevice(g_device)); return 0; }
   int dev = 0;
   if (const char* e = getenv("IA3_DEVICE")) dev = atoi(e);
@@ -214,6 +219,7 @@ static int ensure_device() {
   IA3_CUDA(cudaGetDeviceCount(&n));
   if (n <= 0) { set_error("no CUDA device visible: libia3b200 has no CPU fallback"); return -1; }
   if (dev >= n) dev = dev % n;
+  init_device_flags(dev);
   IA3_CUDA(cudaSetDevice(dev));
   g_device = dev;
   return 0;
@@ -287,6 +293,7 @@ int ia3_init(int device) {
     IA3_CUDA(cudaGetDeviceCount(&n));
     if (n <= 0) { set_error("no CUDA device visible: libia3b200 has no CPU fallback"); return -1; }
     g_device = device % n;
+    init_device_flags(g_device);
   }
   return ensure_device();
 }
