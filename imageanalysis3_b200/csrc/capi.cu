@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <time.h>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -102,7 +103,12 @@ static void release_stream(cudaStream_t st) {
 void set_error(const std::string& msg) { g_err = msg; }
 
 // ---- wall-clock accounting of the entry points (IA3_STATS=1; tools/trace_pipeline.py prints it) ----
-struct StatSlot { const char* name; std::atomic<long long> ns{0}; std::atomic<long long> calls{0}; };
+struct StatSlot { const char* name; std::atomic<long long> ns{0}; std::atomic<long long> cpu_ns{0}; std::atomic<long long> calls{0}; };
+static inline long long thread_cpu_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+  return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
 static StatSlot g_stats[24];
 static std::atomic<int> g_nstats{0};
 static const bool g_stats_on = getenv("IA3_STATS") != nullptr;
@@ -120,10 +126,12 @@ static StatSlot* stat_slot(const char* name) {
 struct StatScope {
   StatSlot* s = nullptr;
   std::chrono::steady_clock::time_point t0;
-  explicit StatScope(const char* name) { if (g_stats_on) { s = stat_slot(name); t0 = std::chrono::steady_clock::now(); } }
+  long long c0 = 0;
+  explicit StatScope(const char* name) { if (g_stats_on) { s = stat_slot(name); t0 = std::chrono::steady_clock::now(); c0 = thread_cpu_ns(); } }
   ~StatScope() {
     if (s) {
       s->ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+      s->cpu_ns += thread_cpu_ns() - c0;
       s->calls += 1;
     }
   }
@@ -308,14 +316,14 @@ int ia3_device_sm_count(void) {
 int64_t ia3_launch_count(void) { return g_launches.load(); }
 int ia3_debug_stats(char* buf, int cap) {
   if (!buf || cap <= 0) {                        // reset
-    for (int i = 0; i < g_nstats.load(); ++i) { g_stats[i].ns = 0; g_stats[i].calls = 0; }
+    for (int i = 0; i < g_nstats.load(); ++i) { g_stats[i].ns = 0; g_stats[i].cpu_ns = 0; g_stats[i].calls = 0; }
     return 0;
   }
   int off = 0;
   const int n = g_nstats.load();
   for (int i = 0; i < n && off < cap - 96; ++i)
-    off += snprintf(buf + off, cap - off, "%-24s calls %8lld  total %10.2f ms\n", g_stats[i].name, g_stats[i].calls.load(),
-                    g_stats[i].ns.load() * 1e-6);
+    off += snprintf(buf + off, cap - off, "%-24s calls %8lld  wall %10.2f ms  cpu %10.2f ms\n", g_stats[i].name, g_stats[i].calls.load(),
+                    g_stats[i].ns.load() * 1e-6, g_stats[i].cpu_ns.load() * 1e-6);
   return off;
 }
 

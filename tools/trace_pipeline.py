@@ -64,6 +64,7 @@ pool = ThreadPoolExecutor(D)
 list(pool.map(step, range(D)))       # warm-up
 trace.clear()
 _lib.debug_stats(reset=True)
+CPU0 = time.process_time()
 T0 = time.perf_counter()
 list(pool.map(step, range(K)))
 total = 1e3 * (time.perf_counter() - T0)
@@ -72,4 +73,5 @@ for i, tid, ev in sorted(trace):
         break
     print(f"step {i} thr {tid:3d}: " + "  ".join(f"{n} {a:7.1f}-{b:7.1f}" for n, a, b in ev))
 print(_lib.debug_stats())
+print(f"process CPU {1e3 * (time.process_time() - CPU0) / K:.2f} ms per step")
 print(f"mode={MODE} D={D} K={K} total {total:.1f} ms -> {total / K:.1f} ms/step")
