@@ -111,11 +111,20 @@ def cpu_sample(im_crop):
 
 
 def _cpu_worker(args):
-    seed, = args
+    seed, crop = args
     from imageanalysis3_b200.synth import synth
-    n = max(10, int(round(N_PLANTED * np.prod(CPU_CROP) / np.prod(SHAPE))))
-    im = synth(CPU_CROP, n, seed)
+    n = max(4, int(round(N_PLANTED * np.prod(crop) / np.prod(SHAPE))))
+    im = synth(crop, n, seed)
     return cpu_sample(im)
+
+
+def _reference_crop(steps, warmup, budget_s=150.0):
+    """Crop of the C2 stack (same spot density) one worker handles per step, sized so that the whole
+    --steps K --warmup W run takes about ``budget_s``: a 50x448x448 crop costs ~3 s with the pool busy."""
+    per_step = budget_s / max(1, steps + warmup)
+    edge = 448.0 * min(1.0, per_step / 3.0) ** 0.5
+    edge = int(max(96, min(448, round(edge / 32.0) * 32)))
+    return (SHAPE[0], edge, edge)
 
 
 def run_reference(args):
@@ -126,18 +135,19 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
     ctx = mp.get_context("fork")
+    crop = _reference_crop(args.steps, args.warmup)
     times, spots = [], []
     with ctx.Pool(procs) as pool:
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(1000 + it * procs + i,) for i in range(procs)], chunksize=1)
+            res = pool.map(_cpu_worker, [(1000 + it * procs + i, crop) for i in range(procs)], chunksize=1)
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)
                 spots.append(sum(r[0] for r in res))
     T = float(np.sum(times))
     value = float(np.sum(spots)) / T
-    vox = float(np.prod(CPU_CROP)) * procs * args.steps
+    vox = float(np.prod(crop)) * procs * args.steps
     line = {
         "impl": "reference", "metric": "spots_fitted_per_s", "value": value, "unit": "spots/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
@@ -146,7 +156,7 @@ def run_reference(args):
         "config": {"workload": "C2: fit_fov_image on 50x2048x2048 uint16 FOV, 5000 planted spots, th_seed=300 "
                                "(reference CPU path timed on crops of that workload)"},
         "cpu_baseline": {"value": value, "unit": "spots/s", "cores": procs, "kind": "port",
-                         "sample": f"{procs} process(es) x one {CPU_CROP[0]}x{CPU_CROP[1]}x{CPU_CROP[2]} crop of the C2 stack per step "
+                         "sample": f"{procs} process(es) x one {crop[0]}x{crop[1]}x{crop[2]} crop of the C2 stack per step "
                                    f"(same spot density), multiprocessing.Pool like classes/field_of_view.py:1129"},
         "e2e": {"value": value, "unit": "spots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
