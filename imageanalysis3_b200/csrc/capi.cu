@@ -594,13 +594,34 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   // neighbour lists (seeds that can own a voxel of this seed's window) and dependency levels
   const double reach = 2.0 * ((double)r + 1.7320508075688772) + 1e-6;
   const double cs = std::ceil(reach);
-  std::vector<long long> key(n);
-  std::unordered_map<long long, std::vector<int>> cells;
-  cells.reserve((size_t)n * 2 + 16);
-  auto cellc = [&](double v) { return (long long)std::floor(v / cs); };
+  // uniform grid of cells of edge >= reach, as a counting sort (cell -> [start, end) in `order`)
+  double lo3[3] = {0, 0, 0}, hi3[3] = {0, 0, 0};
+  for (int64_t i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const double v = f->centers[3 * i + a];
+      if (i == 0 || v < lo3[a]) lo3[a] = v;
+      if (i == 0 || v > hi3[a]) hi3[a] = v;
+    }
+  long long gdim[3];
+  for (int a = 0; a < 3; ++a) gdim[a] = (long long)std::floor((hi3[a] - lo3[a]) / cs) + 1;
+  double cse = cs;
+  while ((double)gdim[0] * (double)gdim[1] * (double)gdim[2] > 4.0e7) {     // absurdly sparse seeds: coarser cells
+    cse *= 2.0;
+    for (int a = 0; a < 3; ++a) gdim[a] = (long long)std::floor((hi3[a] - lo3[a]) / cse) + 1;
+  }
+  auto cellc = [&](double v, int a) { return (long long)std::floor((v - lo3[a]) / cse); };
+  const long long ncell = (n > 0) ? gdim[0] * gdim[1] * gdim[2] : 0;
+  std::vector<int> cell_start((size_t)ncell + 1, 0), order((size_t)n), cell_of((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
     const double* c = &f->centers[3 * i];
-    cells[cell_key(cellc(c[0]), cellc(c[1]), cellc(c[2]))].push_back((int)i);
+    const long long id = (cellc(c[0], 0) * gdim[1] + cellc(c[1], 1)) * gdim[2] + cellc(c[2], 2);
+    cell_of[i] = (int)id;
+    cell_start[id + 1] += 1;
+  }
+  for (long long k = 0; k < ncell; ++k) cell_start[k + 1] += cell_start[k];
+  {
+    std::vector<int> fill(cell_start.begin(), cell_start.end() - (ncell > 0 ? 1 : 0));
+    for (int64_t i = 0; i < n; ++i) order[fill[cell_of[i]]++] = (int)i;
   }
   std::vector<int> nbr_start(n + 1, 0), nbr_idx, own(n);
   f->level.assign(n, 0);
@@ -608,14 +629,16 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   const int lim = 2 * r - 1;
   for (int64_t i = 0; i < n; ++i) {
     const double* c = &f->centers[3 * i];
-    const long long a = cellc(c[0]), b = cellc(c[1]), cc = cellc(c[2]);
+    const long long a = cellc(c[0], 0), b = cellc(c[1], 1), cc = cellc(c[2], 2);
     const int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
     int lvl = 0, ownid = (int)i;
     const size_t begin = nbr_idx.size();
     for (long long da = -1; da <= 1; ++da) for (long long db = -1; db <= 1; ++db) for (long long dc = -1; dc <= 1; ++dc) {
-      auto it = cells.find(cell_key(a + da, b + db, cc + dc));
-      if (it == cells.end()) continue;
-      for (int j : it->second) {
+      const long long ca = a + da, cb = b + db, ccc = cc + dc;
+      if (ca < 0 || ca >= gdim[0] || cb < 0 || cb >= gdim[1] || ccc < 0 || ccc >= gdim[2]) continue;
+      const long long id = (ca * gdim[1] + cb) * gdim[2] + ccc;
+      for (int e = cell_start[id]; e < cell_start[id + 1]; ++e) {
+        const int j = order[e];
         if (j == (int)i) continue;
         const double* q = &f->centers[3 * j];
         const double d0 = q[0] - c[0], d1 = q[1] - c[1], d2 = q[2] - c[2];
