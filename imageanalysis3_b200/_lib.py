@@ -12,7 +12,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libia3b200.so")
+LIB_PATH = os.environ.get("IA3_LIB") or os.path.join(_HERE, "libia3b200.so")   # IA3_LIB: developer override (kernel variants)
 
 DTYPE_U16, DTYPE_F32, DTYPE_F64 = 0, 1, 2
 _NP2DT = {np.dtype(np.uint16): DTYPE_U16, np.dtype(np.float32): DTYPE_F32, np.dtype(np.float64): DTYPE_F64}

@@ -39,6 +39,14 @@ static int acquire_stream(cudaStream_t* out) {
   IA3_CUDA(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
   return 0;
 }
+static cudaStream_t g_upload_stream = nullptr;
+static std::mutex g_upload_mu;
+static int upload_stream(cudaStream_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_upload_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_upload_stream, cudaStreamNonBlocking));
+  *out = g_upload_stream;
+  return 0;
+}
 static int global_stream(cudaStream_t* out) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g_stream) IA3_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
@@ -91,6 +99,30 @@ static int reserve_pinned(void** buf, size_t* cap, size_t bytes) {
   size_t cls = 4096;
   while (cls < bytes) cls <<= 1;
   *cap = cls;
+  return 0;
+}
+
+// ---- small transfers without the copy engines ------------------------------------------------
+// With many stacks in flight the H2D copy engine is busy with other stacks' 400 MB image uploads,
+// and a cudaMemcpyAsync of a few KB (work lists, seed tables, results) queues behind them in the
+// engine's FIFO: every such copy then costs one or more image uploads of latency.  Pinned host
+// memory is device-addressable under UVA, so small transfers are done by a copy KERNEL on the
+// stack's own stream instead (loads / stores over PCIe); only the image itself (and the optional
+// whole-volume fetches) use the copy engines.  The host side of every transfer is a pinned arena.
+constexpr size_t kSmallCopyMax = (size_t)16 << 20;
+template <typename W>
+__global__ void k_copy(W* __restrict__ dst, const W* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static int small_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (bytes > kSmallCopyMax) { IA3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st)); return 0; }
+  const uintptr_t al = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes;
+  auto blocks = [](size_t n) { return (unsigned)std::min<size_t>((n + 255) / 256, 296); };
+  if ((al & 15) == 0) { const size_t n = bytes / 16; k_copy<uint4><<<blocks(n), 256, 0, st>>>((uint4*)dst, (const uint4*)src, n); }
+  else if ((al & 3) == 0) { const size_t n = bytes / 4; k_copy<uint32_t><<<blocks(n), 256, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, n); }
+  else k_copy<uint8_t><<<blocks(bytes), 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, bytes);
+  IA3_LAUNCH_CHECK();
   return 0;
 }
 
@@ -264,6 +296,7 @@ struct ia3_stack {
   uint8_t* bits = nullptr; int* counts = nullptr; long long* offsets = nullptr;
   int32_t* cand_zxy = nullptr; float* cand_h = nullptr;
   int64_t n_cand = 0;
+  void* h_mail = nullptr;            // pinned, device-addressable: scalars the seed stage hands back
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -353,6 +386,7 @@ static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
   s->nvox = (size_t)Z * X * Y;
   if (acquire_stream(&s->stream)) return -1;
   for (auto& e : s->ev) if (acquire_event(&e)) return -1;
+  if (host_alloc(&s->h_mail, 4096)) return -1;
   return 0;
 }
 
@@ -364,8 +398,23 @@ int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack**
   if (stack_common(s, dtype, Z, X, Y)) { delete s; return -1; }
   if (dev_alloc(&s->d_im, s->nvox * dtype_size(dtype))) { delete s; return -1; }
   s->owns = true;
-  IA3_CUDA(cudaMemcpyAsync(s->d_im, im, s->nvox * dtype_size(dtype), cudaMemcpyHostToDevice, s->stream));
-  IA3_CUDA(cudaStreamSynchronize(s->stream));
+  // The image goes up on ONE upload stream shared by all stacks (the copy engine serialises the
+  // uploads anyway): with more stacks in flight than hardware queues (32), a stack's own stream
+  // shares its queue with another stack's, and a 400 MB copy waiting its turn behind other uploads
+  // would hold back that other stack's kernels for as long.
+  {
+    cudaStream_t us;
+    if (upload_stream(&us)) { ia3_stack_destroy(s); return -1; }
+    cudaError_t e;
+    {
+      std::lock_guard<std::mutex> lk(g_upload_mu);
+      e = cudaMemcpyAsync(s->d_im, im, s->nvox * dtype_size(dtype), cudaMemcpyHostToDevice, us);
+      if (e == cudaSuccess) e = cudaEventRecord(s->ev[5], us);
+    }
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->stream, s->ev[5], 0);
+    if (e == cudaSuccess) e = cudaEventSynchronize(s->ev[5]);
+    if (e != cudaSuccess) { set_error(std::string("image upload failed: ") + cudaGetErrorString(e)); ia3_stack_destroy(s); return -1; }
+  }
   *out = s;
   return 0;
 }
@@ -393,6 +442,7 @@ int ia3_stack_destroy(ia3_stack* s) {
   dev_free(s->cand_zxy); dev_free(s->cand_h);
   for (auto& e : s->ev) release_event(e);
   release_stream(s->stream);
+  host_free(s->h_mail);
   delete s;
   return 0;
 }
@@ -468,10 +518,9 @@ static int seed_run_t(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidat
   const Tin* bg = reinterpret_cast<const Tin*>(s->bg_final);
   if (seed_flags<Tin>(fg, bg, d, cfg->variant, s->bits, s->counts, s->offsets, st)) return -1;
   IA3_CUDA(cudaEventRecord(s->ev[3], st));
-  long long total = 0;
-  IA3_DRAIN(st);
-  IA3_CUDA(cudaMemcpyAsync(&total, s->offsets + d.n_blocks, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (small_copy(s->h_mail, s->offsets + d.n_blocks, sizeof(long long), st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
+  const long long total = *static_cast<const long long*>(s->h_mail);
   dev_free(s->cand_zxy); dev_free(s->cand_h);
   s->cand_zxy = nullptr; s->cand_h = nullptr;
   if (dev_alloc((void**)&s->cand_zxy, sizeof(int32_t) * 3 * (size_t)std::max<long long>(total, 1))) return -1;
@@ -510,9 +559,20 @@ int ia3_seed_fetch(ia3_stack* s, int32_t* zxy, float* h, int64_t cap) {
   if (!s) { set_error("null argument"); return -1; }
   const int64_t n = std::min<int64_t>(cap, s->n_cand);
   if (n > 0) {
-    if (zxy) IA3_CUDA(cudaMemcpyAsync(zxy, s->cand_zxy, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
-    if (h) IA3_CUDA(cudaMemcpyAsync(h, s->cand_h, sizeof(float) * n, cudaMemcpyDeviceToHost, s->stream));
-    IA3_CUDA(cudaStreamSynchronize(s->stream));
+    const size_t bz = sizeof(int32_t) * 3 * (size_t)n, bh = sizeof(float) * (size_t)n, oh = (bz + 255) / 256 * 256;
+    void* stage = nullptr;
+    if (host_alloc(&stage, oh + bh)) return -1;
+    char* hp = static_cast<char*>(stage);
+    int rc = 0;
+    if (zxy) rc |= small_copy(hp, s->cand_zxy, bz, s->stream);
+    if (h) rc |= small_copy(hp + oh, s->cand_h, bh, s->stream);
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("seed_fetch: stream failed"); rc = -1; }
+    if (!rc) {
+      if (zxy) memcpy(zxy, hp, bz);
+      if (h) memcpy(h, hp + oh, bh);
+    }
+    host_free(stage);
+    return rc;
   }
   return 0;
 }
@@ -551,7 +611,7 @@ int ia3_box_background(ia3_stack* s, const int32_t* boxes, int64_t n, int first,
   if (host_alloc(&h, bb + ob + 256) || dev_alloc((void**)&d_boxes, bb) || dev_alloc((void**)&d_out, ob)) return -1;
   memcpy(h, boxes, bb);
   char* ho = static_cast<char*>(h) + (bb + 255) / 256 * 256;
-  IA3_CUDA(cudaMemcpyAsync(d_boxes, h, bb, cudaMemcpyHostToDevice, st));
+  if (small_copy(d_boxes, h, bb, st)) return -1;
   const bool whole = (n == 1 && boxes[0] == 0 && boxes[1] == s->Z && boxes[2] == 0 && boxes[3] == s->X && boxes[4] == 0 && boxes[5] == s->Y);
   unsigned* d_ghist = nullptr;
   if (whole) {
@@ -559,7 +619,7 @@ int ia3_box_background(ia3_stack* s, const int32_t* boxes, int64_t n, int first,
     if (volume_background(reinterpret_cast<const uint16_t*>(s->d_im), s->Z, s->X, s->Y, d_boxes, first, bin_size, nbins, max_iter,
                           d_ghist, d_out, st)) return -1;
   } else if (box_background(reinterpret_cast<const uint16_t*>(s->d_im), s->X, s->Y, d_boxes, n, first, bin_size, nbins, max_iter, d_out, st)) return -1;
-  IA3_CUDA(cudaMemcpyAsync(ho, d_out, ob, cudaMemcpyDeviceToHost, st));
+  if (small_copy(ho, d_out, ob, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   memcpy(out, ho, ob);
   host_free(h); dev_free(d_boxes); dev_free(d_out); dev_free(d_ghist);
@@ -672,7 +732,7 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
     if (bytes) {
       char* h = static_cast<char*>(f->h_up) + up_off;
       memcpy(h, src, bytes);
-      if (cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("cudaMemcpyAsync (inputs) failed"); return -1; }
+      if (small_copy(*d, h, bytes, st)) return -1;
       up_off += (bytes + 255) / 256 * 256;
     }
     return 0;
@@ -770,7 +830,7 @@ int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
     IA3_CUDA(cudaMemsetAsync(f->d_tie_count, 0, sizeof(int), st));
     if (launch_voronoi(f->d, st)) return -1;
     if (reserve_pinned(&f->h_stage, &f->stage_cap, 256)) return -1;
-    IA3_CUDA(cudaMemcpyAsync(f->h_stage, f->d_tie_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (small_copy(f->h_stage, f->d_tie_count, sizeof(int), st)) return -1;
     IA3_CUDA(cudaStreamSynchronize(st));
     const int cnt = *static_cast<int*>(f->h_stage);
     f->n_ties = cnt;
@@ -791,8 +851,8 @@ int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
   if (reserve_pinned(&f->h_stage, &f->stage_cap, 2 * sizeof(int) * (size_t)n)) return -1;
   int* sp = static_cast<int*>(f->h_stage);
   int* kk = sp + n;
-  IA3_CUDA(cudaMemcpyAsync(sp, f->d_tie_spot, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
-  IA3_CUDA(cudaMemcpyAsync(kk, f->d_tie_k, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s->stream));
+  if (small_copy(sp, f->d_tie_spot, sizeof(int) * (size_t)n, f->s->stream) ||
+      small_copy(kk, f->d_tie_k, sizeof(int) * (size_t)n, f->s->stream)) return -1;
   IA3_CUDA(cudaStreamSynchronize(f->s->stream));
   for (int64_t i = 0; i < n; ++i) {
     const int sidx = sp[i], k = kk[i];
@@ -817,7 +877,7 @@ int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
   cudaStream_t st = f->s->stream;
   if (reserve_pinned(&f->h_up, &f->up_cap, (size_t)n)) return -1;
   memcpy(f->h_up, keep, (size_t)n);
-  IA3_CUDA(cudaMemcpyAsync(f->d_keep, f->h_up, (size_t)n, cudaMemcpyHostToDevice, st));
+  if (small_copy(f->d_keep, f->h_up, (size_t)n, st)) return -1;
   if (launch_apply_ties(f->d_mask, f->d.KW, f->d_tie_spot, f->d_tie_k, f->d_keep, (int)n, st)) return -1;
   return 0;        // stream-ordered before first_run; the arena is next touched after first_run's synchronisation
 }
@@ -836,7 +896,7 @@ static int fetch_results(ia3_fit* f, float* ps, double* p_raw, uint8_t* success,
   if (reserve_pinned(&f->h_stage, &f->stage_cap, total)) return -1;
   char* h = static_cast<char*>(f->h_stage);
   for (int i = 0; i < 5; ++i)
-    if (dst[i]) IA3_CUDA(cudaMemcpyAsync(h + off[i], src[i], sz[i], cudaMemcpyDeviceToHost, st));
+    if (dst[i] && small_copy(h + off[i], src[i], sz[i], st)) return -1;
   { IA3_STAT("  fetch: wait for stream"); IA3_DRAIN(st); }
   for (int i = 0; i < 5; ++i) if (dst[i]) memcpy(dst[i], h + off[i], sz[i]);
   return 0;
@@ -861,7 +921,7 @@ static int build_work(ia3_fit* f, const uint8_t* active, std::vector<int>& bound
     // the previous call on this handle ended with a stream synchronisation, so the arena is free
     if (reserve_pinned(&f->h_up, &f->up_cap, sizeof(int) * flat.size())) return -1;
     memcpy(f->h_up, flat.data(), sizeof(int) * flat.size());
-    IA3_CUDA(cudaMemcpyAsync(f->d_work, f->h_up, sizeof(int) * flat.size(), cudaMemcpyHostToDevice, f->s->stream));
+    if (small_copy(f->d_work, f->h_up, sizeof(int) * flat.size(), f->s->stream)) return -1;
   }
   return 0;
 }
@@ -1055,7 +1115,7 @@ int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   size_t off = 0;
   auto put = [&](void* d, const void* src, size_t bytes) -> int {
     memcpy(hp + off, src, bytes);
-    if (cudaMemcpyAsync(d, hp + off, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("cudaMemcpyAsync failed"); return -1; }
+    if (small_copy(d, hp + off, bytes, st)) return -1;
     off += (bytes + 255) / 256 * 256;
     return 0;
   };
@@ -1068,7 +1128,7 @@ int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   d.recenter = cfg->recenter ? 1 : 0; d.bk_f = cfg->bk_f; d.out = d_out;
   if (launch_moment_fit(d, st)) return -1;
   char* ho = hp + off;
-  IA3_CUDA(cudaMemcpyAsync(ho, d_out, b_out, cudaMemcpyDeviceToHost, st));
+  if (small_copy(ho, d_out, b_out, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   memcpy(out, ho, b_out);
   host_free(h);

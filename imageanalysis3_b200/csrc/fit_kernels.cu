@@ -27,6 +27,9 @@ constexpr int WARPS = 4;
 // memory of its SM instead of 32 K / 42 KB, so the seed kernels of the other in-flight stacks keep
 // running next to the stragglers.
 constexpr int FIT_WARPS = 1;
+#ifndef IA3_FIT_MINBLOCKS
+#define IA3_FIT_MINBLOCKS 8      // resident spots per SM the register allocation of k_fit aims at (255 registers)
+#endif
 constexpr unsigned FULL = 0xffffffffu;
 
 struct WarpExec {
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_voronoi(FitDev d) {
 
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(FIT_WARPS * 32) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
+__global__ void __launch_bounds__(FIT_WARPS * 32, IA3_FIT_MINBLOCKS) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long wi = (long long)blockIdx.x * FIT_WARPS + warp;

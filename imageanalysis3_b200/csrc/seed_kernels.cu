@@ -303,26 +303,40 @@ __device__ __noinline__ unsigned exact_from_global(const uint16_t* line, long lo
   return (unsigned)__double2int_rz(acc);
 }
 
-// U outputs from the register window; output o is centred on w[C + o]
+// U outputs from the register window; output o is centred on w[C + o].  Window entries are stored
+// biased, w = x + kHalfBias (half the high word of 2^20), so a pair sum is ONE integer add and is
+// already the high word of the double 2^20 + x- + x+.  gw.w[R + 1] = 2^16 + guard - 2^20 * sum(w)
+// turns the accumulator into t = 2^16 + v + guard: the truncated value sits in bits 4..19 of t's high
+// word, the next 32 bits are the fraction.  fraction < 2 * guard <=> v is within the guard of an
+// integer n -> recompute in scipy's exact order (n = 0 needs no check: the sum cannot be negative).
+constexpr int kHalfBias = 0x20980000;
+constexpr unsigned kGuardFrac = 172;       // 2 * kTruncGuard in units of 2^-32
 template <int R, int U, int C, int NW>
 __device__ __forceinline__ void window_outputs(const int (&w)[NW], const GaussW& gw, const double* wsh,
                                                const uint16_t* line, long long stride, int a, int L, unsigned (&res)[U]) {
   double acc[U];
 #pragma unroll
-  for (int o = 0; o < U; ++o) acc[o] = __hiloint2double(0x41300000 + w[C + o], 0) * gw.w[0];
+  for (int o = 0; o < U; ++o) acc[o] = __hiloint2double(w[C + o] + kHalfBias, 0) * gw.w[0];
 #pragma unroll
   for (int j = R; j >= 1; --j) {
 #pragma unroll
     for (int o = 0; o < U; ++o)
-      acc[o] = fma(__hiloint2double(0x41300000 + w[C + o - j] + w[C + o + j], 0), gw.w[j], acc[o]);
+      acc[o] = fma(__hiloint2double(w[C + o - j] + w[C + o + j], 0), gw.w[j], acc[o]);
   }
+  unsigned need = 0;
 #pragma unroll
   for (int o = 0; o < U; ++o) {
-    const double v = acc[o] - gw.w[R + 1];
-    const unsigned rlo = (unsigned)__double2loint(__dadd_rz(fmax(v - kTruncGuard, 0.0), 4503599627370496.0));
-    const unsigned rhi = (unsigned)__double2loint(__dadd_rz(v + kTruncGuard, 4503599627370496.0));
-    res[o] = rlo;
-    if (rlo != rhi && a + o < L) res[o] = exact_from_global<R>(line, stride, a + o, L, wsh);
+    const double t = acc[o] + gw.w[R + 1];
+    const unsigned hi = (unsigned)__double2hiint(t), lo = (unsigned)__double2loint(t);
+    const unsigned frac = __funnelshift_l(lo, hi, 28);
+    const unsigned n = (hi >> 4) & 0xffffu;
+    res[o] = n;
+    if (frac < kGuardFrac && n != 0) need |= 1u << o;
+  }
+  if (need) {
+#pragma unroll
+    for (int o = 0; o < U; ++o)
+      if ((need >> o & 1u) && a + o < L) res[o] = exact_from_global<R>(line, stride, a + o, L, wsh);
   }
 }
 
@@ -350,10 +364,10 @@ k_gauss_strided(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int
   if (!edge) {
     const uint16_t* p = line + (long long)(a0 - R) * inner;
 #pragma unroll
-    for (int i = 0; i < 2 * R; ++i, p += inner) w[i] = *p;
+    for (int i = 0; i < 2 * R; ++i, p += inner) w[i] = *p | kHalfBias;
     for (int a = a0; a < a1; a += U) {
 #pragma unroll
-      for (int i = 0; i < U; ++i, p += inner) w[2 * R + i] = *p;
+      for (int i = 0; i < U; ++i, p += inner) w[2 * R + i] = *p | kHalfBias;
       window_outputs<R, U, R, NW>(w, gw, wsh, line, inner, a, L, res);
 #pragma unroll
       for (int o = 0; o < U; ++o, op += inner) if (a + o < a1) *op = (uint16_t)res[o];
@@ -363,11 +377,11 @@ k_gauss_strided(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int
   } else {
     const int* ri = ridx_s;
 #pragma unroll
-    for (int i = 0; i < 2 * R; ++i) w[i] = line[(long long)ri[i] * inner];
+    for (int i = 0; i < 2 * R; ++i) w[i] = line[(long long)ri[i] * inner] | kHalfBias;
     ri += 2 * R;
     for (int a = a0; a < a1; a += U, ri += U) {
 #pragma unroll
-      for (int i = 0; i < U; ++i) w[2 * R + i] = line[(long long)ri[i] * inner];
+      for (int i = 0; i < U; ++i) w[2 * R + i] = line[(long long)ri[i] * inner] | kHalfBias;
       window_outputs<R, U, R, NW>(w, gw, wsh, line, inner, a, L, res);
 #pragma unroll
       for (int o = 0; o < U; ++o, op += inner) if (a + o < a1) *op = (uint16_t)res[o];
@@ -397,8 +411,10 @@ k_gauss_contig(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int 
   int w[NW];
   unsigned res[U];
   auto unpack = [&](const uint4& q, int at) {
-    w[at + 0] = q.x & 0xffff; w[at + 1] = q.x >> 16; w[at + 2] = q.y & 0xffff; w[at + 3] = q.y >> 16;
-    w[at + 4] = q.z & 0xffff; w[at + 5] = q.z >> 16; w[at + 6] = q.w & 0xffff; w[at + 7] = q.w >> 16;
+    w[at + 0] = __byte_perm(q.x, kHalfBias, 0x7610); w[at + 1] = __byte_perm(q.x, kHalfBias, 0x7632);
+    w[at + 2] = __byte_perm(q.y, kHalfBias, 0x7610); w[at + 3] = __byte_perm(q.y, kHalfBias, 0x7632);
+    w[at + 4] = __byte_perm(q.z, kHalfBias, 0x7610); w[at + 5] = __byte_perm(q.z, kHalfBias, 0x7632);
+    w[at + 6] = __byte_perm(q.w, kHalfBias, 0x7610); w[at + 7] = __byte_perm(q.w, kHalfBias, 0x7632);
   };
   const int* ri = ridx_s;
   if (!edge) {
@@ -407,13 +423,13 @@ k_gauss_contig(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int 
     for (int c = 0; c < 2 * H / 8; ++c) unpack(__ldg(p + c), 8 * c);
   } else {
 #pragma unroll
-    for (int i = 0; i < 2 * H; ++i) w[i] = line[ri[i]];
+    for (int i = 0; i < 2 * H; ++i) w[i] = line[ri[i]] | kHalfBias;
   }
   for (int a = a0; a < a1; a += U) {
     if (!edge) unpack(__ldg(reinterpret_cast<const uint4*>(line + (a + H))), 2 * H);
     else {
 #pragma unroll
-      for (int i = 0; i < U; ++i) w[2 * H + i] = line[ri[(a - a0) + 2 * H + i]];
+      for (int i = 0; i < U; ++i) w[2 * H + i] = line[ri[(a - a0) + 2 * H + i]] | kHalfBias;
     }
     window_outputs<R, U, H, NW>(w, gw, wsh, line, 1, a, L, res);
     uint4 q;
@@ -428,10 +444,10 @@ k_gauss_contig(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int 
 template <int R>
 static int launch_line_u16(const uint16_t* in, uint16_t* out, int L, long long inner, long long n_lines, bool contig,
                            const GaussW& gw, cudaStream_t st) {
-  GaussW gk = gw;                               // w[R + 1] = 2^20 * (w0 + w1 + ... + wR): the offset the kernels remove
+  GaussW gk = gw;                               // w[R + 1] = 2^16 + guard - 2^20 * (w0 + w1 + ... + wR), see window_outputs
   long double acc = 0.0L;
   for (int j = 0; j <= R; ++j) acc += (long double)gw.w[j];
-  gk.w[R + 1] = (double)(acc * 1048576.0L);
+  gk.w[R + 1] = (double)(65536.0L + (long double)kTruncGuard - acc * 1048576.0L);
   const int seg = (L <= 320) ? ((L + 7) / 8) * 8 : 256;
   dim3 grid((unsigned)((n_lines + LINES - 1) / LINES), (unsigned)((L + seg - 1) / seg));
   const size_t smem = (size_t)(seg + 2 * 32 + 2 * R + 16) * sizeof(int);

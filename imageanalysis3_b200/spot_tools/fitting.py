@@ -8,6 +8,8 @@ order- and dtype-sensitive numpy bookkeeping that operates on the (small) candid
 the dynamic-threshold descent, the hot-pixel filter, the unstable argsort and the top-N cut
 (SURVEY.md App. A, steps 6-10).
 """
+import os
+import threading
 import time
 
 import numpy as np
@@ -202,6 +204,13 @@ def _neighbor_slices(coord, crop_size, shape):
     return tuple(slice(int(a), int(b)) for a, b in zip(lo, hi))
 
 
+# Stacks that hold seed-stage work volumes at the same time (callers that keep many stacks in flight,
+# sharding.map_stacks).  The seed kernels fill the GPU with a few stacks; each one needs three more
+# copies of the stack in HBM, and letting all of them seed at once only inflates the allocation pool
+# (cudaMalloc while other stacks' kernels run stalls every stream).
+_SEED_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_SEED_INFLIGHT", "8"))))
+
+
 def fit_fov_image(im, channel, seeds=None,
                   seed_mask=None,
                   max_num_seeds=500,
@@ -224,24 +233,25 @@ def fit_fov_image(im, channel, seeds=None,
     if isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype in (np.uint16, np.float32):
         stack = _lib.Stack(im)     # one upload shared by the seed and the fit stage
     if seeds is None:
-        _seeds = get_seeds(im, max_num_seeds=max_num_seeds,
-                           th_seed=th_seed, th_seed_per=th_seed_per,
-                           use_percentile=use_percentile,
-                           use_dynamic_th=use_dynamic_th,
-                           dynamic_niters=dynamic_niters,
-                           min_dynamic_seeds=min_dynamic_seeds,
-                           remove_hot_pixel=remove_hot_pixel,
-                           return_h=False, verbose=False,
-                           _stack=stack if 'sel_center' not in seeding_kwargs else None,
-                           **seeding_kwargs)
+        with _SEED_GATE:
+            _seeds = get_seeds(im, max_num_seeds=max_num_seeds,
+                               th_seed=th_seed, th_seed_per=th_seed_per,
+                               use_percentile=use_percentile,
+                               use_dynamic_th=use_dynamic_th,
+                               dynamic_niters=dynamic_niters,
+                               min_dynamic_seeds=min_dynamic_seeds,
+                               remove_hot_pixel=remove_hot_pixel,
+                               return_h=False, verbose=False,
+                               _stack=stack if 'sel_center' not in seeding_kwargs else None,
+                               **seeding_kwargs)
+            if stack is not None:
+                stack.trim(1)          # the seed stage's work volumes go back to the other stacks in flight
         if verbose:
             print(f"{len(_seeds)} seeded with th={th_seed}, ", end='')
     else:
         _seeds = np.array(seeds)[:, :len(np.shape(im))]
         if verbose:
             print(f"{len(_seeds)} given, ", end='')
-    if stack is not None:
-        stack.trim(1)          # the seed stage's work volumes go back to the other stacks in flight
     if len(_seeds) == 0:
         return np.array([])
     if seed_mask is not None:

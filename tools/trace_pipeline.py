@@ -17,7 +17,7 @@ from imageanalysis3_b200.synth import synth_torch
 
 D = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-MODE = sys.argv[3] if len(sys.argv) > 3 else "both"      # both | seed | fit
+MODE = sys.argv[3] if len(sys.argv) > 3 else "both"      # both | seed | fit | first | e2e | upload
 QUIET = len(sys.argv) > 4
 SHAPE = (50, 2048, 2048)
 _lib.init(0)
@@ -25,7 +25,9 @@ dev = torch.device("cuda", 0)
 stacks = []
 for i in range(min(D, 4)):
     d = synth_torch(SHAPE, 5000, 1 + i, dev)
-    stacks.append((d, d.cpu().numpy().view(np.uint16)))
+    h = torch.empty(SHAPE, dtype=torch.int16, pin_memory=True)
+    h.copy_(d)
+    stacks.append((d, h.numpy().view(np.uint16)))
 torch.cuda.synchronize()
 T0 = time.perf_counter()
 trace = []
@@ -37,6 +39,16 @@ def step(i):
     def mark(name, t0):
         ev.append((name, 1e3 * (t0 - T0), 1e3 * (time.perf_counter() - T0)))
     t = time.perf_counter()
+    if MODE == "e2e":                      # the public call on a pinned host stack (bench.py's e2e leg)
+        spots = fitting.fit_fov_image(host, '647', th_seed=300.0, max_num_seeds=None, verbose=False)
+        mark("e2e", t)
+        trace.append((i, threading.get_ident() % 1000, ev))
+        return len(spots)
+    if MODE == "upload":                   # host -> device copy of the stack alone
+        _lib.Stack(host).close()
+        mark("upload", t)
+        trace.append((i, threading.get_ident() % 1000, ev))
+        return 0
     st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
     if MODE in ("fit", "first"):
         seeds = SEEDS[i % len(stacks)]
