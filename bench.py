@@ -207,13 +207,7 @@ def run_ours(args):
         """hot path with the stack already in HBM: seed stage + host replay + firstfit + repeatfit"""
         d = devt[i % n_stacks]
         st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
-        seeds = fitting.get_seeds(host[i % n_stacks], max_num_seeds=None, th_seed=TH_SEED, _stack=st)
-        st.trim(1)
-        f = Fitting_v4.iter_fit_seed_points(host[i % n_stacks], seeds.T, _stack=st)
-        f.firstfit()
-        f.repeatfit()
-        spots = f._ps_array()
-        spots = spots[np.sum(np.isnan(spots), axis=1) == 0]
+        spots = fitting.fit_fov_image(host[i % n_stacks], '647', _stack=st, **FIT_KW)
         return len(spots)
 
     def step_e2e(i):

@@ -441,6 +441,81 @@ k_gauss_contig(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int 
   }
 }
 
+// Short strided axis whose length is a compile-time constant (the z pass of the depths the
+// reference's datasets use): a thread holds its WHOLE line in registers, the reflected tap indices
+// are constants, so there is no window shift, no index table and no preload of 2R halo values -- the
+// segment kernel above spends half its instructions on those when the axis is shorter than the filter.
+__host__ __device__ constexpr int reflect_const(int i, int n) {
+  const int p = 2 * n;
+  int m = i % p;
+  if (m < 0) m += p;
+  return m < n ? m : p - 1 - m;
+}
+template <int R, int L, int A0, int U>
+__device__ __forceinline__ void static_outputs(int (&w)[L], const GaussW& gw, const double* wsh, const uint16_t* line,
+                                               long long stride, uint16_t* op) {
+  constexpr int N = (A0 + U <= L) ? U : (L - A0);
+  // the reflection makes index pairs repeat between output groups; without this the compiler keeps
+  // those pair sums alive across groups and spills
+#pragma unroll
+  for (int i = 0; i < L; ++i) asm volatile("" : "+r"(w[i]));
+  double acc[N];
+#pragma unroll
+  for (int o = 0; o < N; ++o) acc[o] = __hiloint2double(w[A0 + o] + kHalfBias, 0) * gw.w[0];
+#pragma unroll
+  for (int j = R; j >= 1; --j) {
+#pragma unroll
+    for (int o = 0; o < N; ++o)
+      acc[o] = fma(__hiloint2double(w[reflect_const(A0 + o - j, L)] + w[reflect_const(A0 + o + j, L)], 0), gw.w[j], acc[o]);
+  }
+  unsigned res[N];
+  unsigned need = 0;
+#pragma unroll
+  for (int o = 0; o < N; ++o) {
+    const double t = acc[o] + gw.w[R + 1];
+    const unsigned hi = (unsigned)__double2hiint(t), lo = (unsigned)__double2loint(t);
+    const unsigned frac = __funnelshift_l(lo, hi, 28);
+    const unsigned n = (hi >> 4) & 0xffffu;
+    res[o] = n;
+    if (frac < kGuardFrac && n != 0) need |= 1u << o;
+  }
+  if (need) {
+#pragma unroll
+    for (int o = 0; o < N; ++o)
+      if (need >> o & 1u) res[o] = exact_from_global<R>(line, stride, A0 + o, L, wsh);
+  }
+#pragma unroll
+  for (int o = 0; o < N; ++o) op[(long long)(A0 + o) * stride] = (uint16_t)res[o];
+  if constexpr (A0 + U < L) static_outputs<R, L, A0 + U, U>(w, gw, wsh, line, stride, op);
+}
+
+template <int R, int L>
+__global__ void __launch_bounds__(LINES, 4)
+k_gauss_short(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long inner, long long n_lines, GaussW gw) {
+  __shared__ double wsh[R + 1];
+  if (threadIdx.x <= R) wsh[threadIdx.x] = gw.w[threadIdx.x];
+  __syncthreads();
+  const long long l = (long long)blockIdx.x * LINES + threadIdx.x;
+  if (l >= n_lines) return;
+  const long long base = (l / inner) * ((long long)L * inner) + (l % inner);
+  const uint16_t* line = in + base;
+  int w[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) w[i] = line[(long long)i * inner] | kHalfBias;
+  static_outputs<R, L, 0, 8>(w, gw, wsh, line, inner, out + base);
+}
+
+template <int R, int L>
+static int launch_short_u16(const uint16_t* in, uint16_t* out, long long inner, long long n_lines, const GaussW& gw, cudaStream_t st) {
+  GaussW gk = gw;
+  long double acc = 0.0L;
+  for (int j = 0; j <= R; ++j) acc += (long double)gw.w[j];
+  gk.w[R + 1] = (double)(65536.0L + (long double)kTruncGuard - acc * 1048576.0L);
+  k_gauss_short<R, L><<<(unsigned)((n_lines + LINES - 1) / LINES), LINES, 0, st>>>(in, out, inner, n_lines, gk);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int R>
 static int launch_line_u16(const uint16_t* in, uint16_t* out, int L, long long inner, long long n_lines, bool contig,
                            const GaussW& gw, cudaStream_t st) {
@@ -513,6 +588,12 @@ static int dispatch_axis_u16(const uint16_t* in, uint16_t* out, int L, long long
                              cudaStream_t st) {
   // register-window kernels; the contiguous pass needs 16-byte aligned rows
   const bool aligned = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  if (!INNER1) {                                  // stack depths of the reference's datasets: whole line in registers
+    if (L == 50 && gw.r == 30) return launch_short_u16<30, 50>(in, out, inner, n_lines, gw, st);
+    if (L == 50 && gw.r == 3) return launch_short_u16<3, 50>(in, out, inner, n_lines, gw, st);
+    if (L == 30 && gw.r == 30) return launch_short_u16<30, 30>(in, out, inner, n_lines, gw, st);
+    if (L == 30 && gw.r == 3) return launch_short_u16<3, 30>(in, out, inner, n_lines, gw, st);
+  }
   if (!INNER1 || aligned) {
     switch (gw.r) {
       case 3: return launch_line_u16<3>(in, out, L, inner, n_lines, INNER1, gw, st);

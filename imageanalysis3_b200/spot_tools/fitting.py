@@ -222,15 +222,16 @@ def fit_fov_image(im, channel, seeds=None,
                   normalize_background=False, normalize_local=False,
                   background_args={},
                   fitting_args={},
-                  remove_boundary_points=True, verbose=True):
+                  remove_boundary_points=True, verbose=True, _stack=None):
     """Seeding + fitting of a whole field-of-view stack -> (M, 11) spots
-    [height, z, x, y, background, sigma_z, sigma_x, sigma_y, sin_t, sin_p, eps]."""
+    [height, z, x, y, background, sigma_z, sigma_x, sigma_y, sin_t, sin_p, eps].
+    `_stack` (not in the reference): a `_lib.Stack` that already holds `im` in HBM."""
     th_seed = float(th_seed)
     if verbose:
         print(f"-- start fitting spots in channel:{channel}, ", end='')
         t0 = time.time()
-    stack = None
-    if isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype in (np.uint16, np.float32):
+    stack = _stack
+    if stack is None and isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype in (np.uint16, np.float32):
         stack = _lib.Stack(im)     # one upload shared by the seed and the fit stage
     if seeds is None:
         with _SEED_GATE:

@@ -24,7 +24,7 @@ def test_gaussian_volumes_bit_exact_u16(lib, golden_seeds, sigma):
     assert np.array_equal(st.seed_volume(1), want)
 
 
-@pytest.mark.parametrize("shape", [(5, 7, 9), (30, 33, 70), (3, 130, 257), (61, 40, 8)])
+@pytest.mark.parametrize("shape", [(5, 7, 9), (30, 33, 70), (3, 130, 257), (61, 40, 8), (50, 24, 72), (50, 130, 33)])
 def test_gaussian_ragged_shapes(lib, shape):
     """radius > axis length (repeated reflection), sizes that are not multiples of the tile"""
     rng = np.random.default_rng(3)
@@ -38,8 +38,9 @@ def test_gaussian_ragged_shapes(lib, shape):
 def test_gaussian_extremes(lib):
     """constant / saturated volumes: sums that are exact integers in exact arithmetic sit on the
     truncation boundary, so the FP64 accumulation order decides the result"""
-    for val in (0, 1, 300, 65535):
-        im = np.full((12, 40, 48), val, dtype=np.uint16)
+    for val, shape in ((0, (12, 40, 48)), (1, (12, 40, 48)), (300, (12, 40, 48)), (65535, (12, 40, 48)),
+                       (300, (50, 16, 24)), (65535, (30, 16, 24)), (0, (50, 16, 24))):   # + the whole-line z kernels
+        im = np.full(shape, val, dtype=np.uint16)
         st = lib.Stack(im)
         st.seed_candidates(_half(0.75), _half(7.5), 3, 0, 2.0, 1e9)
         assert np.array_equal(st.seed_volume(0), seed_oracle.gaussian_filter_c(im, 0.75)), val
