@@ -291,7 +291,7 @@ def run_ours(args):
     achieved = alg_bytes / (bg_launch_ms * 1e-3) / 1e9
     seed_ms_med = float(np.median(stage["seed_total"]))
     stage_bytes = 2.0 * vox + 16.0 * float(np.median(stage["n_cand"]))
-    fp64_inst = 36.0 * vox                                  # 31 DFMA + 5 FP64 adds (offset, guards) per voxel
+    fp64_inst = 32.0 * vox                                  # 1 DMUL + 30 DFMA + 1 DADD (offset + guard) per voxel
     fit_flops_per_spot = 1.67e6                             # model / Jacobian / normal equations per spot
     line = {
         "metric": "spots_fitted_per_s", "value": n_spots / (ms_dev * 1e-3), "unit": "spots/s",
@@ -310,9 +310,10 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps, "stacks_per_s": world * args.steps / (ms_e2e * 1e-3)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(),
-                     "kernel": "k_gauss_strided<30> / k_gauss_contig<30> (one 61-tap bit-exact axis pass; 3 launches per stack, mean)",
+                     "kernel": "k_gauss_short<30,50> / k_gauss_strided<30> / k_gauss_contig<30> (one 61-tap bit-exact axis pass; 3 launches per stack, mean)",
                      "launch_ms": bg_launch_ms, "peak_source": peak_src,
-                     "note": "exact uint16 semantics make this pass FP64-pipe bound, not HBM bound: 36 FP64 instructions per voxel",
+                     "note": "exact uint16 semantics make this pass FP64-pipe / issue bound, not HBM bound: 32 FP64 + ~60 integer instructions per voxel; "
+                             "by time the dominant kernel of a step is k_fit<double> (latency bound, see roofline_fit and profiles/r01_ncu_launch_list_final.csv)",
                      "fp64_inst_per_s": fp64_inst / (bg_launch_ms * 1e-3),
                      "fp64_pipe_frac": fp64_inst / (bg_launch_ms * 1e-3) / (148 * 64 * 1.965e9),
                      "seed_stage": {"ms": seed_ms_med, "algorithmic_bytes": stage_bytes,

@@ -441,6 +441,71 @@ k_gauss_contig(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int 
   }
 }
 
+// Contiguous axis, small radius (R <= 8): a warp owns 256 consecutive outputs of one row.  Every lane
+// loads its 8 values with one 16-byte load (the warp's request is one coalesced 512-byte line) and
+// takes the R halo values on each side from its neighbours' registers by shuffle; only the first and
+// last lane of a row segment read their halo from memory (reflected at the row ends).
+template <int R>
+__global__ void __launch_bounds__(LINES)
+k_gauss_row(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int L, long long n_rows, int segs, GaussW gw) {
+  static_assert(R <= 8, "halo must come from the adjacent lanes");
+  constexpr int U = 8, NW = 2 * R + U;
+  __shared__ double wsh[R + 1];
+  if (threadIdx.x <= R) wsh[threadIdx.x] = gw.w[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * (LINES / 32) + (threadIdx.x >> 5);     // (row, segment)
+  if (item >= n_rows * segs) return;
+  const long long row = item / segs;
+  const int y0 = (int)(item - row * segs) * 256 + lane * U;
+  const uint16_t* line = in + row * (long long)L;
+  const bool active = y0 < L;                                   // L is a multiple of 8
+  uint4 q = make_uint4(0, 0, 0, 0);
+  if (active) q = __ldg(reinterpret_cast<const uint4*>(line + y0));
+  // neighbours' packed words: the last 8 values of lane - 1, the first 8 of lane + 1
+  uint4 ql, qr;
+  ql.x = __shfl_up_sync(0xffffffffu, q.x, 1); ql.y = __shfl_up_sync(0xffffffffu, q.y, 1);
+  ql.z = __shfl_up_sync(0xffffffffu, q.z, 1); ql.w = __shfl_up_sync(0xffffffffu, q.w, 1);
+  qr.x = __shfl_down_sync(0xffffffffu, q.x, 1); qr.y = __shfl_down_sync(0xffffffffu, q.y, 1);
+  qr.z = __shfl_down_sync(0xffffffffu, q.z, 1); qr.w = __shfl_down_sync(0xffffffffu, q.w, 1);
+  if (!active) return;
+  int w[NW];
+  auto unpack = [&](const uint4& v, int (&d)[8]) {
+    d[0] = __byte_perm(v.x, kHalfBias, 0x7610); d[1] = __byte_perm(v.x, kHalfBias, 0x7632);
+    d[2] = __byte_perm(v.y, kHalfBias, 0x7610); d[3] = __byte_perm(v.y, kHalfBias, 0x7632);
+    d[4] = __byte_perm(v.z, kHalfBias, 0x7610); d[5] = __byte_perm(v.z, kHalfBias, 0x7632);
+    d[6] = __byte_perm(v.w, kHalfBias, 0x7610); d[7] = __byte_perm(v.w, kHalfBias, 0x7632);
+  };
+  int c[8], l8[8], r8[8];
+  unpack(q, c); unpack(ql, l8); unpack(qr, r8);
+#pragma unroll
+  for (int i = 0; i < U; ++i) w[R + i] = c[i];
+  const bool first = (lane == 0), last = (lane == 31) || (y0 + U >= L);
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    w[i] = first ? (int)(line[reflect_idx(y0 - R + i, L)] | kHalfBias) : l8[8 - R + i];
+    w[R + U + i] = last ? (int)(line[reflect_idx(y0 + U + i, L)] | kHalfBias) : r8[i];
+  }
+  unsigned res[U];
+  window_outputs<R, U, R, NW>(w, gw, wsh, line, 1, y0, L, res);
+  uint4 o;
+  o.x = res[0] | (res[1] << 16); o.y = res[2] | (res[3] << 16); o.z = res[4] | (res[5] << 16); o.w = res[6] | (res[7] << 16);
+  *reinterpret_cast<uint4*>(out + row * (long long)L + y0) = o;
+}
+
+template <int R>
+static int launch_row_u16(const uint16_t* in, uint16_t* out, int L, long long n_rows, const GaussW& gw, cudaStream_t st) {
+  GaussW gk = gw;
+  long double acc = 0.0L;
+  for (int j = 0; j <= R; ++j) acc += (long double)gw.w[j];
+  gk.w[R + 1] = (double)(65536.0L + (long double)kTruncGuard - acc * 1048576.0L);
+  const int segs = (L + 255) / 256;
+  const long long items = n_rows * segs;
+  k_gauss_row<R><<<(unsigned)((items + LINES / 32 - 1) / (LINES / 32)), LINES, 0, st>>>(in, out, L, n_rows, segs, gk);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
 // Short strided axis whose length is a compile-time constant (the z pass of the depths the
 // reference's datasets use): a thread holds its WHOLE line in registers, the reflected tap indices
 // are constants, so there is no window shift, no index table and no preload of 2R halo values -- the
@@ -594,6 +659,7 @@ static int dispatch_axis_u16(const uint16_t* in, uint16_t* out, int L, long long
     if (L == 30 && gw.r == 30) return launch_short_u16<30, 30>(in, out, inner, n_lines, gw, st);
     if (L == 30 && gw.r == 3) return launch_short_u16<3, 30>(in, out, inner, n_lines, gw, st);
   }
+  if (INNER1 && aligned && gw.r == 3) return launch_row_u16<3>(in, out, L, n_lines, gw, st);
   if (!INNER1 || aligned) {
     switch (gw.r) {
       case 3: return launch_line_u16<3>(in, out, L, inner, n_lines, INNER1, gw, st);

@@ -208,7 +208,7 @@ def _neighbor_slices(coord, crop_size, shape):
 # sharding.map_stacks).  The seed kernels fill the GPU with a few stacks; each one needs three more
 # copies of the stack in HBM, and letting all of them seed at once only inflates the allocation pool
 # (cudaMalloc while other stacks' kernels run stalls every stream).
-_SEED_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_SEED_INFLIGHT", "8"))))
+_SEED_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_SEED_INFLIGHT", "6"))))
 
 
 def fit_fov_image(im, channel, seeds=None,
