@@ -940,6 +940,7 @@ int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw,
   IA3_CUDA(cudaEventRecord(f->e0, st));
   if (launch_init_window(f->d, st)) return -1;
   if (launch_fit(f->d, 0, nullptr, f->n, f->cfg.eval_fp32 != 0, st)) return -1;
+  IA3_DRAIN(st);                                  // see ia3_fit_repeat_sweep
   for (int l = 0; l < f->n_levels; ++l)
     if (launch_subtract(f->d, f->d_work + bounds[l], bounds[l + 1] - bounds[l], st)) return -1;
   if (launch_window_copy(f->d, f->d_snap, nullptr, 0, st)) return -1;
@@ -960,8 +961,14 @@ int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active,
   std::vector<int> bounds;
   if (build_work(f, active, bounds)) return -1;
   IA3_CUDA(cudaEventRecord(f->e0, st));
-  for (int l = 0; l < f->n_levels; ++l)
+  // A sweep kernel lasts as long as its slowest fit (a junk seed that runs MINPACK to maxfev: tens of
+  // ms).  Nothing is queued behind a running k_fit: with more stacks in flight than hardware queues
+  // (32), an item waiting for it would also hold back the other stacks that share the queue, and the
+  // whole pipeline would run at 32 / (latency of one stack).  So wait, then enqueue the next level.
+  for (int l = 0; l < f->n_levels; ++l) {
     if (launch_fit(f->d, 1, f->d_work + bounds[l], bounds[l + 1] - bounds[l], f->cfg.eval_fp32 != 0, st)) return -1;
+    if (bounds[l + 1] > bounds[l]) IA3_DRAIN(st);
+  }
   IA3_CUDA(cudaEventRecord(f->e1, st));
   if (fetch_results(f, ps, p_raw, success, nfev, info)) return -1;
   cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);

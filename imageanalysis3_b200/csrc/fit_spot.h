@@ -13,6 +13,8 @@
 namespace ia3 {
 
 // Per-spot scratch that must be visible to every lane (shared memory on the device).
+constexpr int GRAM_PITCH = 36;    // doubles per column: lanes write consecutive words, fragment reads hit 16 distinct banks
+
 template <typename T>
 struct SpotShared {
   LMState st;
@@ -21,6 +23,7 @@ struct SpotShared {
   double etab[NEXP];      // exp table of the parameter transforms (one slot per lane)
   double x0[NP];
   double small10[10], large10[10];
+  double gram[(NP + 1) * GRAM_PITCH];   // device: [J | f] of the current batch of 32 voxels, column-major (pass_fused_mma)
 };
 
 // Executor interface (WarpExec in fit_kernels.cu, SerialExec in tests/hostsim):
@@ -193,8 +196,86 @@ IA3_HD void pass_jacobian(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, doub
 // saves a voxel sweep per accepted step (most steps are) at the price of a discarded Jacobian per
 // rejected one.  Residuals that are inf / NaN / huge go through pass_residual's enorm-faithful path
 // (the step is then rejected and the sums are never used).
+#if defined(__CUDACC__)
+#ifndef IA3_FIT_MMA
+#define IA3_FIT_MMA 1
+#endif
+// C(8x8) += A(8x4) B(4x8) in FP64 on the tensor cores.  Lane l holds A[l / 4][l % 4], B[l % 4][l / 4] and
+// C[l / 4][2 (l % 4) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// pass_fused on the warp: the normal-equation sums as G^T G with G = [J | f] (m x 11).  The 65 sums
+// used to be 65 FP64 accumulators per lane plus a 65-entry butterfly reduction; here the lanes stage
+// the 11 values of their voxel in shared memory (32 voxels per batch) and three 8x8 FP64 tensor-core
+// tiles accumulate G^T G over the batch's eight 4-voxel slices: rows/columns 0-7 (T00), 0-7 x 8-15
+// (T01) and 8-15 x 8-15 (T11) of the 16x16 padded product.  6 accumulator registers per lane instead
+// of 130, and the cross-lane reduction is part of the MMA.  Same products as the scalar path (float32
+// Jacobian entries widened to FP64), different summation order.
 template <typename T, typename Exec, typename Vox>
-IA3_HD double pass_fused(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* Ag_out) {
+__device__ __forceinline__ double pass_fused_mma(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* Ag_out, double* gt) {
+  static_assert(NP == 10, "tile bookkeeping below assumes 10 parameters + the residual column");
+  const double agiant = 1.304e19 / (double)vox.m;
+  const int lane = ex.lane();
+  const int g = lane >> 2, q = lane & 3;
+  double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c11a = 0.0, c11b = 0.0;
+  int nbad = 0;
+  for (int k0 = 0; k0 < vox.m; k0 += 32) {
+    const int k = k0 + lane;
+    float J[NP];
+    double r = 0.0;
+    if (k < vox.m) {
+      T X0, X1, X2, d, res;
+      vox.get(k, X0, X1, X2, d);
+      eval_jac<T>(vc, X0, X1, X2, d, res, J);
+      r = (double)res;
+      if (!(fabs(r) < agiant)) nbad += 1;
+    } else {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) J[i] = 0.f;
+    }
+    ex.sync();                                   // the previous batch's fragments have been read
+#pragma unroll
+    for (int i = 0; i < NP; ++i) gt[i * GRAM_PITCH + lane] = (double)J[i];
+    gt[NP * GRAM_PITCH + lane] = r;
+    ex.sync();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double f0 = gt[g * GRAM_PITCH + 4 * c + q];                           // column g, voxel 4c + q of the batch
+      const double f1 = (g < 3) ? gt[(8 + g) * GRAM_PITCH + 4 * c + q] : 0.0;     // columns 8, 9 and f; 11-15 are padding
+      dmma884(c00a, c00b, f0, f0);
+      dmma884(c01a, c01b, f0, f1);
+      dmma884(c11a, c11b, f1, f1);
+    }
+  }
+  // scatter the upper triangle / the J^T f column to the packed layout lm_factor reads
+  {
+    const int j0 = 2 * q, j1 = j0 + 1;
+    if (g <= j0) Ag_out[tri(g, j0)] = c00a;
+    if (g <= j1) Ag_out[tri(g, j1)] = c00b;
+    const int ja = 8 + j0, jb = ja + 1;
+    if (ja < NP) Ag_out[tri(g, ja)] = c01a; else if (ja == NP) Ag_out[NTRI + g] = c01a;
+    if (jb < NP) Ag_out[tri(g, jb)] = c01b; else if (jb == NP) Ag_out[NTRI + g] = c01b;
+    const int i = 8 + g;
+    if (i < NP) {
+      if (ja < NP) { if (i <= ja) Ag_out[tri(i, ja)] = c11a; } else if (ja == NP) Ag_out[NTRI + i] = c11a;
+      if (jb < NP) { if (i <= jb) Ag_out[tri(i, jb)] = c11b; } else if (jb == NP) Ag_out[NTRI + i] = c11b;
+    }
+  }
+  const double s2 = ex.bcast(c11a, 9);           // (f, f): lane 9 = row 8 + 2, column 8 + 2
+  nbad = ex.allsum_int(nbad);
+  if (nbad == 0) return sqrt(s2);
+  return pass_residual<T>(ex, vc, vox, (double*)0);
+}
+#endif
+
+template <typename T, typename Exec, typename Vox>
+IA3_HD double pass_fused(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* Ag_out, double* gram) {
+#if defined(__CUDA_ARCH__) && IA3_FIT_MMA
+  if constexpr (Exec::W == 32) return pass_fused_mma<T>(ex, vc, vox, Ag_out, gram);
+#endif
+  (void)gram;
   const double agiant = 1.304e19 / (double)vox.m;
   double acc[NTRI + NP];
 #pragma unroll
@@ -249,7 +330,7 @@ IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const dou
                    const double* origin, const Vox& vox, SpotShared<T>& sh) {
   LMState& st = sh.st;
   build_consts_par<T>(ex, fp, cen_est, origin, sh.x0, sh);
-  const double fn0 = pass_fused<T>(ex, sh.vc, vox, sh.Ag);       // f(x0) and J(x0)
+  const double fn0 = pass_fused<T>(ex, sh.vc, vox, sh.Ag, sh.gram);       // f(x0) and J(x0)
   lm_init(ex, st, sh.x0, fn0);
   for (;;) {
     // sh.Ag holds J^T J, J^T f at st.x (x0, or the trial point that was just accepted)
@@ -259,7 +340,7 @@ IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const dou
     for (;;) {
       lm_propose(ex, st);
       build_consts_par<T>(ex, fp, cen_est, origin, st.xt, sh);
-      const double fn1 = pass_fused<T>(ex, sh.vc, vox, sh.Ag);   // lm_outer has consumed the old sums
+      const double fn1 = pass_fused<T>(ex, sh.vc, vox, sh.Ag, sh.gram);   // lm_outer has consumed the old sums
       action = lm_judge(ex, st, cfg, fn1);
       if (action != LM_RETRY) break;
     }

@@ -1,6 +1,7 @@
 """GPU: where the wall time of D concurrent fit_fov_image-like steps goes (host-side phase trace).
     python tools/trace_pipeline.py [D] [K]
 """
+import os
 import sys
 import threading
 import time
@@ -21,6 +22,12 @@ MODE = sys.argv[3] if len(sys.argv) > 3 else "both"      # both | seed | fit | f
 QUIET = len(sys.argv) > 4
 SHAPE = (50, 2048, 2048)
 _lib.init(0)
+if os.environ.get("TRACE_MAXFEV"):         # experiment only (not reference semantics): how much of the pipeline's
+    _orig_cfg = _lib.make_fit_cfg          # latency is the few junk seeds that run MINPACK to maxfev = 1000
+    def _cfg(*a, **kw):
+        kw["maxfev"] = int(os.environ["TRACE_MAXFEV"])
+        return _orig_cfg(*a, **kw)
+    _lib.make_fit_cfg = _cfg
 dev = torch.device("cuda", 0)
 stacks = []
 for i in range(min(D, 4)):
