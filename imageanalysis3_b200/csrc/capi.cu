@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <thread>
 #include <time.h>
 #include <cmath>
 #include <cstdlib>
@@ -14,6 +16,7 @@
 
 #include "../../include/ia3b200.h"
 #include "fit_kernels.h"
+#include "fit_spot.h"
 #include "ia3_device.h"
 #include "seed_kernels.h"
 
@@ -322,9 +325,115 @@ struct ia3_fit {
   void* h_stage = nullptr; size_t stage_cap = 0;      // pinned staging, device -> host (results, ties)
   void* h_up = nullptr; size_t up_cap = 0;            // pinned staging, host -> device (inputs, work lists)
   uint8_t* d_keep = nullptr; size_t keep_cap = 0;
+  LMPause* d_pause = nullptr; int* d_pause_ctl = nullptr; int* h_pause_ctl = nullptr;   // suspended long runs (k_fit)
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   float last_ms = 0.f;
 };
+
+// ---- continuation service ---------------------------------------------------------------------
+// k_fit suspends a run after g_fit_cap function evaluations (fit_kernels.cu: fit_one).  The suspended
+// spots of every stack in flight are continued here, together, by one thread on one stream: a round =
+// one k_fit_resume launch over all pending spots, g_fit_cap more evaluations each.  A stack's own
+// launches therefore stay short, and the few junk seeds that run MINPACK to maxfev hold one hardware
+// queue in total instead of one per stack.
+static int fit_cap_from_env() {
+  const char* e = getenv("IA3_FIT_CAP");
+  const int v = e ? atoi(e) : 100;
+  return v < 0 ? 0 : v;
+}
+static const int g_fit_cap = fit_cap_from_env();
+struct SvcJob {
+  FitDev d;
+  int mode = 0;
+  std::vector<int> spots;
+  bool done = false, failed = false;
+  std::condition_variable cv;
+};
+// never destroyed: the service thread is detached and may be waiting on them when the process exits
+// (destroying a condition variable with a waiter blocks the exit)
+static std::mutex& g_svc_mu = *new std::mutex;
+static std::condition_variable& g_svc_cv = *new std::condition_variable;
+static std::vector<SvcJob*>& g_svc_in = *new std::vector<SvcJob*>;
+static std::once_flag g_svc_once;
+
+static void svc_main(int device) {
+  constexpr int MAXJ = 512, MAXE = 16384;
+  FitDev* devs = nullptr;
+  FitResume* ent = nullptr;
+  cudaStream_t st = nullptr;
+  bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMallocHost((void**)&devs, sizeof(FitDev) * MAXJ) == cudaSuccess && cudaMallocHost((void**)&ent, sizeof(FitResume) * MAXE) == cudaSuccess;
+  std::vector<SvcJob*> active, batch;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(g_svc_mu);
+      if (active.empty()) g_svc_cv.wait(lk, [] { return !g_svc_in.empty(); });
+      active.insert(active.end(), g_svc_in.begin(), g_svc_in.end());
+      g_svc_in.clear();
+    }
+    batch.clear();
+    int ne = 0, smem = 0;
+    for (SvcJob* j : active) {
+      if ((int)batch.size() == MAXJ || ne + (int)j->spots.size() > MAXE) break;
+      devs[batch.size()] = j->d;
+      for (int sp : j->spots) ent[ne++] = FitResume{(int)batch.size(), sp, j->mode, -1};
+      smem = std::max(smem, fit_smem_bytes(j->d.K, false));
+      batch.push_back(j);
+    }
+    bool fail = !ok;
+    if (!fail) fail = launch_fit_resume(devs, ent, ne, g_fit_cap, smem, st) != 0 || cudaStreamSynchronize(st) != cudaSuccess;
+    if (fail) {
+      std::lock_guard<std::mutex> lk(g_svc_mu);
+      for (SvcJob* j : active) { j->failed = true; j->done = true; j->cv.notify_all(); }
+      active.clear();
+      continue;
+    }
+    for (SvcJob* j : batch) j->spots.clear();
+    for (int e = 0; e < ne; ++e)
+      if (ent[e].status != FIT_DONE) batch[ent[e].job]->spots.push_back(ent[e].spot);
+    std::vector<SvcJob*> still;
+    {
+      std::lock_guard<std::mutex> lk(g_svc_mu);
+      for (SvcJob* j : active) {
+        if (j->spots.empty()) { j->done = true; j->cv.notify_all(); }
+        else still.push_back(j);
+      }
+    }
+    active.swap(still);
+  }
+}
+
+// blocks until the suspended spots (h_pause_ctl[1..np]) of this handle have finished
+static int service_run(ia3_fit* f, int mode, int np) {
+  std::call_once(g_svc_once, [] { std::thread(svc_main, g_device).detach(); });
+  SvcJob job;
+  job.d = f->d;
+  job.mode = mode;
+  job.spots.assign(f->h_pause_ctl + 1, f->h_pause_ctl + 1 + np);
+  std::unique_lock<std::mutex> lk(g_svc_mu);
+  g_svc_in.push_back(&job);
+  g_svc_cv.notify_one();
+  job.cv.wait(lk, [&] { return job.done; });
+  if (job.failed) { set_error("continuation of suspended fits failed"); return -1; }
+  return 0;
+}
+
+// one k_fit launch on the handle's stream, then (cap > 0) hand the spots it suspended to the service
+static int run_fit_launch(ia3_fit* f, int mode, const int* work, long long n_work) {
+  if (n_work <= 0) return 0;
+  cudaStream_t st = f->s->stream;
+  const bool capped = f->d.cap > 0;
+  if (capped) IA3_CUDA(cudaMemsetAsync(f->d_pause_ctl, 0, sizeof(int), st));
+  if (launch_fit(f->d, mode, work, n_work, f->cfg.eval_fp32 != 0, st)) return -1;
+  if (capped && small_copy(f->h_pause_ctl, f->d_pause_ctl, sizeof(int) * (size_t)(1 + f->d.pause_slots), st)) return -1;
+  // A sweep kernel lasts as long as its slowest fit; nothing is queued behind it (an item waiting for it
+  // would also hold back the other stacks that share the hardware queue).
+  IA3_DRAIN(st);
+  if (!capped) return 0;
+  const int np = std::min(f->h_pause_ctl[0], f->d.pause_slots);
+  { IA3_STAT("  suspended spots -> service"); if (np > 0 && service_run(f, mode, np)) return -1; }
+  return 0;
+}
 
 extern "C" {
 
@@ -790,6 +899,16 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   d.lm.ftol = 1.49012e-8; d.lm.xtol = 1.49012e-8; d.lm.gtol = 0.0; d.lm.factor = 100.0;
   d.lm.maxfev = cfg->maxfev > 0 ? cfg->maxfev : (cfg->personality == 4 ? 1000 : 1100);
   for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
+  d.cap = (cfg->eval_fp32 != 0) ? 0 : g_fit_cap;
+  if (d.cap > 0) {
+    d.pause_slots = (int)std::min<int64_t>(std::max<int64_t>(n, 1), 1024);
+    void* hp = nullptr;
+    if (dev_alloc((void**)&f->d_pause, sizeof(LMPause) * (size_t)d.pause_slots) ||
+        dev_alloc((void**)&f->d_pause_ctl, sizeof(int) * (size_t)(1 + d.pause_slots)) ||
+        host_alloc(&hp, sizeof(int) * (size_t)(1 + d.pause_slots))) { ia3_fit_destroy(f); return -1; }
+    f->h_pause_ctl = static_cast<int*>(hp);
+    d.pause_buf = f->d_pause; d.pause_ctl = f->d_pause_ctl;
+  }
   IA3_CUDA(cudaStreamSynchronize(st));
   *out = f;
   return 0;
@@ -808,7 +927,8 @@ int ia3_fit_destroy(ia3_fit* f) {
   release_event(f->e1);
   host_free(f->h_stage);
   host_free(f->h_up);
-  dev_free(f->d_keep);
+  host_free(f->h_pause_ctl);
+  dev_free(f->d_keep); dev_free(f->d_pause); dev_free(f->d_pause_ctl);
   delete f;
   return 0;
 }
@@ -939,8 +1059,7 @@ int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw,
   if (build_work(f, nullptr, bounds)) return -1;
   IA3_CUDA(cudaEventRecord(f->e0, st));
   if (launch_init_window(f->d, st)) return -1;
-  if (launch_fit(f->d, 0, nullptr, f->n, f->cfg.eval_fp32 != 0, st)) return -1;
-  IA3_DRAIN(st);                                  // see ia3_fit_repeat_sweep
+  if (run_fit_launch(f, 0, nullptr, f->n)) return -1;
   for (int l = 0; l < f->n_levels; ++l)
     if (launch_subtract(f->d, f->d_work + bounds[l], bounds[l + 1] - bounds[l], st)) return -1;
   if (launch_window_copy(f->d, f->d_snap, nullptr, 0, st)) return -1;
@@ -961,14 +1080,8 @@ int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active,
   std::vector<int> bounds;
   if (build_work(f, active, bounds)) return -1;
   IA3_CUDA(cudaEventRecord(f->e0, st));
-  // A sweep kernel lasts as long as its slowest fit (a junk seed that runs MINPACK to maxfev: tens of
-  // ms).  Nothing is queued behind a running k_fit: with more stacks in flight than hardware queues
-  // (32), an item waiting for it would also hold back the other stacks that share the queue, and the
-  // whole pipeline would run at 32 / (latency of one stack).  So wait, then enqueue the next level.
-  for (int l = 0; l < f->n_levels; ++l) {
-    if (launch_fit(f->d, 1, f->d_work + bounds[l], bounds[l + 1] - bounds[l], f->cfg.eval_fp32 != 0, st)) return -1;
-    if (bounds[l + 1] > bounds[l]) IA3_DRAIN(st);
-  }
+  for (int l = 0; l < f->n_levels; ++l)
+    if (run_fit_launch(f, 1, f->d_work + bounds[l], bounds[l + 1] - bounds[l])) return -1;
   IA3_CUDA(cudaEventRecord(f->e1, st));
   if (fetch_results(f, ps, p_raw, success, nfev, info)) return -1;
   cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);

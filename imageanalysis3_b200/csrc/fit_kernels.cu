@@ -208,17 +208,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_voronoi(FitDev d) {
 }
 
 // ------------------------------------------------------------------------------------------
+// One spot, one warp.  Returns FIT_SUSPENDED if the run spent `cap` function evaluations without
+// finishing: its LM state is then parked in d.pause_buf and a later launch (resume = true) continues
+// it bit-identically -- the window is gathered again (nothing that overlaps it changes meanwhile: the
+// other spots of its level do not touch it and the next level waits for it).  Why: a junk seed that runs
+// MINPACK to maxfev = 1000 keeps its kernel alive for tens of ms; a stack's kernels occupy one of the 32
+// hardware queues for as long, and 32 / (sum of a stack's kernel times) capped the pipeline at
+// ~150 stacks/s with the GPU mostly idle.  Suspended spots of ALL stacks in flight are continued
+// together by one service stream (capi.cu), so a stack's own launches stay short.
 template <typename T>
-__global__ void __launch_bounds__(FIT_WARPS * 32, IA3_FIT_MINBLOCKS) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long wi = (long long)blockIdx.x * FIT_WARPS + warp;
-  if (wi >= n_work) return;
-  const long long s = work ? (long long)work[wi] : wi;
+__device__ __forceinline__ int fit_one(const FitDev& d, int mode, long long s, unsigned char* base, int cap, bool resume) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = d.K;
-  // per-warp shared layout
-  const size_t per_warp = (sizeof(SpotShared<T>) + 15) / 16 * 16 + ((size_t)K * (8 + 4) + 15) / 16 * 16;
-  unsigned char* base = smem_raw + per_warp * warp;
   SpotShared<T>& sh = *reinterpret_cast<SpotShared<T>*>(base);
   double* dv = reinterpret_cast<double*>(base + (sizeof(SpotShared<T>) + 15) / 16 * 16);
   uint32_t* pk = reinterpret_cast<uint32_t*>(dv + K);
@@ -266,17 +267,48 @@ __global__ void __launch_bounds__(FIT_WARPS * 32, IA3_FIT_MINBLOCKS) k_fit(FitDe
         for (int i = 0; i < NP; ++i) d.p_raw[s * NP + i] = NAN;
       }
     }
-    return;
+    return FIT_DONE;
   }
 
   FitParams fp = d.fp;
+  // also when resuming: the v3 width prior lives in fp.init_wt, which initial_guess derives from the window
   select10(ex, dv, m, false, sh.small10);
   select10(ex, dv, m, true, sh.large10);
   if (lane == 0) initial_guess(fp, sh.small10, sh.large10, d.init_w, sh.x0);
   __syncwarp();
 
   BallVox<T> vox{m, pk, dv};
-  run_lm<T>(ex, fp, d.lm, c, origin, vox, sh);
+  {
+    constexpr int NW64 = (int)(sizeof(LMPause) / 8);
+    static_assert(sizeof(LMPause) % 8 == 0 && sizeof(LMState) % 8 == 0, "suspended state is copied in 8-byte words");
+    int slot = -1, start = LM_START_FRESH;
+    if (resume) {
+      slot = -d.info[s] - 1;
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.pause_buf + slot);
+      unsigned long long* st64 = reinterpret_cast<unsigned long long*>(&sh.st);
+      unsigned long long* ag64 = reinterpret_cast<unsigned long long*>(sh.Ag);
+      constexpr int NS = (int)(sizeof(LMState) / 8);
+      for (int i = lane; i < NW64; i += 32) { if (i < NS) st64[i] = src[i]; else ag64[i - NS] = src[i]; }
+      __syncwarp();
+      start = LM_START_CONTINUE;
+    }
+    bool suspended = run_lm<T>(ex, fp, d.lm, c, origin, vox, sh, cap, start);
+    if (suspended && slot < 0) {
+      if (lane == 0) slot = atomicAdd(d.pause_ctl, 1);
+      slot = __shfl_sync(FULL, slot, 0);
+      if (slot >= d.pause_slots) suspended = run_lm<T>(ex, fp, d.lm, c, origin, vox, sh, 0, LM_START_CONTINUE);   // no room: finish here
+      else if (lane == 0) d.pause_ctl[1 + slot] = (int)s;
+    }
+    if (suspended) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.pause_buf + slot);
+      const unsigned long long* st64 = reinterpret_cast<const unsigned long long*>(&sh.st);
+      const unsigned long long* ag64 = reinterpret_cast<const unsigned long long*>(sh.Ag);
+      constexpr int NS = (int)(sizeof(LMState) / 8);
+      for (int i = lane; i < NW64; i += 32) dst[i] = (i < NS) ? st64[i] : ag64[i - NS];
+      if (lane == 0) d.info[s] = -(slot + 1);
+      return FIT_SUSPENDED;
+    }
+  }
   __shared__ FitResult res_s[FIT_WARPS];
   FitResult& res = res_s[warp];
   finish_fit<T>(ex, fp, c, origin, vox, sh, &res);
@@ -301,6 +333,35 @@ __global__ void __launch_bounds__(FIT_WARPS * 32, IA3_FIT_MINBLOCKS) k_fit(FitDe
       d.vol[vol_index(d, ic[0] + dz, ic[1] + dx, ic[2] + dy)] = dv[pos] - f0;
     }
   }
+  return FIT_DONE;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(FIT_WARPS * 32, IA3_FIT_MINBLOCKS) k_fit(FitDev d, int mode, const int* __restrict__ work, long long n_work) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const long long wi = (long long)blockIdx.x * FIT_WARPS + warp;
+  if (wi >= n_work) return;
+  const long long s = work ? (long long)work[wi] : wi;
+  const size_t per_warp = (sizeof(SpotShared<T>) + 15) / 16 * 16 + ((size_t)d.K * (8 + 4) + 15) / 16 * 16;
+  fit_one<T>(d, mode, s, smem_raw + per_warp * warp, d.cap, false);
+}
+
+// Continuation of suspended spots of several handles (one spot per CTA; FitDev table and entries in
+// device-addressable pinned memory).
+__global__ void __launch_bounds__(32, IA3_FIT_MINBLOCKS) k_fit_resume(const FitDev* __restrict__ devs, FitResume* entries, int n, int cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if ((int)blockIdx.x >= n) return;
+  __shared__ FitDev d_s;
+  const FitResume e = entries[blockIdx.x];
+  {
+    const int* src = reinterpret_cast<const int*>(devs + e.job);
+    int* dst = reinterpret_cast<int*>(&d_s);
+    for (int i = threadIdx.x; i < (int)(sizeof(FitDev) / 4); i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+  const int status = fit_one<double>(d_s, e.mode, (long long)e.spot, smem_raw, cap, true);
+  if (threadIdx.x == 0) entries[blockIdx.x].status = status;
 }
 
 // firstfit: ims_rec[s] = get_im() over the full clipped window; im_subtr[window] -= im_rec (:629-633)
@@ -419,10 +480,20 @@ int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, boo
     once_err = cudaFuncSetAttribute(k_fit<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (once_err == cudaSuccess)
       once_err = cudaFuncSetAttribute(k_fit<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (once_err == cudaSuccess)
+      once_err = cudaFuncSetAttribute(k_fit_resume, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem - 1024);
   });
   IA3_CUDA(once_err);
   if (fp32) k_fit<float><<<grid, FIT_WARPS * 32, smem, st>>>(d, mode, work, n_work);
   else k_fit<double><<<grid, FIT_WARPS * 32, smem, st>>>(d, mode, work, n_work);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_fit_resume(const FitDev* devs, FitResume* entries, int n, int cap, int smem_bytes, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (smem_bytes > 227 * 1024 - 4096 - 1024) { set_error("radius_fit too large for the shared-memory window"); return -1; }
+  k_fit_resume<<<(unsigned)n, 32, smem_bytes, st>>>(devs, entries, n, cap);
   IA3_LAUNCH_CHECK();
   return 0;
 }

@@ -7,6 +7,8 @@
 
 namespace ia3 {
 
+struct LMPause;                       // fit_spot.h
+
 struct FitDev {
   // image / volumes
   const void* im; int im_dtype;       // original stack (u16 / f32 / f64)
@@ -35,7 +37,17 @@ struct FitDev {
   double* rec;                        // n x K reconstructions (ims_rec)
   // config
   FitParams fp; LMConfig lm; double init_w[3];
+  // suspension of long runs (see k_fit): cap = function evaluations per launch (0 = run to the end);
+  // pause_ctl[0] = number of suspended spots of the last launch, pause_ctl[1 + i] = spot of slot i;
+  // while a spot is suspended info[spot] = -(slot + 1)
+  int cap; int pause_slots;
+  LMPause* pause_buf; int* pause_ctl;
 };
+
+// One entry of the continuation service's table (device-addressable pinned memory): which handle
+// (index into the FitDev table), which spot, the fit mode; status is written by the kernel.
+struct FitResume { int job; int spot; int mode; int status; };
+enum { FIT_DONE = 0, FIT_SUSPENDED = 1 };
 
 int fit_smem_bytes(int K, bool fp32);
 int launch_init_window(const FitDev& d, cudaStream_t st);
@@ -43,6 +55,8 @@ int launch_voronoi(const FitDev& d, cudaStream_t st);
 // mode 0 = firstfit (image data, Voronoi mask), 1 = repeatfit (vol + own rec, full window, write back)
 int launch_fit(const FitDev& d, int mode, const int* work, long long n_work, bool fp32, cudaStream_t st);
 int launch_subtract(const FitDev& d, const int* work, long long n_work, cudaStream_t st);
+// continues suspended spots of several handles in one launch (FP64 model only)
+int launch_fit_resume(const FitDev* devs, FitResume* entries, int n, int cap, int smem_bytes, cudaStream_t st);
 
 struct MomentDev {                    // fast_fit_big_image / gfit_fast (Fitting_v4.py:433-556)
   const void* im; int im_dtype;

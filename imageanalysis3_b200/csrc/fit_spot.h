@@ -324,17 +324,33 @@ IA3_HD void build_consts_par(Exec& ex, const FitParams& fp, const double* cen_es
   ex.sync();
 }
 
-// Runs leastsq from sh.x0.  Every lane must call this; results are in sh.st (shared) after return.
+// Everything that is live at the top of lmder's outer loop: a run can be suspended there and resumed
+// later (by another kernel launch) without changing a single bit of its trajectory.
+struct LMPause {
+  LMState st;
+  double Ag[NTRI + NP];
+};
+enum { LM_START_FRESH = 0, LM_START_CONTINUE = 1 };
+
+// Runs leastsq from sh.x0 (LM_START_FRESH) or continues the run whose state is in sh.st / sh.Ag
+// (LM_START_CONTINUE).  Every lane must call this; results are in sh.st (shared) after return.
+// cap > 0: return true ("suspended", state consistent in sh.st / sh.Ag) once cap function evaluations
+// have been spent in this call and the run is not finished; false = finished.
 template <typename T, typename Exec, typename Vox>
-IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen_est,
-                   const double* origin, const Vox& vox, SpotShared<T>& sh) {
+IA3_HD bool run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen_est,
+                   const double* origin, const Vox& vox, SpotShared<T>& sh, int cap = 0, int start = LM_START_FRESH) {
   LMState& st = sh.st;
-  build_consts_par<T>(ex, fp, cen_est, origin, sh.x0, sh);
-  const double fn0 = pass_fused<T>(ex, sh.vc, vox, sh.Ag, sh.gram);       // f(x0) and J(x0)
-  lm_init(ex, st, sh.x0, fn0);
+  if (start == LM_START_FRESH) {
+    build_consts_par<T>(ex, fp, cen_est, origin, sh.x0, sh);
+    const double fn0 = pass_fused<T>(ex, sh.vc, vox, sh.Ag, sh.gram);       // f(x0) and J(x0)
+    lm_init(ex, st, sh.x0, fn0);
+  }
+  ex.sync();
+  const int nfev_entry = st.nfev;
   for (;;) {
     // sh.Ag holds J^T J, J^T f at st.x (x0, or the trial point that was just accepted)
     ex.sync();
+    if (cap > 0 && st.nfev - nfev_entry >= cap) return true;
     if (!lm_outer(ex, st, cfg, sh.Ag, sh.Ag + NTRI)) break;
     int action;
     for (;;) {
@@ -347,6 +363,7 @@ IA3_HD void run_lm(Exec& ex, const FitParams& fp, const LMConfig& cfg, const dou
     if (action == LM_DONE) break;
   }
   ex.sync();
+  return false;
 }
 
 // to_natural_paramaters() with the final parameters (Fitting_v4.py:244-258): ps[0..9] natural
