@@ -7,6 +7,7 @@ classes/field_of_view.py:1129) before any GPU work happens.
 """
 import ctypes as C
 import os
+import threading
 import weakref
 
 import numpy as np
@@ -57,7 +58,13 @@ EXPORTS = [
 
 _lib = None
 # bytes this process copied through the C ABI (host->device, device->host); bench.py's e2e record
-COPIED = {"h2d": 0, "d2h": 0}
+COPIED = {"h2d": 0, "d2h": 0}     # bytes moved over PCIe by this process (bench.py's e2e accounting)
+_COPIED_LOCK = threading.Lock()
+
+
+def _count(kind, nbytes):
+    with _COPIED_LOCK:               # stacks are driven by many host threads; `+=` on a dict entry is not atomic
+        COPIED[kind] += int(nbytes)
 
 
 def load():
@@ -168,7 +175,7 @@ class Stack:
             self.dtype = im.dtype
             self._keep = im
             _check(lib.ia3_stack_create(_ptr(im), _NP2DT[im.dtype], *im.shape, C.byref(self._h)))
-            COPIED["h2d"] += im.nbytes
+            _count("h2d", im.nbytes)
             self._keep = None
         self._fin = weakref.finalize(self, lib.ia3_stack_destroy, self._h)
 
@@ -211,7 +218,7 @@ class Stack:
         h = np.empty((n,), dtype=np.float32)
         if n:
             _check(lib.ia3_seed_fetch(self._h, _ptr(zxy), _ptr(h), n))
-        COPIED["d2h"] += zxy.nbytes + h.nbytes + 8
+        _count("d2h", zxy.nbytes + h.nbytes + 8)
         return zxy, h, t
 
     def box_background(self, boxes, first, last, bin_size, max_iter):
@@ -219,8 +226,8 @@ class Stack:
         boxes = np.ascontiguousarray(boxes, dtype=np.int32).reshape(-1, 6)
         out = np.empty(len(boxes), dtype=np.float64)
         _check(load().ia3_box_background(self._h, _ptr(boxes), len(boxes), int(first), int(last), int(bin_size), int(max_iter), _ptr(out)))
-        COPIED["h2d"] += boxes.nbytes
-        COPIED["d2h"] += out.nbytes
+        _count("h2d", boxes.nbytes)
+        _count("d2h", out.nbytes)
         return out
 
     def moment_fit(self, centers_nx3, radius, avoid_neighbors=True, recenter=False, bk_f=0.1):
@@ -229,8 +236,8 @@ class Stack:
         out = np.empty((len(cen), 12), dtype=np.float64)
         cfg = MomentCfg(int(radius), int(bool(avoid_neighbors)), int(bool(recenter)), float(bk_f))
         _check(load().ia3_moment_fit(self._h, _ptr(cen), len(cen), C.byref(cfg), _ptr(out)))
-        COPIED["h2d"] += cen.nbytes
-        COPIED["d2h"] += out.nbytes
+        _count("h2d", cen.nbytes)
+        _count("d2h", out.nbytes)
         return out
 
     def seed_volume(self, which):
@@ -265,7 +272,7 @@ class FitHandle:
         self._h = C.c_void_p()
         _check(lib.ia3_fit_create(stack.handle, _ptr(self.centers), self.n, C.byref(cfg), C.byref(self._h)))
         self._fin = weakref.finalize(self, lib.ia3_fit_destroy, self._h)
-        COPIED["h2d"] += self.centers.nbytes * 2
+        _count("h2d", self.centers.nbytes * 2)
         self.ps = np.full((self.n, 11), np.nan, dtype=np.float32)
         self.p_raw = np.full((self.n, 10), np.nan, dtype=np.float64)
         self.success = np.zeros(self.n, dtype=np.uint8)
@@ -294,15 +301,15 @@ class FitHandle:
     def first_run(self, delta_center):
         _check(load().ia3_fit_first_run(self._h, float(delta_center), _ptr(self.ps), _ptr(self.p_raw),
                                         _ptr(self.success), _ptr(self.nfev), _ptr(self.info)))
-        COPIED["d2h"] += self._result_bytes()
-        COPIED["h2d"] += 4 * self.n
+        _count("d2h", self._result_bytes())
+        _count("h2d", 4 * self.n)
 
     def repeat_sweep(self, delta_center, active):
         active = np.ascontiguousarray(active, dtype=np.uint8)
         _check(load().ia3_fit_repeat_sweep(self._h, float(delta_center), _ptr(active), _ptr(self.ps), _ptr(self.p_raw),
                                            _ptr(self.success), _ptr(self.nfev), _ptr(self.info)))
-        COPIED["d2h"] += self._result_bytes()
-        COPIED["h2d"] += 4 * int(np.count_nonzero(active))
+        _count("d2h", self._result_bytes())
+        _count("h2d", 4 * int(np.count_nonzero(active)))
 
     def _result_bytes(self):
         return self.ps.nbytes + self.p_raw.nbytes + self.success.nbytes + self.nfev.nbytes + self.info.nbytes
