@@ -42,7 +42,7 @@ struct ArrayVox {
 template <typename T>
 static int run(int personality, const double* values, const int* coords, int m, const double* cen,
                double delta, double min_w, double max_w, const double* init_w, double weight_sigma,
-               int maxfev, double* p_raw, float* ps, int* stats) {
+               int maxfev, double* p_raw, float* ps, int* stats, int cap = 0) {
   if (m < NP) return 1;
   FitParams fp;
   fp.min_w2 = min_w * min_w; fp.max_w2 = max_w * max_w; fp.delta = delta;
@@ -62,7 +62,26 @@ static int run(int personality, const double* values, const int* coords, int m, 
   select10(ex, values, m, true, sh.large10);
   initial_guess(fp, sh.small10, sh.large10, init_w, sh.x0);
   ArrayVox<T> vox{m, rel.data(), data.data()};
-  run_lm<T>(ex, fp, cfg, cen, origin, vox, sh);
+  const FitParams fp_in = fp;          // initial_guess fills the v3 width prior in fp
+  bool suspended = run_lm<T>(ex, fp, cfg, cen, origin, vox, sh, cap, LM_START_FRESH);
+  int rounds = 0;
+  while (suspended) {
+    // what the device does between two launches (fit_kernels.cu: fit_one): park LMState + the normal
+    // equation sums, forget everything else, rebuild the prologue, continue
+    static LMPause park;
+    park.st = sh.st;
+    memcpy(park.Ag, sh.Ag, sizeof(park.Ag));
+    memset(static_cast<void*>(&sh), 0xA5, sizeof(sh));
+    fp = fp_in;
+    select10(ex, values, m, false, sh.small10);
+    select10(ex, values, m, true, sh.large10);
+    initial_guess(fp, sh.small10, sh.large10, init_w, sh.x0);
+    sh.st = park.st;
+    memcpy(sh.Ag, park.Ag, sizeof(park.Ag));
+    suspended = run_lm<T>(ex, fp, cfg, cen, origin, vox, sh, cap, LM_START_CONTINUE);
+    ++rounds;
+  }
+  if (cap > 0) stats[3] = rounds;
   FitResult res;
   finish_fit<T>(ex, fp, cen, origin, vox, sh, &res);
   memcpy(p_raw, res.p_raw, sizeof(double) * NP);
@@ -77,6 +96,14 @@ extern "C" int hostsim_fit(int personality, int use_float, const double* values,
   if (use_float)
     return run<float>(personality, values, coords, m, cen, delta, min_w, max_w, init_w, weight_sigma, maxfev, p_raw, ps, stats);
   return run<double>(personality, values, coords, m, cen, delta, min_w, max_w, init_w, weight_sigma, maxfev, p_raw, ps, stats);
+}
+
+// the same fit, suspended every `cap` function evaluations and resumed from the parked state only
+// (stats[3] = number of suspensions): must be bit-identical to hostsim_fit
+extern "C" int hostsim_fit_capped(int personality, const double* values, const int* coords, int m, const double* cen,
+                                  double delta, double min_w, double max_w, const double* init_w, double weight_sigma,
+                                  int maxfev, int cap, double* p_raw, float* ps, int* stats) {
+  return run<double>(personality, values, coords, m, cen, delta, min_w, max_w, init_w, weight_sigma, maxfev, p_raw, ps, stats, cap);
 }
 
 // reconstruction f0 over arbitrary integer voxels (GaussianFit.get_im, Fitting_v4.py:394-396)

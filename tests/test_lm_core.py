@@ -127,3 +127,30 @@ def test_ill_posed_reference_fits_are_not_reproducible_by_minpack_itself(hostsim
         _, ps, st = _hostfit_qr(hostsim, 4, vals, X, cen, 2.5, [1.5] * 3)
         assert st[0] == ref["nfev"]
         assert np.allclose(ps, ref["p"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("version,ws,cap", [(4, 0.0, 1), (4, 0.0, 3), (3, 1000.0, 2), (3, 0.0, 2)])
+def test_suspended_runs_resume_bit_identically(hostsim, golden_fits, version, ws, cap):
+    """k_fit parks a run after `cap` function evaluations (LMState + normal-equation sums) and a later
+    launch continues it: the trajectory must not change by a single bit (fit_kernels.cu: fit_one)."""
+    init_w = [1.5] * 3 if version == 4 else fit_oracle.SIGMA_ZXY
+    maxfev = 1000 if version == 4 else 1100
+    n_suspensions = 0
+    for vals, X, cen in _problems(golden_fits, 8):
+        rc, praw, ps, st = _hostfit(hostsim, version, 0, vals, X, cen, 2.5, init_w, ws, maxfev)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        coords = np.ascontiguousarray(np.asarray(X).T, dtype=np.int32)
+        c = np.ascontiguousarray(cen, dtype=np.float64)
+        iw = np.ascontiguousarray(init_w, dtype=np.float64)
+        praw2, ps2, st2 = np.zeros(10), np.zeros(11, np.float32), np.zeros(4, np.int32)
+        rc2 = hostsim.hostsim_fit_capped(version, v.ctypes.data_as(P(ctypes.c_double)), coords.ctypes.data_as(P(ctypes.c_int)),
+                                         len(v), c.ctypes.data_as(P(ctypes.c_double)), ctypes.c_double(2.5), ctypes.c_double(0.5),
+                                         ctypes.c_double(4.0), iw.ctypes.data_as(P(ctypes.c_double)), ctypes.c_double(ws), maxfev, cap,
+                                         praw2.ctypes.data_as(P(ctypes.c_double)), ps2.ctypes.data_as(P(ctypes.c_float)),
+                                         st2.ctypes.data_as(P(ctypes.c_int)))
+        assert rc == 0 and rc2 == 0
+        assert np.array_equal(praw.view(np.uint64), praw2.view(np.uint64))
+        assert np.array_equal(ps.view(np.uint32), ps2.view(np.uint32))
+        assert list(st[:3]) == list(st2[:3])
+        n_suspensions += int(st2[3])
+    assert n_suspensions >= 4          # runs were actually interrupted (a v3 fit needs ~6 evaluations in all)
