@@ -327,3 +327,46 @@ def test_remaining_argument_paths_match_fixture(lib, golden_fits):
     assert c.shape == g["centers_crop"].shape and np.abs(c - g["centers_crop"]).max() <= 1e-3
     c = get_centers(im, th_seed=300, remove_close_pts=False, max_num_seeds=12)
     assert c.shape == g["centers_noclose"].shape and np.abs(c - g["centers_noclose"]).max() <= 1e-3
+
+
+_SUSPEND_SCRIPT = r'''
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+from imageanalysis3_b200.External import Fitting_v3, Fitting_v4
+from imageanalysis3_b200.spot_tools import fitting
+from imageanalysis3_b200.synth import synth
+im = synth((30, 128, 128), 400, 31, h_range=(500.0, 3000.0))       # crowded: many long LM runs
+seeds = fitting.get_seeds(im, max_num_seeds=None, th_seed=200.0)
+out = {}
+for name, mod in (("v4", Fitting_v4), ("v3", Fitting_v3)):
+    f = mod.iter_fit_seed_points(im, seeds.T)
+    f.firstfit()
+    out[name + "_first"] = np.array(f.ps)
+    f.repeatfit()
+    out[name + "_ps"] = np.array(f.ps)
+    out[name + "_nfev"] = np.array(f.nfev)
+    out[name + "_n_iter"] = f.n_iter
+np.savez(sys.argv[1], **out)
+'''
+
+
+def test_suspended_fits_continue_bit_identically(lib, tmp_path):
+    """IA3_FIT_CAP: k_fit parks a run after that many function evaluations and the continuation service
+    finishes it (capi.cu).  cap = 3 suspends nearly every fit several times; the results must be the
+    very same bits as with suspension switched off."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for cap in (0, 3):
+        path = str(tmp_path / f"cap{cap}.npz")
+        subprocess.run([sys.executable, "-c", _SUSPEND_SCRIPT, path], cwd=root, check=True, timeout=300,
+                       env={**os.environ, "IA3_FIT_CAP": str(cap)})
+        res[cap] = np.load(path)
+    assert res[0]["v4_nfev"].max() > 50                       # the image does contain long runs
+    for key in res[0].files:
+        a, b = res[0][key], res[3][key]
+        assert a.shape == b.shape and a.dtype == b.dtype, key
+        assert np.array_equal(a, b, equal_nan=True), key
