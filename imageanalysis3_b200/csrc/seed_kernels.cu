@@ -481,10 +481,14 @@ k_gauss_row(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int L, 
 #pragma unroll
   for (int i = 0; i < U; ++i) w[R + i] = c[i];
   const bool first = (lane == 0), last = (lane == 31) || (y0 + U >= L);
+  // R <= 8 <= L: at most one reflection, no modulo needed
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    w[i] = first ? (int)(line[reflect_idx(y0 - R + i, L)] | kHalfBias) : l8[8 - R + i];
-    w[R + U + i] = last ? (int)(line[reflect_idx(y0 + U + i, L)] | kHalfBias) : r8[i];
+    int yl = y0 - R + i, yr = y0 + U + i;
+    if (yl < 0) yl = -1 - yl;
+    if (yr >= L) yr = 2 * L - 1 - yr;
+    w[i] = first ? (int)(line[yl] | kHalfBias) : l8[8 - R + i];
+    w[R + U + i] = last ? (int)(line[yr] | kHalfBias) : r8[i];
   }
   unsigned res[U];
   window_outputs<R, U, R, NW>(w, gw, wsh, line, 1, y0, L, res);
