@@ -361,7 +361,12 @@ static void svc_main(int device) {
   FitDev* devs = nullptr;
   FitResume* ent = nullptr;
   cudaStream_t st = nullptr;
-  bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess &&
+  // highest priority: a round's few CTAs should not wait for free slots behind thousands of ordinary
+  // fits of later-launched kernels -- every stack with a suspended spot is waiting for this stream
+  int prio_lo = 0, prio_hi = 0;
+  cudaSetDevice(device);
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  bool ok = cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
             cudaMallocHost((void**)&devs, sizeof(FitDev) * MAXJ) == cudaSuccess && cudaMallocHost((void**)&ent, sizeof(FitResume) * MAXE) == cudaSuccess;
   std::vector<SvcJob*> active, batch;
   for (;;) {
@@ -381,7 +386,11 @@ static void svc_main(int device) {
       batch.push_back(j);
     }
     bool fail = !ok;
-    if (!fail) fail = launch_fit_resume(devs, ent, ne, g_fit_cap, smem, st) != 0 || cudaStreamSynchronize(st) != cudaSuccess;
+    if (!fail) {
+      IA3_STAT("  service round");
+      fail = launch_fit_resume(devs, ent, ne, g_fit_cap, smem, st) != 0 || cudaStreamSynchronize(st) != cudaSuccess;
+    }
+    if (g_stats_on) { static StatSlot* spots_slot = stat_slot("  service spots (calls = spots)"); spots_slot->calls += ne; }
     if (fail) {
       std::lock_guard<std::mutex> lk(g_svc_mu);
       for (SvcJob* j : active) { j->failed = true; j->done = true; j->cv.notify_all(); }
