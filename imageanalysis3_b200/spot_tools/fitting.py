@@ -209,9 +209,37 @@ def _neighbor_slices(coord, crop_size, shape):
 # copies of the stack in HBM, and letting all of them seed at once only inflates the allocation pool
 # (cudaMalloc while other stacks' kernels run stalls every stream).
 _SEED_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_SEED_INFLIGHT", "6"))))
+# Stacks between "upload started" and "firstfit done" (they hold the 400 MB image in HBM and a place in
+# the upload queue).  repeatfit is a chain of short kernels separated by waits for a few long LM runs:
+# many stacks have to be in it at once to keep the GPU busy, but they need only their sparse work
+# volume -- so callers can keep 100+ stacks in flight while only this many are in the heavy front part.
+_ADMIT_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_ADMIT_INFLIGHT", "24"))))
 
 
-def fit_fov_image(im, channel, seeds=None,
+def fit_fov_image(im, channel, *args, **kwargs):
+    """Seeding + fitting of a whole field-of-view stack -> (M, 11) spots
+    [height, z, x, y, background, sigma_z, sigma_x, sigma_y, sin_t, sin_p, eps]
+    (signature and defaults of the reference: see _fit_fov_image)."""
+    state = {"held": True}
+
+    def front_done():
+        if state["held"]:
+            state["held"] = False
+            _ADMIT_GATE.release()
+    _ADMIT_GATE.acquire()
+    try:
+        return _fit_fov_image(im, channel, *args, _front_done=front_done, **kwargs)
+    finally:
+        front_done()
+
+
+def _public_signature():
+    import inspect
+    sig = inspect.signature(_fit_fov_image)
+    return sig.replace(parameters=[p for n, p in sig.parameters.items() if n != "_front_done"])
+
+
+def _fit_fov_image(im, channel, seeds=None,
                   seed_mask=None,
                   max_num_seeds=500,
                   th_seed=300, th_seed_per=95, use_percentile=False,
@@ -222,10 +250,9 @@ def fit_fov_image(im, channel, seeds=None,
                   normalize_background=False, normalize_local=False,
                   background_args={},
                   fitting_args={},
-                  remove_boundary_points=True, verbose=True, _stack=None):
-    """Seeding + fitting of a whole field-of-view stack -> (M, 11) spots
-    [height, z, x, y, background, sigma_z, sigma_x, sigma_y, sin_t, sin_p, eps].
-    `_stack` (not in the reference): a `_lib.Stack` that already holds `im` in HBM."""
+                  remove_boundary_points=True, verbose=True, _stack=None, _front_done=None):
+    """spot_tools/fitting.py:169-262.  `_stack` (not in the reference): a `_lib.Stack` that already holds
+    `im` in HBM; `_front_done`: called once the image is no longer needed on the device."""
     th_seed = float(th_seed)
     if verbose:
         print(f"-- start fitting spots in channel:{channel}, ", end='')
@@ -267,6 +294,8 @@ def fit_fov_image(im, channel, seeds=None,
     _need_image = normalize_local or normalize_background
     if stack is not None and not _need_image:
         stack.trim(2)          # repeatfit only touches the sparse work volume, not the image
+    if _front_done is not None:
+        _front_done()
     fitter.repeatfit()
     _spots = fitter._ps_array()                 # == np.array(fitter.ps)
     _spots = _spots[np.sum(np.isnan(_spots), axis=1) == 0]
@@ -357,3 +386,6 @@ def select_sparse_centers(centers, distance_th=9,
     if verbose:
         print(f"-- {len(kept)} among {len(centers)} centers are selected by th={distance_th}")
     return np.array(kept)
+
+
+fit_fov_image.__signature__ = _public_signature()      # the reference's parameters and defaults (+ _stack)
