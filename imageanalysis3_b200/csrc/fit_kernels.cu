@@ -22,14 +22,13 @@
 namespace ia3 {
 
 constexpr int WARPS = 4;
-// One warp (= one spot) per CTA in the fit kernels.  A fit that runs MINPACK to maxfev keeps its CTA
-// resident for ~1000 iterations; with one warp per CTA it pins 8 K registers and 10 KB of shared
-// memory of its SM instead of 32 K / 42 KB, so the seed kernels of the other in-flight stacks keep
-// running next to the stragglers.
+// One warp (= one spot) per CTA in the fit kernels.  A long fit keeps its CTA resident; with one warp
+// per CTA it pins 4.7 K registers and 15 KB of shared memory of its SM instead of four times that, so
+// the seed kernels of the other in-flight stacks keep running next to it.
 constexpr int FIT_WARPS = 1;
 #ifndef IA3_FIT_MINBLOCKS
-#define IA3_FIT_MINBLOCKS 8      // resident spots per SM the register allocation of k_fit aims at (255 registers)
-#endif
+#define IA3_FIT_MINBLOCKS 8      // lower bound for ptxas; k_fit needs 146 registers (12 spots per SM) since the
+#endif                           // normal-equation sums moved to the tensor cores (255 before)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct WarpExec {
