@@ -84,3 +84,25 @@ def test_two_rank_gloo_shards_and_gathers():
     for i, (shape, v) in got.items():
         assert shape == (i % 4, 11)
         assert v is None or v == float(i)
+
+
+def test_fit_fov_image_gates_are_released_on_errors():
+    """fit_fov_image holds an admission slot (stacks between upload and the end of firstfit) and, while
+    seeding, a seed-stage slot: a call that fails must give them back, or the 25th failing caller of a
+    `map_stacks` run would wait forever.  No GPU involved: the reference's TypeError for a non-array
+    image is raised before any device work."""
+    import inspect
+    from imageanalysis3_b200.spot_tools import fitting
+    n_slots = fitting._ADMIT_GATE._initial_value
+
+    def bad(_):
+        with pytest.raises(TypeError):
+            fitting.fit_fov_image("not an image", '647', verbose=False)
+        return 1
+    assert sum(sharding.map_stacks(bad, range(3 * n_slots + 5), inflight=8)) == 3 * n_slots + 5
+    for gate in (fitting._ADMIT_GATE, fitting._SEED_GATE):
+        assert gate._value == gate._initial_value
+    # the wrapper keeps the reference's parameters and defaults visible
+    params = inspect.signature(fitting.fit_fov_image).parameters
+    assert list(params)[:4] == ["im", "channel", "seeds", "seed_mask"] and params["max_num_seeds"].default == 500
+    assert "_front_done" not in params
