@@ -20,9 +20,9 @@ class iter_fit_seed_points(IterFitBase):
     _personality = 3
 
     def __init__(self, im, centers, radius_fit=5, min_delta_center=1., max_delta_center=2.5,
-                 n_max_iter=10, max_dist_th=0.1, init_w=_sigma_zxy, weight_sigma=0, _stack=None, eval_fp32=False):
+                 n_max_iter=10, max_dist_th=0.1, init_w=_sigma_zxy, weight_sigma=0, _stack=None):
         self._setup(im, centers, radius_fit, min_delta_center, max_delta_center, n_max_iter, max_dist_th,
-                    0.5, 4., np.array(init_w[:3], dtype=float), weight_sigma, _stack, eval_fp32)
+                    0.5, 4., np.array(init_w[:3], dtype=float), weight_sigma, _stack)
 
     def firstfit(self):
         if len(self.centers) > 0:
@@ -44,11 +44,14 @@ def get_seed_points_base(im, gfilt_size_min=1, gfilt_size_max=3, filt_size=3, th
     zxy, _, _ = st.seed_candidates(None, None, int(filt_size), 0, 0.0, -1e300)       # (max == im) & (min != im)
     z, x, y = (zxy[:, a].astype(np.int64) for a in range(3))
     st.seed_candidates(_gauss_half_kernel(gfilt_size_min), _gauss_half_kernel(gfilt_size_max), int(filt_size), 0, 0.0, 1e300)
-    g_filt_sm, g_filt = st.seed_volume(0).astype(im_plt.dtype, copy=False), st.seed_volume(1).astype(im_plt.dtype, copy=False)
+    # the two blurs are read at the candidate voxels only (a gather on the device, a few kB back)
+    flat = (z * im_plt.shape[1] + x) * im_plt.shape[2] + y
+    g_sm = st.seed_volume_at(0, flat).astype(im_plt.dtype, copy=False)
+    g_bg = st.seed_volume_at(1, flat).astype(im_plt.dtype, copy=False)
     st.close()
     with np.errstate(all='ignore'):
-        h = g_filt_sm[z, x, y] - g_filt[z, x, y]
-        snr = 1. * g_filt_sm[z, x, y] / g_filt[z, x, y]
+        h = g_sm - g_bg
+        snr = 1. * g_sm / g_bg
     keep = snr > th_seed if use_snr else h > th_seed
     x, y, z = x[keep], y[keep], z[keep]
     h, snr = h[keep], snr[keep]

@@ -25,11 +25,11 @@ class iter_fit_seed_points(IterFitBase):
 
     def __init__(self, im, centers, radius_fit=5, min_delta_center=1., max_delta_center=2.5,
                  n_max_iter=10, max_dist_th=0.1,
-                 min_w=0.5, max_w=4, init_w=1.5, _stack=None, eval_fp32=False):
+                 min_w=0.5, max_w=4, init_w=1.5, _stack=None):
         """Given seeds <centers> (3,N) in a 3d image <im>, iteratively fit 3d gaussians around
         the seeds (in order of brightness) and subtract the gaussian signal."""
         self._setup(im, centers, radius_fit, min_delta_center, max_delta_center, n_max_iter, max_dist_th,
-                    min_w, max_w, init_w, 0.0, _stack, eval_fp32)
+                    min_w, max_w, init_w, 0.0, _stack)
 
     def firstfit(self):
         """First fit with the gaussian constrained close to the seed (delta = min_delta_center);

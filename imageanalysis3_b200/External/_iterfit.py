@@ -76,7 +76,7 @@ class IterFitBase:
 
     # -- construction ----------------------------------------------------------------------
     def _setup(self, im, centers, radius_fit, min_delta_center, max_delta_center, n_max_iter, max_dist_th,
-               min_w, max_w, init_w, weight_sigma, _stack, eval_fp32):
+               min_w, max_w, init_w, weight_sigma, _stack):
         self.im = im
         self.radius_fit = radius_fit
         self.n_max_iter = n_max_iter
@@ -93,19 +93,19 @@ class IterFitBase:
         self.init_w = init_w
         self.weight_sigma = weight_sigma
         self._stack = _stack
-        self._eval_fp32 = eval_fp32
         self._h = None
 
     def _make_handle(self):
         if self._stack is None:
             self._stack = _lib.Stack(np.asarray(self.im))
         cfg = _lib.make_fit_cfg(self._personality, self.radius_fit, self.min_w, self.max_w, self.init_w,
-                                weight_sigma=self.weight_sigma, maxfev=0, eval_fp32=self._eval_fp32)
+                                weight_sigma=self.weight_sigma, maxfev=0)
         self._h = _lib.FitHandle(self._stack, np.asarray(self.centers, dtype=np.float64), cfg)
         return self._h
 
     # -- firstfit ----------------------------------------------------------------------------
-    def _firstfit_device(self):
+    def _prepare_device(self):
+        """handle + Voronoi membership of the window voxels; ties go through scipy's own tree"""
         h = self._make_handle()
         n_ties = h.first_prepare()
         self.n_tie_voxels = n_ties
@@ -117,12 +117,29 @@ class IterFitBase:
             tree = cKDTree(self.centers)
             _, nn = tree.query(zxy, distance_upper_bound=self.radius_fit * 2)
             h.first_resolve(nn == spot)
-        h.first_run(self.min_delta_center)
+        return h
+
+    def _take_first(self):
+        h = self._h
         self._ps = h.ps.copy()
         self._succ = h.success.astype(bool)
         self._has_fit = self._succ.copy()
         self.nfev = h.nfev.copy()
         self.info = h.info.copy()
+
+    def _firstfit_device(self):
+        h = self._prepare_device()
+        h.run(1, self.min_delta_center, self.max_delta_center, self.max_dist_th ** 2, self.n_max_iter)
+        self._take_first()
+
+    def _fit_all(self):
+        """firstfit() followed by repeatfit() as ONE device run (no host round trip in between, the first
+        repeat visit of isolated seeds overlaps their firstfit).  Leaves the object as the two calls do."""
+        if len(self.centers) == 0:
+            return self.firstfit()             # raises exactly as the reference does on an empty seed list
+        h = self._prepare_device()
+        h.run(3, self.min_delta_center, self.max_delta_center, self.max_dist_th ** 2, self.n_max_iter)
+        self._take_repeat()
 
     # -- list-valued attributes the callers read --------------------------------------------
     @property
@@ -177,7 +194,43 @@ class IterFitBase:
         return out
 
     # -- repeatfit ---------------------------------------------------------------------------
+    def _take_repeat(self):
+        """attributes of the reference after repeatfit() from the per-seed results of the device run"""
+        h = self._h
+        n = len(self.centers)
+        self._ps = h.ps.copy()
+        self._succ = h.success.astype(bool)
+        self._has_fit = self._succ.copy()        # every seed is visited in sweep 1: it holds a fit iff its last visit succeeded
+        self.nfev = h.nfev.copy()
+        self.info = h.info.copy()
+        self.n_iter = int(h.n_visits.max()) if n else 0
+        self.converged = h.converged.astype(bool)
+        self.dists = h.dists.copy()
+        # state at the start of the last sweep: seeds visited in it held success_old / centers_old
+        last = h.n_visits == self.n_iter
+        self.success_old = np.where(last, h.success_old.astype(bool), self._succ)
+        had_fit = np.where(last & (self.n_iter == 1), h.success_old.astype(bool), self._has_fit)
+        old = np.where(last[:, None], h.centers_old, self._ps[:, 1:4])
+        if had_fit.all():
+            self.centers_fit_old = np.ascontiguousarray(old, dtype=np.float32)
+        else:
+            old = old.astype(np.float64)
+            old[~had_fit] = np.nan
+            self.centers_fit_old = old
+
     def repeatfit(self):
+        n = len(self.centers)
+        if n == 0:
+            self.n_iter = 0
+            self.converged = np.zeros(0, dtype=bool)
+            self.dists = np.zeros(0) + np.inf
+            return
+        self._h.run(2, self.min_delta_center, self.max_delta_center, self.max_dist_th ** 2, self.n_max_iter)
+        self._take_repeat()
+
+    def _repeatfit_host_loop(self):
+        """The reference's loop run on the host, one device sweep per iteration (Fitting_v4.py:641-683):
+        kept as a cross-check of the device-resident rule above (tests)."""
         n = len(self.centers)
         self.n_iter = 0
         self.converged = np.zeros(n, dtype=bool)

@@ -43,16 +43,22 @@ class FitCfg(C.Structure):
     _fields_ = [("personality", C.c_int), ("radius", C.c_int),
                 ("min_w", C.c_double), ("max_w", C.c_double),
                 ("init_w", C.c_double * 3), ("weight_sigma", C.c_double),
-                ("maxfev", C.c_int), ("eval_fp32", C.c_int)]
+                ("maxfev", C.c_int), ("eval_fp32", C.c_int)]      # eval_fp32: reserved, 0
+
+
+class FitOut(C.Structure):
+    _fields_ = [("ps", C.c_void_p), ("p_raw", C.c_void_p), ("success", C.c_void_p), ("nfev", C.c_void_p), ("info", C.c_void_p),
+                ("converged", C.c_void_p), ("dists", C.c_void_p), ("n_visits", C.c_void_p),
+                ("success_old", C.c_void_p), ("centers_old", C.c_void_p)]
 
 
 EXPORTS = [
     "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count", "ia3_debug_stats",
     "ia3_timer_start", "ia3_timer_stop",
     "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
-    "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_box_background",
+    "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_seed_gather_volume", "ia3_box_background",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
-    "ia3_fit_first_resolve", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_get_volume",
+    "ia3_fit_first_resolve", "ia3_fit_run", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_engine_stats", "ia3_fit_get_volume",
     "ia3_fit_get_rec", "ia3_fit_num_levels", "ia3_fit_last_ms", "ia3_gaussfit_batch", "ia3_gauss_eval", "ia3_moment_fit",
 ]
 
@@ -92,12 +98,15 @@ def load():
     lib.ia3_seed_run.argtypes = [vp, P(SeedCfg), P(i64), P(SeedTiming)]
     lib.ia3_seed_fetch.argtypes = [vp, vp, vp, i64]
     lib.ia3_seed_fetch_volume.argtypes = [vp, i32, vp]
+    lib.ia3_seed_gather_volume.argtypes = [vp, i32, vp, i64, vp]
     lib.ia3_box_background.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp]
     lib.ia3_fit_create.argtypes = [vp, vp, i64, P(FitCfg), P(vp)]
     lib.ia3_fit_destroy.argtypes = [vp]
     lib.ia3_fit_first_prepare.argtypes = [vp, P(i64)]
     lib.ia3_fit_first_ties.argtypes = [vp, vp, vp, i64]
     lib.ia3_fit_first_resolve.argtypes = [vp, vp, i64]
+    lib.ia3_fit_run.argtypes = [vp, i32, dbl, dbl, dbl, i32, P(FitOut)]
+    lib.ia3_fit_engine_stats.argtypes = [vp, vp, i32]
     lib.ia3_fit_first_run.argtypes = [vp, dbl, vp, vp, vp, vp, vp]
     lib.ia3_fit_repeat_sweep.argtypes = [vp, dbl, vp, vp, vp, vp, vp, vp]
     lib.ia3_fit_get_volume.argtypes = [vp, i32, vp]
@@ -245,8 +254,17 @@ class Stack:
         _check(load().ia3_seed_fetch_volume(self._h, int(which), _ptr(out)))
         return out
 
+    def seed_volume_at(self, which, flat_idx):
+        """values of the foreground (0) / background (1) blur at flat C-order voxel indices"""
+        idx = np.ascontiguousarray(flat_idx, dtype=np.int64).ravel()
+        out = np.empty(len(idx), dtype=self.dtype)
+        _check(load().ia3_seed_gather_volume(self._h, int(which), _ptr(idx), len(idx), _ptr(out)))
+        _count("h2d", idx.nbytes)
+        _count("d2h", out.nbytes)
+        return out
 
-def make_fit_cfg(personality, radius, min_w, max_w, init_w, weight_sigma=0.0, maxfev=0, eval_fp32=False):
+
+def make_fit_cfg(personality, radius, min_w, max_w, init_w, weight_sigma=0.0, maxfev=0):
     cfg = FitCfg()
     cfg.personality = int(personality)
     cfg.radius = int(radius)
@@ -257,7 +275,7 @@ def make_fit_cfg(personality, radius, min_w, max_w, init_w, weight_sigma=0.0, ma
         cfg.init_w[i] = float(iw[i])
     cfg.weight_sigma = float(weight_sigma)
     cfg.maxfev = int(maxfev)
-    cfg.eval_fp32 = int(bool(eval_fp32))
+    cfg.eval_fp32 = 0
     return cfg
 
 
@@ -278,6 +296,11 @@ class FitHandle:
         self.success = np.zeros(self.n, dtype=np.uint8)
         self.nfev = np.zeros(self.n, dtype=np.int32)
         self.info = np.zeros(self.n, dtype=np.int32)
+        self.converged = np.zeros(self.n, dtype=np.uint8)
+        self.dists = np.full(self.n, np.inf, dtype=np.float64)
+        self.n_visits = np.zeros(self.n, dtype=np.int32)
+        self.success_old = np.zeros(self.n, dtype=np.uint8)
+        self.centers_old = np.full((self.n, 3), np.nan, dtype=np.float32)
 
     def close(self):
         self._fin()
@@ -285,6 +308,7 @@ class FitHandle:
     def first_prepare(self):
         n = C.c_int64(0)
         _check(load().ia3_fit_first_prepare(self._h, C.byref(n)))
+        _count("d2h", 8 * min(int(n.value), 16384) + 256)
         return n.value
 
     def first_ties(self, n):
@@ -297,19 +321,33 @@ class FitHandle:
     def first_resolve(self, keep):
         keep = np.ascontiguousarray(keep, dtype=np.uint8)
         _check(load().ia3_fit_first_resolve(self._h, _ptr(keep), len(keep)))
+        _count("h2d", keep.nbytes)
+
+    def run(self, phases, min_delta_center, max_delta_center, max_dist_th2, n_max_iter):
+        """firstfit (1), repeatfit (2) or both (3) on the device; fills every result array of the handle"""
+        out = FitOut(*[a.ctypes.data for a in (self.ps, self.p_raw, self.success, self.nfev, self.info, self.converged,
+                                               self.dists, self.n_visits, self.success_old, self.centers_old)])
+        _check(load().ia3_fit_run(self._h, int(phases), float(min_delta_center), float(max_delta_center), float(max_dist_th2),
+                                  int(n_max_iter), C.byref(out)))
+        _count("d2h", self._result_bytes() + self.n * (1 + 8 + 4 + 1 + 12))
 
     def first_run(self, delta_center):
         _check(load().ia3_fit_first_run(self._h, float(delta_center), _ptr(self.ps), _ptr(self.p_raw),
                                         _ptr(self.success), _ptr(self.nfev), _ptr(self.info)))
         _count("d2h", self._result_bytes())
-        _count("h2d", 4 * self.n)
 
     def repeat_sweep(self, delta_center, active):
         active = np.ascontiguousarray(active, dtype=np.uint8)
         _check(load().ia3_fit_repeat_sweep(self._h, float(delta_center), _ptr(active), _ptr(self.ps), _ptr(self.p_raw),
                                            _ptr(self.success), _ptr(self.nfev), _ptr(self.info)))
         _count("d2h", self._result_bytes())
-        _count("h2d", 4 * int(np.count_nonzero(active)))
+        _count("h2d", self.n)
+
+    def engine_stats(self):
+        out = np.zeros(10, dtype=np.int64)
+        _check(load().ia3_fit_engine_stats(self._h, _ptr(out), 10))
+        keys = ("rounds", "tasks", "lm_runs", "evals", "memo_hits", "spec_runs", "spec_hits", "parked", "team_tasks", "bricks")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def _result_bytes(self):
         return self.ps.nbytes + self.p_raw.nbytes + self.success.nbytes + self.nfev.nbytes + self.info.nbytes

@@ -303,146 +303,15 @@ struct ia3_stack {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
-struct ia3_fit {
-  ia3_stack* s = nullptr;
-  ia3_fit_cfg cfg;
-  FitDev d;
-  int64_t n = 0;
-  std::vector<double> centers;
-  std::vector<int> level;            // per seed, 0-based
-  int n_levels = 0;
-  std::vector<int8_t> offs;
-  bool prepared = false, first_done = false;
-  int64_t n_ties = 0;
-  // device arrays owned here
-  double* d_centers = nullptr; int* d_own = nullptr; int* d_nbr_start = nullptr; int* d_nbr_idx = nullptr;
-  int8_t* d_offs = nullptr; uint32_t* d_mask = nullptr;
-  int* d_tie_count = nullptr; int* d_tie_spot = nullptr; int* d_tie_k = nullptr; int tie_cap = 0;
-  float* d_ps = nullptr; double* d_praw = nullptr; uint8_t* d_succ = nullptr; int* d_nfev = nullptr; int* d_info = nullptr;
-  double* d_rec = nullptr; double* d_snap = nullptr; double* d_vol = nullptr; int* d_brick_tab = nullptr;
-  int64_t n_bricks = 0;
-  int* d_work = nullptr; size_t work_cap = 0;
-  void* h_stage = nullptr; size_t stage_cap = 0;      // pinned staging, device -> host (results, ties)
-  void* h_up = nullptr; size_t up_cap = 0;            // pinned staging, host -> device (inputs, work lists)
-  uint8_t* d_keep = nullptr; size_t keep_cap = 0;
-  LMPause* d_pause = nullptr; int* d_pause_ctl = nullptr; int* h_pause_ctl = nullptr;   // suspended long runs (k_fit)
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  float last_ms = 0.f;
+struct ia3_fit;
+
+// device and pinned blocks that a call must hand back on every path out of it
+struct Scoped {
+  std::vector<void*> dev, host;
+  ~Scoped() { for (void* p : dev) dev_free(p); for (void* p : host) host_free(p); }
+  template <typename T> int dalloc(T** p, size_t bytes) { if (dev_alloc((void**)p, bytes)) return -1; dev.push_back(*p); return 0; }
+  int halloc(void** p, size_t bytes) { if (host_alloc(p, bytes)) return -1; host.push_back(*p); return 0; }
 };
-
-// ---- continuation service ---------------------------------------------------------------------
-// k_fit suspends a run after g_fit_cap function evaluations (fit_kernels.cu: fit_one).  The suspended
-// spots of every stack in flight are continued here, together, by one thread on one stream: a round =
-// one k_fit_resume launch over all pending spots, g_fit_cap more evaluations each.  A stack's own
-// launches therefore stay short, and the few junk seeds that run MINPACK to maxfev hold one hardware
-// queue in total instead of one per stack.
-static int fit_cap_from_env() {
-  const char* e = getenv("IA3_FIT_CAP");
-  const int v = e ? atoi(e) : 100;
-  return v < 0 ? 0 : v;
-}
-static const int g_fit_cap = fit_cap_from_env();
-struct SvcJob {
-  FitDev d;
-  int mode = 0;
-  std::vector<int> spots;
-  bool done = false, failed = false;
-  std::condition_variable cv;
-};
-// never destroyed: the service thread is detached and may be waiting on them when the process exits
-// (destroying a condition variable with a waiter blocks the exit)
-static std::mutex& g_svc_mu = *new std::mutex;
-static std::condition_variable& g_svc_cv = *new std::condition_variable;
-static std::vector<SvcJob*>& g_svc_in = *new std::vector<SvcJob*>;
-static std::once_flag g_svc_once;
-
-static void svc_main(int device) {
-  constexpr int MAXJ = 512, MAXE = 16384;
-  FitDev* devs = nullptr;
-  FitResume* ent = nullptr;
-  cudaStream_t st = nullptr;
-  // highest priority: a round's few CTAs should not wait for free slots behind thousands of ordinary
-  // fits of later-launched kernels -- every stack with a suspended spot is waiting for this stream
-  int prio_lo = 0, prio_hi = 0;
-  cudaSetDevice(device);
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  bool ok = cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-            cudaMallocHost((void**)&devs, sizeof(FitDev) * MAXJ) == cudaSuccess && cudaMallocHost((void**)&ent, sizeof(FitResume) * MAXE) == cudaSuccess;
-  std::vector<SvcJob*> active, batch;
-  for (;;) {
-    {
-      std::unique_lock<std::mutex> lk(g_svc_mu);
-      if (active.empty()) g_svc_cv.wait(lk, [] { return !g_svc_in.empty(); });
-      active.insert(active.end(), g_svc_in.begin(), g_svc_in.end());
-      g_svc_in.clear();
-    }
-    batch.clear();
-    int ne = 0, smem = 0;
-    for (SvcJob* j : active) {
-      if ((int)batch.size() == MAXJ || ne + (int)j->spots.size() > MAXE) break;
-      devs[batch.size()] = j->d;
-      for (int sp : j->spots) ent[ne++] = FitResume{(int)batch.size(), sp, j->mode, -1};
-      smem = std::max(smem, fit_smem_bytes(j->d.K, false));
-      batch.push_back(j);
-    }
-    bool fail = !ok;
-    if (!fail) {
-      IA3_STAT("  service round");
-      fail = launch_fit_resume(devs, ent, ne, g_fit_cap, smem, st) != 0 || cudaStreamSynchronize(st) != cudaSuccess;
-    }
-    if (g_stats_on) { static StatSlot* spots_slot = stat_slot("  service spots (calls = spots)"); spots_slot->calls += ne; }
-    if (fail) {
-      std::lock_guard<std::mutex> lk(g_svc_mu);
-      for (SvcJob* j : active) { j->failed = true; j->done = true; j->cv.notify_all(); }
-      active.clear();
-      continue;
-    }
-    for (SvcJob* j : batch) j->spots.clear();
-    for (int e = 0; e < ne; ++e)
-      if (ent[e].status != FIT_DONE) batch[ent[e].job]->spots.push_back(ent[e].spot);
-    std::vector<SvcJob*> still;
-    {
-      std::lock_guard<std::mutex> lk(g_svc_mu);
-      for (SvcJob* j : active) {
-        if (j->spots.empty()) { j->done = true; j->cv.notify_all(); }
-        else still.push_back(j);
-      }
-    }
-    active.swap(still);
-  }
-}
-
-// blocks until the suspended spots (h_pause_ctl[1..np]) of this handle have finished
-static int service_run(ia3_fit* f, int mode, int np) {
-  std::call_once(g_svc_once, [] { std::thread(svc_main, g_device).detach(); });
-  SvcJob job;
-  job.d = f->d;
-  job.mode = mode;
-  job.spots.assign(f->h_pause_ctl + 1, f->h_pause_ctl + 1 + np);
-  std::unique_lock<std::mutex> lk(g_svc_mu);
-  g_svc_in.push_back(&job);
-  g_svc_cv.notify_one();
-  job.cv.wait(lk, [&] { return job.done; });
-  if (job.failed) { set_error("continuation of suspended fits failed"); return -1; }
-  return 0;
-}
-
-// one k_fit launch on the handle's stream, then (cap > 0) hand the spots it suspended to the service
-static int run_fit_launch(ia3_fit* f, int mode, const int* work, long long n_work) {
-  if (n_work <= 0) return 0;
-  cudaStream_t st = f->s->stream;
-  const bool capped = f->d.cap > 0;
-  if (capped) IA3_CUDA(cudaMemsetAsync(f->d_pause_ctl, 0, sizeof(int), st));
-  if (launch_fit(f->d, mode, work, n_work, f->cfg.eval_fp32 != 0, st)) return -1;
-  if (capped && small_copy(f->h_pause_ctl, f->d_pause_ctl, sizeof(int) * (size_t)(1 + f->d.pause_slots), st)) return -1;
-  // A sweep kernel lasts as long as its slowest fit; nothing is queued behind it (an item waiting for it
-  // would also hold back the other stacks that share the hardware queue).
-  IA3_DRAIN(st);
-  if (!capped) return 0;
-  const int np = std::min(f->h_pause_ctl[0], f->d.pause_slots);
-  { IA3_STAT("  suspended spots -> service"); if (np > 0 && service_run(f, mode, np)) return -1; }
-  return 0;
-}
 
 extern "C" {
 
@@ -497,6 +366,107 @@ int ia3_timer_stop(float* ms) {
   return 0;
 }
 
+}  // extern "C"
+
+// ---- image upload ---------------------------------------------------------------------------
+// A cudaMemcpyAsync from PAGEABLE memory is staged by the driver through its own small bounce buffer,
+// synchronously, at a fraction of the link rate, and it stalls the other host threads' CUDA calls while
+// it runs.  The reference's callers hand over plain numpy arrays, so pageable input is the normal
+// case: it goes through pinned staging chunks filled by a few worker threads (one thread's memcpy is
+// ~10 GB/s, the link takes 55) -- the host memcpy of one chunk overlaps the DMA of the others, every
+// chunk is one cudaMemcpyAsync from pinned memory on the shared upload stream.  Pinned input (allocated
+// or registered with CUDA by the caller) is handed to the copy engine directly.
+constexpr size_t kStageChunk = (size_t)4 << 20;     // one DMA
+constexpr size_t kStageJob = (size_t)16 << 20;      // one queue entry (contiguous part of an image)
+struct StageJob { const char* src; char* dst; size_t bytes; std::atomic<int>* pending; std::atomic<int>* err; };
+static std::mutex& g_sq_mu = *new std::mutex;
+static std::condition_variable& g_sq_cv = *new std::condition_variable;
+static std::condition_variable& g_sq_done = *new std::condition_variable;
+static std::vector<StageJob>& g_sq = *new std::vector<StageJob>;
+static size_t g_sq_head = 0;
+static std::once_flag g_sq_once;
+
+static void stage_worker(int device, cudaStream_t us) {
+  void* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  bool ok = cudaSetDevice(device) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i)
+    ok = cudaMallocHost(&buf[i], kStageChunk) == cudaSuccess && cudaEventCreateWithFlags(&ev[i], cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
+  int k = 0;
+  for (;;) {
+    StageJob j;
+    {
+      std::unique_lock<std::mutex> lk(g_sq_mu);
+      g_sq_cv.wait(lk, [] { return g_sq_head < g_sq.size(); });
+      j = g_sq[g_sq_head++];
+      if (g_sq_head == g_sq.size()) { g_sq.clear(); g_sq_head = 0; }
+    }
+    cudaError_t e = ok ? cudaSuccess : cudaErrorMemoryAllocation;
+    for (size_t off = 0; off < j.bytes && e == cudaSuccess; off += kStageChunk) {
+      const size_t nb = std::min(kStageChunk, j.bytes - off);
+      if (used[k]) e = cudaEventSynchronize(ev[k]);            // the DMA that last read this chunk is done
+      if (e != cudaSuccess) break;
+      memcpy(buf[k], j.src + off, nb);
+      e = cudaMemcpyAsync(j.dst + off, buf[k], nb, cudaMemcpyHostToDevice, us);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[k], us);
+      used[k] = true;
+      k ^= 1;
+    }
+    if (e != cudaSuccess) j.err->store(1);
+    if (j.pending->fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(g_sq_mu); g_sq_done.notify_all(); }
+  }
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice;
+}
+
+static int upload_image(ia3_stack* s, const void* im, size_t bytes) {
+  cudaStream_t us;
+  if (upload_stream(&us)) return -1;
+  cudaError_t e = cudaSuccess;
+  if (is_pinned(im)) {
+    std::lock_guard<std::mutex> lk(g_upload_mu);
+    e = cudaMemcpyAsync(s->d_im, im, bytes, cudaMemcpyHostToDevice, us);
+    if (e == cudaSuccess) e = cudaEventRecord(s->ev[5], us);
+  } else {
+    IA3_STAT("  upload: pinned staging");
+    std::call_once(g_sq_once, [us] {
+      int nthr = 6;
+      if (const char* ev = getenv("IA3_STAGE_THREADS")) nthr = atoi(ev);
+      nthr = std::max(1, std::min(nthr, 32));
+      for (int i = 0; i < nthr; ++i) std::thread(stage_worker, g_device, us).detach();
+    });
+    std::atomic<int> pending{0}, err{0};
+    const int njobs = (int)((bytes + kStageJob - 1) / kStageJob);
+    pending.store(njobs);
+    {
+      std::lock_guard<std::mutex> lk(g_sq_mu);
+      for (int j = 0; j < njobs; ++j) {
+        const size_t off = (size_t)j * kStageJob;
+        g_sq.push_back(StageJob{static_cast<const char*>(im) + off, static_cast<char*>(s->d_im) + off, std::min(kStageJob, bytes - off), &pending, &err});
+      }
+    }
+    g_sq_cv.notify_all();
+    {
+      std::unique_lock<std::mutex> lk(g_sq_mu);
+      g_sq_done.wait(lk, [&] { return pending.load() == 0; });
+    }
+    if (err.load()) { set_error("image upload failed in the staging workers"); return -1; }
+    std::lock_guard<std::mutex> lk(g_upload_mu);
+    e = cudaEventRecord(s->ev[5], us);                          // behind every chunk's DMA
+  }
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(s->stream, s->ev[5], 0);
+  if (e == cudaSuccess) e = cudaEventSynchronize(s->ev[5]);
+  if (e != cudaSuccess) { set_error(std::string("image upload failed: ") + cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+extern "C" {
+
 // ---- stacks ---------------------------------------------------------------------------------
 static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
   if (dtype < 0 || dtype > 2 || Z <= 0 || X <= 0 || Y <= 0) { set_error("bad stack dtype/shape"); return -1; }
@@ -520,19 +490,7 @@ int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack**
   // uploads anyway): with more stacks in flight than hardware queues (32), a stack's own stream
   // shares its queue with another stack's, and a 400 MB copy waiting its turn behind other uploads
   // would hold back that other stack's kernels for as long.
-  {
-    cudaStream_t us;
-    if (upload_stream(&us)) { ia3_stack_destroy(s); return -1; }
-    cudaError_t e;
-    {
-      std::lock_guard<std::mutex> lk(g_upload_mu);
-      e = cudaMemcpyAsync(s->d_im, im, s->nvox * dtype_size(dtype), cudaMemcpyHostToDevice, us);
-      if (e == cudaSuccess) e = cudaEventRecord(s->ev[5], us);
-    }
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->stream, s->ev[5], 0);
-    if (e == cudaSuccess) e = cudaEventSynchronize(s->ev[5]);
-    if (e != cudaSuccess) { set_error(std::string("image upload failed: ") + cudaGetErrorString(e)); ia3_stack_destroy(s); return -1; }
-  }
+  if (upload_image(s, im, s->nvox * dtype_size(dtype))) { ia3_stack_destroy(s); return -1; }
   *out = s;
   return 0;
 }
@@ -722,32 +680,130 @@ int ia3_box_background(ia3_stack* s, const int32_t* boxes, int64_t n, int first,
     if (b[0] < 0 || b[1] > s->Z || b[2] < 0 || b[3] > s->X || b[4] < 0 || b[5] > s->Y) { set_error("box outside the stack"); return -1; }
   }
   cudaStream_t st = s->stream;
+  Scoped sc;
   void* h = nullptr;
   int* d_boxes = nullptr;
   double* d_out = nullptr;
   const size_t bb = (size_t)n * 6 * 4, ob = (size_t)n * 8;
-  if (host_alloc(&h, bb + ob + 256) || dev_alloc((void**)&d_boxes, bb) || dev_alloc((void**)&d_out, ob)) return -1;
+  if (sc.halloc(&h, bb + ob + 256) || sc.dalloc(&d_boxes, bb) || sc.dalloc(&d_out, ob)) return -1;
   memcpy(h, boxes, bb);
   char* ho = static_cast<char*>(h) + (bb + 255) / 256 * 256;
   if (small_copy(d_boxes, h, bb, st)) return -1;
   const bool whole = (n == 1 && boxes[0] == 0 && boxes[1] == s->Z && boxes[2] == 0 && boxes[3] == s->X && boxes[4] == 0 && boxes[5] == s->Y);
-  unsigned* d_ghist = nullptr;
   if (whole) {
-    if (dev_alloc((void**)&d_ghist, (size_t)nbins * 4)) return -1;
+    unsigned* d_ghist = nullptr;
+    if (sc.dalloc(&d_ghist, (size_t)nbins * 4)) return -1;
     if (volume_background(reinterpret_cast<const uint16_t*>(s->d_im), s->Z, s->X, s->Y, d_boxes, first, bin_size, nbins, max_iter,
                           d_ghist, d_out, st)) return -1;
   } else if (box_background(reinterpret_cast<const uint16_t*>(s->d_im), s->X, s->Y, d_boxes, n, first, bin_size, nbins, max_iter, d_out, st)) return -1;
   if (small_copy(ho, d_out, ob, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   memcpy(out, ho, ob);
-  host_free(h); dev_free(d_boxes); dev_free(d_out); dev_free(d_ghist);
+  return 0;
+}
+
+// Values of an intermediate seed-stage volume at n voxels (flat C-order indices): which = 0 foreground
+// blur, 1 background blur; out has the stack's dtype.  (Fitting_v3.get_seed_points_base reads its two
+// blurs at the candidate voxels only, External/Fitting_v3.py:276-283.)
+int ia3_seed_gather_volume(ia3_stack* s, int which, const int64_t* flat_idx, int64_t n, void* out) {
+  if (ensure_device()) return -1;
+  if (!s || (n > 0 && (!flat_idx || !out))) { set_error("null argument"); return -1; }
+  const void* src = which == 0 ? s->fg_final : s->bg_final;
+  if (!src) { set_error("seed stage has not run"); return -1; }
+  if (n <= 0) return 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (flat_idx[i] < 0 || (size_t)flat_idx[i] >= s->nvox) { set_error("voxel index outside the stack"); return -1; }
+  Scoped sc;
+  const size_t bi = (size_t)n * 8, bo = (size_t)n * dtype_size(s->dtype), obo = (bi + 255) / 256 * 256;
+  void* h = nullptr; long long* d_idx = nullptr; void* d_out = nullptr;
+  if (sc.halloc(&h, obo + bo) || sc.dalloc(&d_idx, bi) || sc.dalloc(&d_out, bo)) return -1;
+  memcpy(h, flat_idx, bi);
+  cudaStream_t st = s->stream;
+  if (small_copy(d_idx, h, bi, st)) return -1;
+  if (launch_gather_u16(src, s->dtype, d_idx, n, d_out, st)) return -1;
+  if (small_copy(static_cast<char*>(h) + obo, d_out, bo, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  memcpy(out, static_cast<char*>(h) + obo, bo);
   return 0;
 }
 
 // ---- fit stage ------------------------------------------------------------------------------
-static inline long long cell_key(long long a, long long b, long long c) {
-  return ((a + (1LL << 20)) << 42) | ((b + (1LL << 20)) << 21) | (c + (1LL << 20));
+}  // extern "C"
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
+// function evaluations per round for one-warp runs; >= team_after evaluations so far: a team of warps
+// continues the run, team_cap (long: nothing else pending) evaluations per round.  0 = never suspend.
+static const int g_cap_bulk = std::max(0, env_int("IA3_FIT_CAP", 12));
+static const int g_team_after = std::max(1, env_int("IA3_FIT_TEAM_AFTER", 48));
+static const int g_team_cap = std::max(1, env_int("IA3_FIT_TEAM_CAP", 32));
+static const int g_team_cap_long = std::max(1, env_int("IA3_FIT_TEAM_CAP_LONG", 160));
+static const int g_memo_on = env_int("IA3_FIT_MEMO", 1) != 0;
+static const int g_spec_on = env_int("IA3_FIT_SPEC", 1) != 0;
+static const int g_chunk = std::max(1, env_int("IA3_FIT_CHUNK", 8));
+
+struct ia3_fit {
+  ia3_stack* s = nullptr;
+  ia3_fit_cfg cfg;
+  FitDev d;
+  int64_t n = 0;
+  std::vector<double> centers;
+  std::vector<int8_t> offs;
+  bool prepared = false, started = false, first_done = false;
+  int64_t n_ties = 0;
+  int ties_prefetched = 0;
+  cudaStream_t st2 = nullptr;                     // team kernels of a round run beside the one-warp kernel
+  cudaEvent_t ev_s = nullptr, ev_t = nullptr, ev_chunk[2] = {nullptr, nullptr}, e0 = nullptr, e1 = nullptr;
+  void* arena = nullptr;                          // all per-seed device arrays
+  int* d_nbr_idx = nullptr; int* d_dep_idx = nullptr;
+  int* d_tie_spot = nullptr; int* d_tie_k = nullptr;
+  double* d_vol = nullptr;
+  int* d_cells = nullptr;                         // cell_cnt, cell_start, cell_cur
+  uint8_t* d_keep = nullptr; size_t keep_cap = 0;
+  CellGrid grid;
+  void* h_pin = nullptr;                          // pinned: done flag, copy of EngineCtl, prefetched ties
+  void* h_stage = nullptr; size_t stage_cap = 0;  // pinned staging, device -> host (results)
+  void* h_up = nullptr; size_t up_cap = 0;        // pinned staging, host -> device (centres, offsets)
+  void* h_keep = nullptr; size_t hkeep_cap = 0;   // pinned staging of the tie decisions (its own buffer: the copy is asynchronous)
+  int round = 0, gsweep = 0;
+  float last_ms = 0.f;
+  int n_levels = -1;
+  int* h_done() const { return static_cast<int*>(h_pin); }
+  EngineCtl* h_ctl() const { return reinterpret_cast<EngineCtl*>(static_cast<char*>(h_pin) + 256); }
+  int* h_ties() const { return reinterpret_cast<int*>(static_cast<char*>(h_pin) + 1024); }
+};
+constexpr int kTiePrefetch = 16384;               // ties copied with the count (one wait instead of two)
+constexpr size_t kPinBytes = 1024 + 2 * sizeof(int) * kTiePrefetch;
+
+static std::vector<cudaEvent_t> g_bs_event_pool;  // blocking-sync events: a waiting host thread sleeps
+static int acquire_event_bs(cudaEvent_t* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_bs_event_pool.empty()) { *out = g_bs_event_pool.back(); g_bs_event_pool.pop_back(); return 0; }
+  }
+  IA3_CUDA(cudaEventCreateWithFlags(out, cudaEventBlockingSync | cudaEventDisableTiming));
+  return 0;
+}
+static void release_event_bs(cudaEvent_t e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_bs_event_pool.push_back(e);
+}
+
+static int build_neighbours(ia3_fit* f) {
+  cudaStream_t st = f->s->stream;
+  const size_t nc = (size_t)f->grid.ncell;
+  int* cnt = f->d_cells;
+  int* start = cnt + nc;
+  int* cur = start + nc + 1;
+  int* order = cur + nc;
+  IA3_CUDA(cudaMemsetAsync(&f->d.ctl->pool_v, 0, 3 * sizeof(int), st));      // pool_v, pool_o, overflow
+  return launch_build_neighbours(f->d, f->grid, cnt, start, cur, order, st);
+}
+
+extern "C" {
 
 int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_fit_cfg* cfg, ia3_fit** out) {
   IA3_STAT("ia3_fit_create");
@@ -756,8 +812,17 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   if (cfg->radius < 1 || cfg->radius > 7) { set_error("radius_fit must be in 1..7 (window of at most 2048 voxels)"); return -1; }
   if (cfg->personality != 3 && cfg->personality != 4) { set_error("personality must be 3 or 4"); return -1; }
-  for (int64_t i = 0; i < 3 * n; ++i)
-    if (!(std::fabs(centers_zxy[i]) < 1e6)) { set_error("seed coordinates must be finite and |c| < 1e6"); return -1; }
+  if (cfg->eval_fp32) { set_error("eval_fp32 was removed: the fit evaluates in FP64 like the reference"); return -1; }
+  if (n >= (int64_t)TASK_SEED_MASK / 2) { set_error("too many seeds"); return -1; }
+  // window centres are int(c): keep them representable
+  double lo3[3] = {0, 0, 0}, hi3[3] = {0, 0, 0};
+  for (int64_t i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) {
+      const double v = centers_zxy[3 * i + a];
+      if (!(std::fabs(v) < 1e6)) { set_error("seed coordinates must be finite and |c| < 1e6"); return -1; }
+      if (i == 0 || v < lo3[a]) lo3[a] = v;
+      if (i == 0 || v > hi3[a]) hi3[a] = v;
+    }
   ia3_fit* f = new ia3_fit();
   f->s = s; f->cfg = *cfg; f->n = n;
   f->centers.assign(centers_zxy, centers_zxy + 3 * n);
@@ -768,157 +833,89 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
     if (a * a + b * b + c * c <= r * r) { f->offs.push_back((int8_t)a); f->offs.push_back((int8_t)b); f->offs.push_back((int8_t)c); }
   const int K = (int)(f->offs.size() / 3);
   const int KW = (K + 31) / 32;
-
-  // neighbour lists (seeds that can own a voxel of this seed's window) and dependency levels
-  const double reach = 2.0 * ((double)r + 1.7320508075688772) + 1e-6;
-  const double cs = std::ceil(reach);
-  // uniform grid of cells of edge >= reach, as a counting sort (cell -> [start, end) in `order`)
-  double lo3[3] = {0, 0, 0}, hi3[3] = {0, 0, 0};
-  for (int64_t i = 0; i < n; ++i)
-    for (int a = 0; a < 3; ++a) {
-      const double v = f->centers[3 * i + a];
-      if (i == 0 || v < lo3[a]) lo3[a] = v;
-      if (i == 0 || v > hi3[a]) hi3[a] = v;
-    }
-  long long gdim[3];
-  for (int a = 0; a < 3; ++a) gdim[a] = (long long)std::floor((hi3[a] - lo3[a]) / cs) + 1;
-  double cse = cs;
-  while ((double)gdim[0] * (double)gdim[1] * (double)gdim[2] > 4.0e7) {     // absurdly sparse seeds: coarser cells
-    cse *= 2.0;
-    for (int a = 0; a < 3; ++a) gdim[a] = (long long)std::floor((hi3[a] - lo3[a]) / cse) + 1;
-  }
-  auto cellc = [&](double v, int a) { return (long long)std::floor((v - lo3[a]) / cse); };
-  const long long ncell = (n > 0) ? gdim[0] * gdim[1] * gdim[2] : 0;
-  std::vector<int> cell_start((size_t)ncell + 1, 0), order((size_t)n), cell_of((size_t)n);
-  for (int64_t i = 0; i < n; ++i) {
-    const double* c = &f->centers[3 * i];
-    const long long id = (cellc(c[0], 0) * gdim[1] + cellc(c[1], 1)) * gdim[2] + cellc(c[2], 2);
-    cell_of[i] = (int)id;
-    cell_start[id + 1] += 1;
-  }
-  for (long long k = 0; k < ncell; ++k) cell_start[k + 1] += cell_start[k];
-  {
-    std::vector<int> fill(cell_start.begin(), cell_start.end() - (ncell > 0 ? 1 : 0));
-    for (int64_t i = 0; i < n; ++i) order[fill[cell_of[i]]++] = (int)i;
-  }
-  std::vector<int> nbr_start(n + 1, 0), nbr_idx, own(n);
-  f->level.assign(n, 0);
-  int n_levels = 0;
-  const int lim = 2 * r - 1;
-  for (int64_t i = 0; i < n; ++i) {
-    const double* c = &f->centers[3 * i];
-    const long long a = cellc(c[0], 0), b = cellc(c[1], 1), cc = cellc(c[2], 2);
-    const int ic[3] = {(int)c[0], (int)c[1], (int)c[2]};
-    int lvl = 0, ownid = (int)i;
-    const size_t begin = nbr_idx.size();
-    for (long long da = -1; da <= 1; ++da) for (long long db = -1; db <= 1; ++db) for (long long dc = -1; dc <= 1; ++dc) {
-      const long long ca = a + da, cb = b + db, ccc = cc + dc;
-      if (ca < 0 || ca >= gdim[0] || cb < 0 || cb >= gdim[1] || ccc < 0 || ccc >= gdim[2]) continue;
-      const long long id = (ca * gdim[1] + cb) * gdim[2] + ccc;
-      for (int e = cell_start[id]; e < cell_start[id + 1]; ++e) {
-        const int j = order[e];
-        if (j == (int)i) continue;
-        const double* q = &f->centers[3 * j];
-        const double d0 = q[0] - c[0], d1 = q[1] - c[1], d2 = q[2] - c[2];
-        if (d0 * d0 + d1 * d1 + d2 * d2 <= reach * reach) nbr_idx.push_back(j);
-        if (d0 == 0 && d1 == 0 && d2 == 0 && j < ownid) ownid = j;
-        if (j < (int)i) {
-          const int e0 = std::abs((int)q[0] - ic[0]), e1 = std::abs((int)q[1] - ic[1]), e2 = std::abs((int)q[2] - ic[2]);
-          if (e0 <= lim && e1 <= lim && e2 <= lim && e0 * e0 + e1 * e1 + e2 * e2 <= 4 * r * r)
-            lvl = std::max(lvl, f->level[j] + 1);
-        }
-      }
-    }
-    std::sort(nbr_idx.begin() + begin, nbr_idx.end());
-    nbr_start[i + 1] = (int)nbr_idx.size();
-    own[i] = ownid;
-    f->level[i] = lvl;
-    n_levels = std::max(n_levels, lvl + 1);
-  }
-  f->n_levels = n_levels;
-
-  // inputs go through one pinned arena (no pageable copies), the brick table included
-  const int nbz = (s->Z + 7) / 8, nbx = (s->X + 7) / 8, nby = (s->Y + 7) / 8;
-  const size_t tab_n = (size_t)nbz * nbx * nby;
-  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  const size_t up_total = al(f->centers.size() * 8) + al(own.size() * 4) + al(nbr_start.size() * 4) + al(nbr_idx.size() * 4) +
-                          al(f->offs.size()) + al(tab_n * 4) + al((size_t)std::max<int64_t>(n, 1) * 4);
-  if (reserve_pinned(&f->h_up, &f->up_cap, up_total)) { ia3_fit_destroy(f); return -1; }
-  size_t up_off = 0;
-  auto put = [&](void** d, const void* src, size_t bytes) -> int {
-    if (dev_alloc(d, bytes)) return -1;
-    if (bytes) {
-      char* h = static_cast<char*>(f->h_up) + up_off;
-      memcpy(h, src, bytes);
-      if (small_copy(*d, h, bytes, st)) return -1;
-      up_off += (bytes + 255) / 256 * 256;
-    }
-    return 0;
-  };
-  if (put((void**)&f->d_centers, f->centers.data(), f->centers.size() * 8) || put((void**)&f->d_own, own.data(), own.size() * 4) ||
-      put((void**)&f->d_nbr_start, nbr_start.data(), nbr_start.size() * 4) || put((void**)&f->d_nbr_idx, nbr_idx.data(), nbr_idx.size() * 4) ||
-      put((void**)&f->d_offs, f->offs.data(), f->offs.size())) { ia3_fit_destroy(f); return -1; }
   const size_t nn = (size_t)std::max<int64_t>(n, 1);
-  if (dev_alloc((void**)&f->d_mask, nn * KW * 4) || dev_alloc((void**)&f->d_ps, nn * NOUT * 4) ||
-      dev_alloc((void**)&f->d_praw, nn * NP * 8) || dev_alloc((void**)&f->d_succ, nn) ||
-      dev_alloc((void**)&f->d_nfev, nn * 4) || dev_alloc((void**)&f->d_info, nn * 4) ||
-      dev_alloc((void**)&f->d_rec, nn * K * 8) || dev_alloc((void**)&f->d_snap, nn * K * 8) ||
-      dev_alloc((void**)&f->d_tie_count, 256)) { ia3_fit_destroy(f); return -1; }
-  // sparse float64 work volume: the 8x8x8 bricks touched by some seed's (clipped) window
-  {
-    std::vector<int> tab(tab_n, -1);
-    int next = 0;
-    for (int64_t i = 0; i < n; ++i) {
-      int lo[3], hi[3];
-      const int dims[3] = {s->Z, s->X, s->Y};
-      bool empty = false;
-      for (int a = 0; a < 3; ++a) {
-        const int ic = (int)f->centers[3 * i + a];
-        lo[a] = std::max(ic - r, 0);
-        hi[a] = std::min(ic + r - 1, dims[a] - 1);
-        if (lo[a] > hi[a]) empty = true;
-      }
-      if (empty) continue;
-      for (int bz = lo[0] >> 3; bz <= hi[0] >> 3; ++bz)
-        for (int bx = lo[1] >> 3; bx <= hi[1] >> 3; ++bx)
-          for (int by = lo[2] >> 3; by <= hi[2] >> 3; ++by) {
-            int& t = tab[((size_t)bz * nbx + bx) * nby + by];
-            if (t < 0) t = next++;
-          }
-    }
-    f->n_bricks = next;
-    if (put((void**)&f->d_brick_tab, tab.data(), tab_n * 4) || dev_alloc((void**)&f->d_vol, (size_t)std::max(next, 1) * 512 * 8)) { ia3_fit_destroy(f); return -1; }
+
+  // uniform grid of cells of edge >= the neighbour reach (coarser if the seeds are absurdly sparse)
+  CellGrid& g = f->grid;
+  g.cs = std::ceil(2.0 * ((double)r + 1.7320508075688772) + 1e-6);
+  for (;;) {
+    double prod = 1.0;
+    for (int a = 0; a < 3; ++a) { g.lo[a] = lo3[a]; g.g[a] = (int)std::floor((hi3[a] - lo3[a]) / g.cs) + 1; prod *= (double)g.g[a]; }
+    if (prod <= 4.0e6) break;
+    g.cs *= 2.0;
   }
-  IA3_CUDA(cudaMemsetAsync(f->d_succ, 0, nn, st));
-  IA3_CUDA(cudaMemsetAsync(f->d_rec, 0, nn * K * 8, st));
-  if (acquire_event(&f->e0) || acquire_event(&f->e1)) { ia3_fit_destroy(f); return -1; }
+  g.ncell = (long long)g.g[0] * g.g[1] * g.g[2];
+
+#define FAIL() do { ia3_fit_destroy(f); return -1; } while (0)
+  if (acquire_stream(&f->st2) || acquire_event_bs(&f->ev_chunk[0]) || acquire_event_bs(&f->ev_chunk[1]) ||
+      acquire_event(&f->ev_s) || acquire_event(&f->ev_t) || acquire_event(&f->e0) || acquire_event(&f->e1)) FAIL();
+  if (host_alloc(&f->h_pin, kPinBytes)) FAIL();
+  memset(f->h_pin, 0, 1024);
 
   FitDev& d = f->d;
   memset(&d, 0, sizeof(d));
-  d.im = s->d_im; d.im_dtype = s->dtype; d.vol = f->d_vol; d.brick_tab = f->d_brick_tab; d.nbx = nbx; d.nby = nby;
+  const int nbz = (s->Z + 7) / 8, nbx = (s->X + 7) / 8, nby = (s->Y + 7) / 8;
+  const size_t tab_n = (size_t)nbz * nbx * nby;
+  d.list_cap = (int)(2 * nn + 64);
+  // one arena for every per-seed array
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_ctl = carve(sizeof(EngineCtl)), o_cen = carve(nn * 24), o_offs = carve(f->offs.size()), o_own = carve(nn * 4),
+               o_ns = carve(nn * 4), o_nc = carve(nn * 4), o_ds = carve(nn * 4), o_dc = carve(nn * 4), o_nl = carve(nn * 4),
+               o_mask = carve(nn * KW * 4), o_ps = carve(nn * NOUT * 4), o_praw = carve(nn * NP * 8), o_succ = carve(nn),
+               o_nfev = carve(nn * 4), o_info = carve(nn * 4), o_rec = carve(nn * K * 8), o_pf = carve(nn * NP * 8), o_sf = carve(nn),
+               o_stage = carve(nn * 4), o_fin = carve(nn), o_busy = carve(nn), o_conv = carve(nn), o_spec = carve(nn),
+               o_sprev = carve(nn), o_cprev = carve(nn * 12), o_dists = carve(nn * 8), o_kd = carve(nn * K * 4), o_kx = carve(nn * NP * 8),
+               o_mp = carve(nn * NP * 8), o_mm = carve(nn * 16), o_mv = carve(nn), o_mc = carve(nn), o_live = carve(2 * nn * sizeof(LMLive)),
+               o_lists = carve((size_t)6 * d.list_cap * 4), o_tab = carve(tab_n * 4);
+  if (dev_alloc(&f->arena, off)) FAIL();
+  char* A = static_cast<char*>(f->arena);
+  d.ctl = reinterpret_cast<EngineCtl*>(A + o_ctl);
+  d.centers = reinterpret_cast<double*>(A + o_cen); d.offs = reinterpret_cast<int8_t*>(A + o_offs);
+  d.own_id = reinterpret_cast<int*>(A + o_own); d.nbr_start = reinterpret_cast<int*>(A + o_ns); d.nbr_cnt = reinterpret_cast<int*>(A + o_nc);
+  d.dep_start = reinterpret_cast<int*>(A + o_ds); d.dep_cnt = reinterpret_cast<int*>(A + o_dc); d.n_lower = reinterpret_cast<int*>(A + o_nl);
+  d.mask = reinterpret_cast<uint32_t*>(A + o_mask); d.ps = reinterpret_cast<float*>(A + o_ps); d.p_raw = reinterpret_cast<double*>(A + o_praw);
+  d.success = reinterpret_cast<uint8_t*>(A + o_succ); d.nfev = reinterpret_cast<int*>(A + o_nfev); d.info = reinterpret_cast<int*>(A + o_info);
+  d.rec = reinterpret_cast<double*>(A + o_rec); d.praw_first = reinterpret_cast<double*>(A + o_pf); d.succ_first = reinterpret_cast<uint8_t*>(A + o_sf);
+  d.stage = reinterpret_cast<int*>(A + o_stage); d.fin = reinterpret_cast<uint8_t*>(A + o_fin); d.busy = reinterpret_cast<uint8_t*>(A + o_busy);
+  d.conv = reinterpret_cast<uint8_t*>(A + o_conv); d.specst = reinterpret_cast<uint8_t*>(A + o_spec); d.succ_prev = reinterpret_cast<uint8_t*>(A + o_sprev);
+  d.cen_prev = reinterpret_cast<float*>(A + o_cprev); d.dists = reinterpret_cast<double*>(A + o_dists);
+  d.key_d32 = reinterpret_cast<float*>(A + o_kd); d.key_x0 = reinterpret_cast<double*>(A + o_kx); d.memo_praw = reinterpret_cast<double*>(A + o_mp);
+  d.memo_meta = reinterpret_cast<int*>(A + o_mm); d.memo_valid = reinterpret_cast<uint8_t*>(A + o_mv); d.memo_committed = reinterpret_cast<uint8_t*>(A + o_mc);
+  d.live = reinterpret_cast<LMLive*>(A + o_live); d.lists = reinterpret_cast<unsigned*>(A + o_lists); d.brick_tab = reinterpret_cast<int*>(A + o_tab);
+  d.h_done = f->h_done();
+
+  d.pool_cap_v = (int)std::min<size_t>(std::max<size_t>(32 * nn, 4096), (size_t)1 << 28);
+  d.pool_cap_o = d.pool_cap_v;
+  d.tie_cap = (int)std::min<int64_t>(std::max<int64_t>(n * 8, 4096), (int64_t)1 << 24);
+  if (dev_alloc((void**)&f->d_nbr_idx, sizeof(int) * (size_t)d.pool_cap_v) || dev_alloc((void**)&f->d_dep_idx, sizeof(int) * (size_t)d.pool_cap_o) ||
+      dev_alloc((void**)&f->d_tie_spot, sizeof(int) * (size_t)d.tie_cap) || dev_alloc((void**)&f->d_tie_k, sizeof(int) * (size_t)d.tie_cap) ||
+      dev_alloc((void**)&f->d_cells, sizeof(int) * ((size_t)3 * g.ncell + 1 + nn))) FAIL();
+  d.nbr_idx = f->d_nbr_idx; d.dep_idx = f->d_dep_idx; d.tie_spot = f->d_tie_spot; d.tie_k = f->d_tie_k;
+
+  d.im = s->d_im; d.im_dtype = s->dtype; d.nbz = nbz; d.nbx = nbx; d.nby = nby;
   d.Z = s->Z; d.X = s->X; d.Y = s->Y;
-  d.n = n; d.centers = f->d_centers; d.own_id = f->d_own; d.nbr_start = f->d_nbr_start; d.nbr_idx = f->d_nbr_idx;
-  d.K = K; d.KW = KW; d.offs = f->d_offs; d.mask = f->d_mask;
-  d.tie_count = f->d_tie_count;
-  d.ps = f->d_ps; d.p_raw = f->d_praw; d.success = f->d_succ; d.nfev = f->d_nfev; d.info = f->d_info;
-  d.rec = f->d_rec;
+  d.n = n; d.K = K; d.KW = KW; d.radius = r;
   d.fp.min_w2 = cfg->min_w * cfg->min_w; d.fp.max_w2 = cfg->max_w * cfg->max_w;
   d.fp.delta = 1.0; d.fp.weight_sigma = cfg->weight_sigma; d.fp.personality = cfg->personality;
   d.fp.init_wt[0] = d.fp.init_wt[1] = d.fp.init_wt[2] = 0.0;
   d.lm.ftol = 1.49012e-8; d.lm.xtol = 1.49012e-8; d.lm.gtol = 0.0; d.lm.factor = 100.0;
   d.lm.maxfev = cfg->maxfev > 0 ? cfg->maxfev : (cfg->personality == 4 ? 1000 : 1100);
   for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
-  d.cap = (cfg->eval_fp32 != 0) ? 0 : g_fit_cap;
-  if (d.cap > 0) {
-    d.pause_slots = (int)std::min<int64_t>(std::max<int64_t>(n, 1), 1024);
-    void* hp = nullptr;
-    if (dev_alloc((void**)&f->d_pause, sizeof(LMPause) * (size_t)d.pause_slots) ||
-        dev_alloc((void**)&f->d_pause_ctl, sizeof(int) * (size_t)(1 + d.pause_slots)) ||
-        host_alloc(&hp, sizeof(int) * (size_t)(1 + d.pause_slots))) { ia3_fit_destroy(f); return -1; }
-    f->h_pause_ctl = static_cast<int*>(hp);
-    d.pause_buf = f->d_pause; d.pause_ctl = f->d_pause_ctl;
-  }
-  IA3_CUDA(cudaStreamSynchronize(st));
+  d.delta_first = 1.0; d.delta_repeat = 2.5; d.th2 = 0.01; d.max_sweeps = 11;
+  d.cap_bulk = g_cap_bulk; d.team_after = g_team_after; d.cap_team_short = g_team_cap; d.cap_team_long = g_team_cap_long;
+  d.memo_on = g_memo_on;
+
+  // inputs go through one pinned arena (no pageable copies); it is next written after a synchronisation
+  const size_t b_cen = (size_t)n * 24, b_off = f->offs.size();
+  if (reserve_pinned(&f->h_up, &f->up_cap, (b_cen + 255) / 256 * 256 + b_off)) FAIL();
+  char* hu = static_cast<char*>(f->h_up);
+  if (b_cen) memcpy(hu, f->centers.data(), b_cen);
+  memcpy(hu + (b_cen + 255) / 256 * 256, f->offs.data(), b_off);
+  if (small_copy(const_cast<double*>(d.centers), hu, b_cen, st) || small_copy(const_cast<int8_t*>(d.offs), hu + (b_cen + 255) / 256 * 256, b_off, st)) FAIL();
+  if (cudaMemsetAsync(d.ctl, 0, sizeof(EngineCtl), st) != cudaSuccess) { set_error("cudaMemsetAsync failed"); FAIL(); }
+  if (build_neighbours(f) || launch_build_bricks(d, st)) FAIL();
+#undef FAIL
   *out = f;
   return 0;
 }
@@ -928,16 +925,13 @@ int ia3_fit_destroy(ia3_fit* f) {
   if (!f) return 0;
   if (g_device >= 0) cudaSetDevice(g_device);
   if (f->s && f->s->stream) cudaStreamSynchronize(f->s->stream);
-  void* ptrs[] = {f->d_centers, f->d_own, f->d_nbr_start, f->d_nbr_idx, f->d_offs, f->d_mask, f->d_tie_count,
-                  f->d_tie_spot, f->d_tie_k, f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info, f->d_rec,
-                  f->d_snap, f->d_vol, f->d_work, f->d_brick_tab};
+  if (f->st2) cudaStreamSynchronize(f->st2);
+  void* ptrs[] = {f->arena, f->d_nbr_idx, f->d_dep_idx, f->d_tie_spot, f->d_tie_k, f->d_vol, f->d_cells, f->d_keep};
   for (void* p : ptrs) dev_free(p);
-  release_event(f->e0);
-  release_event(f->e1);
-  host_free(f->h_stage);
-  host_free(f->h_up);
-  host_free(f->h_pause_ctl);
-  dev_free(f->d_keep); dev_free(f->d_pause); dev_free(f->d_pause_ctl);
+  release_event(f->ev_s); release_event(f->ev_t); release_event(f->e0); release_event(f->e1);
+  release_event_bs(f->ev_chunk[0]); release_event_bs(f->ev_chunk[1]);
+  release_stream(f->st2);
+  host_free(f->h_pin); host_free(f->h_stage); host_free(f->h_up); host_free(f->h_keep);
   delete f;
   return 0;
 }
@@ -946,29 +940,45 @@ int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
   IA3_STAT("ia3_fit_first_prepare");
   if (ensure_device()) return -1;
   if (!f) { set_error("null argument"); return -1; }
+  if (f->prepared) { if (n_ties) *n_ties = f->n_ties; return 0; }
   cudaStream_t st = f->s->stream;
-  int cap = (int)std::min<int64_t>(std::max<int64_t>(f->n * 8, 4096), (int64_t)1 << 24);
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    if (cap > f->tie_cap) {
+  FitDev& d = f->d;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    IA3_CUDA(cudaMemsetAsync(&d.ctl->tie_count, 0, sizeof(int), st));
+    if (launch_voronoi(d, st)) return -1;
+    const int npre = std::min(d.tie_cap, kTiePrefetch);
+    if (small_copy(f->h_ctl(), d.ctl, sizeof(EngineCtl), st) || small_copy(f->h_ties(), d.tie_spot, sizeof(int) * (size_t)npre, st) ||
+        small_copy(f->h_ties() + kTiePrefetch, d.tie_k, sizeof(int) * (size_t)npre, st)) return -1;
+    IA3_CUDA(cudaStreamSynchronize(st));
+    const EngineCtl& c = *f->h_ctl();
+    if (c.overflow) {               // a neighbour pool was too small (dense clusters): the counts are the sizes needed
+      dev_free(f->d_nbr_idx); dev_free(f->d_dep_idx);
+      f->d_nbr_idx = f->d_dep_idx = nullptr;
+      d.pool_cap_v = std::max(c.pool_v, 1); d.pool_cap_o = std::max(c.pool_o, 1);
+      if (dev_alloc((void**)&f->d_nbr_idx, sizeof(int) * (size_t)d.pool_cap_v) || dev_alloc((void**)&f->d_dep_idx, sizeof(int) * (size_t)d.pool_cap_o)) return -1;
+      d.nbr_idx = f->d_nbr_idx; d.dep_idx = f->d_dep_idx;
+      if (build_neighbours(f)) return -1;
+      continue;
+    }
+    f->n_ties = c.tie_count;
+    if (c.tie_count > d.tie_cap) {
       dev_free(f->d_tie_spot); dev_free(f->d_tie_k);
       f->d_tie_spot = f->d_tie_k = nullptr;
-      if (dev_alloc((void**)&f->d_tie_spot, sizeof(int) * (size_t)cap) || dev_alloc((void**)&f->d_tie_k, sizeof(int) * (size_t)cap)) return -1;
-      f->tie_cap = cap;
+      d.tie_cap = c.tie_count;
+      if (dev_alloc((void**)&f->d_tie_spot, sizeof(int) * (size_t)d.tie_cap) || dev_alloc((void**)&f->d_tie_k, sizeof(int) * (size_t)d.tie_cap)) return -1;
+      d.tie_spot = f->d_tie_spot; d.tie_k = f->d_tie_k;
+      continue;
     }
-    f->d.tie_cap = f->tie_cap; f->d.tie_spot = f->d_tie_spot; f->d.tie_k = f->d_tie_k;
-    IA3_CUDA(cudaMemsetAsync(f->d_tie_count, 0, sizeof(int), st));
-    if (launch_voronoi(f->d, st)) return -1;
-    if (reserve_pinned(&f->h_stage, &f->stage_cap, 256)) return -1;
-    if (small_copy(f->h_stage, f->d_tie_count, sizeof(int), st)) return -1;
-    IA3_CUDA(cudaStreamSynchronize(st));
-    const int cnt = *static_cast<int*>(f->h_stage);
-    f->n_ties = cnt;
-    if (cnt <= f->tie_cap) break;
-    cap = cnt;
+    f->ties_prefetched = std::min<int>(c.tie_count, npre);
+    // sparse float64 work volume: the 8x8x8 bricks touched by some seed's (clipped) window
+    if (!f->d_vol && dev_alloc((void**)&f->d_vol, (size_t)std::max(c.n_bricks, 1) * 512 * 8)) return -1;
+    d.vol = f->d_vol;
+    f->prepared = true;
+    if (n_ties) *n_ties = f->n_ties;
+    return 0;
   }
-  f->prepared = true;
-  if (n_ties) *n_ties = f->n_ties;
-  return 0;
+  set_error("first_prepare: neighbour / tie buffers did not settle");
+  return -1;
 }
 
 int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
@@ -977,12 +987,16 @@ int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
   if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
   const int64_t n = std::min<int64_t>(cap, f->n_ties);
   if (n <= 0) return 0;
-  if (reserve_pinned(&f->h_stage, &f->stage_cap, 2 * sizeof(int) * (size_t)n)) return -1;
-  int* sp = static_cast<int*>(f->h_stage);
-  int* kk = sp + n;
-  if (small_copy(sp, f->d_tie_spot, sizeof(int) * (size_t)n, f->s->stream) ||
-      small_copy(kk, f->d_tie_k, sizeof(int) * (size_t)n, f->s->stream)) return -1;
-  IA3_CUDA(cudaStreamSynchronize(f->s->stream));
+  const int* sp = f->h_ties();
+  const int* kk = f->h_ties() + kTiePrefetch;
+  if (n > f->ties_prefetched) {
+    if (reserve_pinned(&f->h_stage, &f->stage_cap, 2 * sizeof(int) * (size_t)n)) return -1;
+    int* a = static_cast<int*>(f->h_stage);
+    if (small_copy(a, f->d_tie_spot, sizeof(int) * (size_t)n, f->s->stream) ||
+        small_copy(a + n, f->d_tie_k, sizeof(int) * (size_t)n, f->s->stream)) return -1;
+    IA3_CUDA(cudaStreamSynchronize(f->s->stream));
+    sp = a; kk = a + n;
+  }
   for (int64_t i = 0; i < n; ++i) {
     const int sidx = sp[i], k = kk[i];
     spot[i] = sidx;
@@ -995,6 +1009,7 @@ int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
   IA3_STAT("ia3_fit_first_resolve");
   if (ensure_device()) return -1;
   if (!f || !f->prepared) { set_error("first_prepare has not run"); return -1; }
+  if (f->started) { set_error("first_resolve after the fit has started"); return -1; }
   n = std::min<int64_t>(n, f->n_ties);
   if (n <= 0) return 0;
   if ((size_t)n > f->keep_cap) {
@@ -1004,79 +1019,116 @@ int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
     f->keep_cap = (size_t)n;
   }
   cudaStream_t st = f->s->stream;
-  if (reserve_pinned(&f->h_up, &f->up_cap, (size_t)n)) return -1;
-  memcpy(f->h_up, keep, (size_t)n);
-  if (small_copy(f->d_keep, f->h_up, (size_t)n, st)) return -1;
-  if (launch_apply_ties(f->d_mask, f->d.KW, f->d_tie_spot, f->d_tie_k, f->d_keep, (int)n, st)) return -1;
-  return 0;        // stream-ordered before first_run; the arena is next touched after first_run's synchronisation
-}
-
-static int fetch_results(ia3_fit* f, float* ps, double* p_raw, uint8_t* success, int32_t* nfev, int32_t* info) {
-  cudaStream_t st = f->s->stream;
-  const size_t n = (size_t)f->n;
-  if (n == 0) return 0;
-  // device -> pinned staging (asynchronous copies queued behind the kernels), one wait, then plain
-  // memcpy into the caller's arrays: no pageable-memory copy ever enters the driver
-  const size_t sz[5] = {n * NOUT * 4, n * NP * 8, n, n * 4, n * 4};
-  const void* src[5] = {f->d_ps, f->d_praw, f->d_succ, f->d_nfev, f->d_info};
-  void* dst[5] = {ps, p_raw, success, nfev, info};
-  size_t off[5], total = 0;
-  for (int i = 0; i < 5; ++i) { off[i] = total; total += (sz[i] + 255) / 256 * 256; }
-  if (reserve_pinned(&f->h_stage, &f->stage_cap, total)) return -1;
-  char* h = static_cast<char*>(f->h_stage);
-  for (int i = 0; i < 5; ++i)
-    if (dst[i] && small_copy(h + off[i], src[i], sz[i], st)) return -1;
-  { IA3_STAT("  fetch: wait for stream"); IA3_DRAIN(st); }
-  for (int i = 0; i < 5; ++i) if (dst[i]) memcpy(dst[i], h + off[i], sz[i]);
+  // the copy is asynchronous: the flags get a pinned buffer of their own, which nothing else writes
+  if (reserve_pinned(&f->h_keep, &f->hkeep_cap, (size_t)n)) return -1;
+  memcpy(f->h_keep, keep, (size_t)n);
+  if (small_copy(f->d_keep, f->h_keep, (size_t)n, st)) return -1;
+  if (launch_apply_ties(f->d.mask, f->d.KW, f->d_tie_spot, f->d_tie_k, f->d_keep, (int)n, st)) return -1;
   return 0;
 }
 
-// builds per-level work lists of the selected seeds; returns level boundaries
-static int build_work(ia3_fit* f, const uint8_t* active, std::vector<int>& bounds) {
-  IA3_STAT("  build_work");
-  std::vector<std::vector<int>> per(f->n_levels);
-  for (int64_t i = 0; i < f->n; ++i)
-    if (!active || active[i]) per[f->level[i]].push_back((int)i);
-  std::vector<int> flat;
-  bounds.assign(1, 0);
-  for (auto& v : per) { flat.insert(flat.end(), v.begin(), v.end()); bounds.push_back((int)flat.size()); }
-  if (flat.size() > f->work_cap) {
-    dev_free(f->d_work);
-    f->d_work = nullptr;
-    if (dev_alloc((void**)&f->d_work, sizeof(int) * std::max<size_t>(flat.size(), (size_t)f->n))) return -1;
-    f->work_cap = std::max<size_t>(flat.size(), (size_t)f->n);
+}  // extern "C"
+
+// rounds until the scheduler reports that nothing is left to do.  Rounds are enqueued a chunk ahead of
+// the host's look at the done flag, so the device never waits for the host; the rounds still queued
+// when the flag is seen find empty work lists.
+static int engine_run(ia3_fit* f, int phases, int sweep_cap) {
+  cudaStream_t st = f->s->stream, st2 = f->st2;
+  const FitDev& d = f->d;
+  if (f->n == 0) return 0;
+  *(volatile int*)f->h_done() = 0;
+  IA3_CUDA(cudaMemsetAsync(&d.ctl->done, 0, sizeof(int), st));
+  for (int chunk = 0;; ++chunk) {
+    if (chunk > 100000) { set_error("fit engine did not finish"); return -1; }
+    for (int r = 0; r < g_chunk; ++r) {
+      if (launch_sched(d, f->round, phases, sweep_cap, st)) return -1;
+      IA3_CUDA(cudaEventRecord(f->ev_s, st));
+      IA3_CUDA(cudaStreamWaitEvent(st2, f->ev_s, 0));
+      if (launch_fit_round(d, f->round, true, st2)) return -1;
+      IA3_CUDA(cudaEventRecord(f->ev_t, st2));
+      if (launch_fit_round(d, f->round, false, st)) return -1;
+      IA3_CUDA(cudaStreamWaitEvent(st, f->ev_t, 0));
+      ++f->round;
+    }
+    IA3_CUDA(cudaEventRecord(f->ev_chunk[chunk & 1], st));
+    if (chunk >= 1) {
+      IA3_STAT("  engine: wait for chunk");
+      IA3_CUDA(cudaEventSynchronize(f->ev_chunk[(chunk - 1) & 1]));
+      if (*(volatile int*)f->h_done()) break;
+    }
   }
-  if (!flat.empty()) {
-    // the previous call on this handle ended with a stream synchronisation, so the arena is free
-    if (reserve_pinned(&f->h_up, &f->up_cap, sizeof(int) * flat.size())) return -1;
-    memcpy(f->h_up, flat.data(), sizeof(int) * flat.size());
-    if (small_copy(f->d_work, f->h_up, sizeof(int) * flat.size(), f->s->stream)) return -1;
+  return 0;
+}
+
+static int engine_start(ia3_fit* f) {
+  if (f->started) return 0;
+  cudaStream_t st = f->s->stream;
+  if (!f->prepared && ia3_fit_first_prepare(f, nullptr)) return -1;
+  if (launch_engine_reset(f->d, st) || launch_member_stats(f->d, st) || launch_init_window(f->d, st)) return -1;
+  f->started = true;
+  return 0;
+}
+
+static int fetch_results(ia3_fit* f, const ia3_fit_out* o) {
+  cudaStream_t st = f->s->stream;
+  const size_t n = (size_t)f->n;
+  if (n == 0 || !o) return 0;
+  // device -> pinned staging (copy kernels queued behind the rounds), one wait, then plain memcpy
+  // into the caller's arrays: no pageable-memory copy ever enters the driver
+  const FitDev& d = f->d;
+  constexpr int NA = 10;
+  const size_t sz[NA] = {n * NOUT * 4, n * NP * 8, n, n * 4, n * 4, n, n * 8, n * 4, n, n * 12};
+  const void* src[NA] = {d.ps, d.p_raw, d.success, d.nfev, d.info, d.conv, d.dists, d.stage, d.succ_prev, d.cen_prev};
+  void* dst[NA] = {o->ps, o->p_raw, o->success, o->nfev, o->info, o->converged, o->dists, o->n_visits, o->success_old, o->centers_old};
+  size_t off[NA], total = 0;
+  for (int i = 0; i < NA; ++i) { off[i] = total; total += (sz[i] + 255) / 256 * 256; }
+  if (reserve_pinned(&f->h_stage, &f->stage_cap, total)) return -1;
+  char* h = static_cast<char*>(f->h_stage);
+  for (int i = 0; i < NA; ++i)
+    if (dst[i] && small_copy(h + off[i], src[i], sz[i], st)) return -1;
+  { IA3_STAT("  fetch: wait for stream"); IA3_DRAIN(st); }
+  for (int i = 0; i < NA; ++i) if (dst[i]) memcpy(dst[i], h + off[i], sz[i]);
+  return 0;
+}
+
+extern "C" {
+
+int ia3_fit_run(ia3_fit* f, int phases, double min_delta_center, double max_delta_center, double max_dist_th2,
+                int n_max_iter, const ia3_fit_out* out) {
+  IA3_STAT("ia3_fit_run");
+  if (ensure_device()) return -1;
+  if (!f) { set_error("null argument"); return -1; }
+  if (!(phases & 3)) { set_error("phases: 1 = firstfit, 2 = repeatfit, 3 = both"); return -1; }
+  if ((phases & 1) && f->first_done) phases &= ~1;
+  if ((phases & 2) && !(phases & 1) && !f->first_done) { set_error("firstfit has not run"); return -1; }
+  if ((phases & 1) && !f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  cudaStream_t st = f->s->stream;
+  FitDev& d = f->d;
+  if (phases & 1) d.delta_first = min_delta_center;
+  if (phases & 2) {
+    if (f->started && d.delta_repeat != max_delta_center) IA3_CUDA(cudaMemsetAsync(d.memo_valid, 0, (size_t)std::max<int64_t>(f->n, 1), st));
+    d.delta_repeat = max_delta_center;
+    d.th2 = max_dist_th2;
+    d.max_sweeps = std::max(1, n_max_iter + 1);       // n_iter > n_max_iter stops the reference's loop
   }
+  if (engine_start(f)) return -1;
+  int ph = phases & 3;
+  if (phases == 3 && g_spec_on && g_memo_on) ph |= 4;
+  IA3_CUDA(cudaEventRecord(f->e0, st));
+  if (ph && engine_run(f, ph, 1 << 20)) return -1;
+  IA3_CUDA(cudaEventRecord(f->e1, st));
+  if (fetch_results(f, out)) return -1;
+  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  if (phases & 1) f->first_done = true;
   return 0;
 }
 
 int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw, uint8_t* success, int32_t* nfev,
                       int32_t* info) {
-  IA3_STAT("ia3_fit_first_run");
-  if (ensure_device()) return -1;
-  if (!f) { set_error("null argument"); return -1; }
-  if (!f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
-  if (!f->prepared && ia3_fit_first_prepare(f, nullptr)) return -1;
-  cudaStream_t st = f->s->stream;
-  f->d.fp.delta = delta_center;
-  std::vector<int> bounds;
-  if (build_work(f, nullptr, bounds)) return -1;
-  IA3_CUDA(cudaEventRecord(f->e0, st));
-  if (launch_init_window(f->d, st)) return -1;
-  if (run_fit_launch(f, 0, nullptr, f->n)) return -1;
-  for (int l = 0; l < f->n_levels; ++l)
-    if (launch_subtract(f->d, f->d_work + bounds[l], bounds[l + 1] - bounds[l], st)) return -1;
-  if (launch_window_copy(f->d, f->d_snap, nullptr, 0, st)) return -1;
-  IA3_CUDA(cudaEventRecord(f->e1, st));
-  if (fetch_results(f, ps, p_raw, success, nfev, info)) return -1;
-  cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
-  f->first_done = true;
-  return 0;
+  ia3_fit_out o;
+  memset(&o, 0, sizeof(o));
+  o.ps = ps; o.p_raw = p_raw; o.success = success; o.nfev = nfev; o.info = info;
+  return ia3_fit_run(f, 1, delta_center, 0.0, 0.0, 0, &o);
 }
 
 int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active, float* ps, double* p_raw,
@@ -1085,15 +1137,41 @@ int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active,
   if (ensure_device()) return -1;
   if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
   cudaStream_t st = f->s->stream;
-  f->d.fp.delta = delta_center;
-  std::vector<int> bounds;
-  if (build_work(f, active, bounds)) return -1;
+  FitDev& d = f->d;
+  const size_t n = (size_t)f->n;
+  if (d.delta_repeat != delta_center && f->gsweep > 0) IA3_CUDA(cudaMemsetAsync(d.memo_valid, 0, std::max<size_t>(n, 1), st));
+  d.delta_repeat = delta_center;
+  d.th2 = -1.0;                        // the caller decides who is visited again
+  d.max_sweeps = 1 << 20;
+  if (n) {
+    // fin = !active (all seeds if active == NULL); the previous call ended with a synchronisation
+    if (reserve_pinned(&f->h_up, &f->up_cap, n)) return -1;
+    uint8_t* h = static_cast<uint8_t*>(f->h_up);
+    for (size_t i = 0; i < n; ++i) h[i] = (active && !active[i]) ? 1 : 0;
+    if (small_copy(d.fin, h, n, st)) return -1;
+  }
+  f->gsweep += 1;
   IA3_CUDA(cudaEventRecord(f->e0, st));
-  for (int l = 0; l < f->n_levels; ++l)
-    if (run_fit_launch(f, 1, f->d_work + bounds[l], bounds[l + 1] - bounds[l])) return -1;
+  if (engine_run(f, 2, f->gsweep)) return -1;
   IA3_CUDA(cudaEventRecord(f->e1, st));
-  if (fetch_results(f, ps, p_raw, success, nfev, info)) return -1;
+  ia3_fit_out o;
+  memset(&o, 0, sizeof(o));
+  o.ps = ps; o.p_raw = p_raw; o.success = success; o.nfev = nfev; o.info = info;
+  if (fetch_results(f, &o)) return -1;
   cudaEventElapsedTime(&f->last_ms, f->e0, f->e1);
+  return 0;
+}
+
+int ia3_fit_engine_stats(ia3_fit* f, int64_t* out, int cap) {
+  if (ensure_device()) return -1;
+  if (!f || !out) { set_error("null argument"); return -1; }
+  cudaStream_t st = f->s->stream;
+  if (small_copy(f->h_ctl(), f->d.ctl, sizeof(EngineCtl), st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  const EngineCtl& c = *f->h_ctl();
+  const int64_t v[10] = {c.st_rounds, c.st_tasks, c.st_lm_runs, (int64_t)c.st_evals, c.st_memo_hits, c.st_spec_runs, c.st_spec_hits,
+                         c.st_parked, c.st_team_tasks, c.n_bricks};
+  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
   return 0;
 }
 
@@ -1102,24 +1180,37 @@ int ia3_fit_get_volume(ia3_fit* f, int which, double* out) {
   if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
   if (!f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   cudaStream_t st = f->s->stream;
+  Scoped sc;
   double* tmp = nullptr;
-  if (dev_alloc((void**)&tmp, f->s->nvox * 8)) return -1;
+  if (sc.dalloc(&tmp, f->s->nvox * 8)) return -1;
   if (launch_to_f64(f->s->d_im, f->s->dtype, tmp, (long long)f->s->nvox, st)) return -1;
+  const size_t nn = (size_t)std::max<int64_t>(f->n, 1);
   if (which == 0) {
-    if (launch_window_copy(f->d, f->d_snap, tmp, 1, st)) return -1;
+    // im_subtr: the image minus firstfit's reconstructions, subtracted in seed order where windows
+    // overlap (replayed from firstfit's parameters; passes = dependency depth)
+    uint8_t* done = nullptr; int* pending = nullptr; void* hp = nullptr;
+    if (sc.dalloc(&done, 2 * nn) || sc.dalloc(&pending, 256) || sc.halloc(&hp, 256)) return -1;
+    IA3_CUDA(cudaMemsetAsync(done, 0, 2 * nn, st));
+    for (int pass = 0;; ++pass) {
+      if (pass > f->n + 1) { set_error("im_subtr: dependency replay did not finish"); return -1; }
+      IA3_CUDA(cudaMemsetAsync(pending, 0, sizeof(int), st));
+      uint8_t* a = done + (size_t)(pass & 1) * nn;
+      uint8_t* b = done + (size_t)((pass & 1) ^ 1) * nn;
+      if (launch_subtract_dense(f->d, tmp, a, b, pending, st)) return -1;
+      if (small_copy(hp, pending, sizeof(int), st)) return -1;
+      IA3_CUDA(cudaStreamSynchronize(st));
+      if (*static_cast<int*>(hp) == 0) break;
+    }
   } else {
     // im_add: current work volume on the window voxels
-    double* snap2 = nullptr;
-    if (dev_alloc((void**)&snap2, (size_t)std::max<int64_t>(f->n, 1) * f->d.K * 8)) return -1;
-    if (launch_window_copy(f->d, snap2, nullptr, 0, st)) return -1;
-    if (launch_window_copy(f->d, snap2, tmp, 1, st)) return -1;
-    IA3_CUDA(cudaStreamSynchronize(st));
-    dev_free(snap2);
+    double* snap = nullptr;
+    if (sc.dalloc(&snap, nn * f->d.K * 8)) return -1;
+    if (launch_window_copy(f->d, snap, nullptr, 0, st)) return -1;
+    if (launch_window_copy(f->d, snap, tmp, 1, st)) return -1;
   }
   IA3_DRAIN(st);
   IA3_CUDA(cudaMemcpyAsync(out, tmp, f->s->nvox * 8, cudaMemcpyDeviceToHost, st));
   IA3_CUDA(cudaStreamSynchronize(st));
-  dev_free(tmp);
   return 0;
 }
 
@@ -1128,7 +1219,8 @@ int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* c
   if (!f || i < 0 || i >= f->n) { set_error("bad seed index"); return -1; }
   const int K = f->d.K;
   std::vector<double> full(K);
-  IA3_CUDA(cudaMemcpyAsync(full.data(), f->d_rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost, f->s->stream));
+  IA3_CUDA(cudaStreamSynchronize(f->s->stream));
+  IA3_CUDA(cudaMemcpyAsync(full.data(), f->d.rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost, f->s->stream));
   IA3_CUDA(cudaStreamSynchronize(f->s->stream));
   int m = 0;
   for (int k = 0; k < K; ++k) {
@@ -1143,10 +1235,46 @@ int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* c
   return 0;
 }
 
-int ia3_fit_num_levels(ia3_fit* f) { return f ? f->n_levels : 0; }
+// depth of the dependency order (seed j is one level above every lower-index seed whose window
+// overlaps its own): how many seeds in a row the reference's in-order sweep forces apart
+int ia3_fit_num_levels(ia3_fit* f) {
+  if (!f) return 0;
+  if (f->n_levels >= 0) return f->n_levels;
+  if (f->n == 0) { f->n_levels = 0; return 0; }
+  if (ensure_device() || (!f->prepared && ia3_fit_first_prepare(f, nullptr))) return -1;
+  const size_t n = (size_t)f->n;
+  const size_t pool = (size_t)std::max(f->h_ctl()->pool_o, 1);
+  std::vector<int> ds(n), dc(n), di(pool);
+  cudaStream_t st = f->s->stream;
+  if (cudaStreamSynchronize(st) != cudaSuccess ||
+      cudaMemcpy(ds.data(), f->d.dep_start, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(dc.data(), f->d.dep_cnt, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(di.data(), f->d.dep_idx, pool * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("num_levels: copy failed"); return -1; }
+  std::vector<int> level(n, 0);
+  int nl = 0;
+  for (size_t i = 0; i < n; ++i) {
+    int lvl = 0;
+    for (int e = ds[i]; e < ds[i] + dc[i]; ++e) if (di[e] < (int)i) lvl = std::max(lvl, level[di[e]] + 1);
+    level[i] = lvl;
+    nl = std::max(nl, lvl + 1);
+  }
+  f->n_levels = nl;
+  return nl;
+}
 float ia3_fit_last_ms(ia3_fit* f) { return f ? f->last_ms : 0.f; }
 
 // ---- standalone GaussianFit -----------------------------------------------------------------
+}  // extern "C"
+
+// a pooled stream for the duration of a call (concurrent callers do not queue behind each other)
+struct ScopedStream {
+  cudaStream_t st = nullptr;
+  ~ScopedStream() { if (st) release_stream(st); }
+  int get() { return acquire_stream(&st); }
+};
+
+extern "C" {
+
 int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_problems, const int64_t* off,
                        const double* values, const float* coords, const double* centers, float* ps, double* p_raw,
                        uint8_t* success, int32_t* nfev, int32_t* info, double* rec) {
@@ -1154,21 +1282,39 @@ int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_pr
   if (!cfg || n_problems < 0 || (n_problems > 0 && (!off || !values || !coords || !centers))) { set_error("null argument"); return -1; }
   if (n_problems == 0) return 0;
   const int64_t total = off[n_problems];
-  cudaStream_t st;
-  if (global_stream(&st)) return -1;
+  ScopedStream ss;
+  if (ss.get()) return -1;
+  cudaStream_t st = ss.st;
+  Scoped sc;
   GenericFitDev d;
   memset(&d, 0, sizeof(d));
   long long* d_off; double* d_val; float* d_co; double* d_cen; double* d_tmp; double* d_rec = nullptr;
   float* d_ps; double* d_praw; uint8_t* d_s; int* d_nf; int* d_in;
   const size_t np_ = (size_t)n_problems, tt = (size_t)std::max<int64_t>(total, 1);
-  if (dev_alloc((void**)&d_off, (np_ + 1) * 8) || dev_alloc((void**)&d_val, tt * 8) || dev_alloc((void**)&d_co, tt * 12) ||
-      dev_alloc((void**)&d_cen, np_ * 24) || dev_alloc((void**)&d_tmp, tt * 8) || dev_alloc((void**)&d_ps, np_ * NOUT * 4) ||
-      dev_alloc((void**)&d_praw, np_ * NP * 8) || dev_alloc((void**)&d_s, np_) || dev_alloc((void**)&d_nf, np_ * 4) ||
-      dev_alloc((void**)&d_in, np_ * 4) || (rec && dev_alloc((void**)&d_rec, tt * 8))) return -1;
-  IA3_CUDA(cudaMemcpyAsync(d_off, off, (np_ + 1) * 8, cudaMemcpyHostToDevice, st));
-  IA3_CUDA(cudaMemcpyAsync(d_val, values, (size_t)total * 8, cudaMemcpyHostToDevice, st));
-  IA3_CUDA(cudaMemcpyAsync(d_co, coords, (size_t)total * 12, cudaMemcpyHostToDevice, st));
-  IA3_CUDA(cudaMemcpyAsync(d_cen, centers, np_ * 24, cudaMemcpyHostToDevice, st));
+  if (sc.dalloc(&d_off, (np_ + 1) * 8) || sc.dalloc(&d_val, tt * 8) || sc.dalloc(&d_co, tt * 12) ||
+      sc.dalloc(&d_cen, np_ * 24) || sc.dalloc(&d_tmp, tt * 8) || sc.dalloc(&d_ps, np_ * NOUT * 4) ||
+      sc.dalloc(&d_praw, np_ * NP * 8) || sc.dalloc(&d_s, np_) || sc.dalloc(&d_nf, np_ * 4) ||
+      sc.dalloc(&d_in, np_ * 4) || (rec && sc.dalloc(&d_rec, tt * 8))) return -1;
+  // inputs and outputs through one pinned arena (no pageable copy enters the driver)
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t in_sz[4] = {(np_ + 1) * 8, (size_t)total * 8, (size_t)total * 12, np_ * 24};
+  const void* in_src[4] = {off, values, coords, centers};
+  void* in_dst[4] = {d_off, d_val, d_co, d_cen};
+  const size_t out_sz[6] = {np_ * NOUT * 4, np_ * NP * 8, np_, np_ * 4, np_ * 4, (size_t)total * 8};
+  const void* out_src[6] = {d_ps, d_praw, d_s, d_nf, d_in, d_rec};
+  void* out_dst[6] = {ps, p_raw, success, nfev, info, rec};
+  size_t need = 0;
+  for (size_t b : in_sz) need += al(b);
+  for (size_t b : out_sz) need += al(b);
+  void* h = nullptr;
+  if (sc.halloc(&h, need)) return -1;
+  char* hp = static_cast<char*>(h);
+  size_t o = 0;
+  for (int i = 0; i < 4; ++i) {
+    memcpy(hp + o, in_src[i], in_sz[i]);
+    if (small_copy(in_dst[i], hp + o, in_sz[i], st)) return -1;
+    o += al(in_sz[i]);
+  }
   d.n = n_problems; d.off = d_off; d.values = d_val; d.coords = d_co; d.centers = d_cen; d.tmp = d_tmp;
   d.ps = d_ps; d.p_raw = d_praw; d.success = d_s; d.nfev = d_nf; d.info = d_in; d.rec = d_rec;
   d.fp.min_w2 = cfg->min_w * cfg->min_w; d.fp.max_w2 = cfg->max_w * cfg->max_w; d.fp.delta = delta_center;
@@ -1177,17 +1323,19 @@ int ia3_gaussfit_batch(const ia3_fit_cfg* cfg, double delta_center, int64_t n_pr
   d.lm.maxfev = cfg->maxfev > 0 ? cfg->maxfev : (cfg->personality == 4 ? 1000 : 1100);
   for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
   if (launch_generic_fit(d, st)) return -1;
-  IA3_DRAIN(st);
-  if (ps) IA3_CUDA(cudaMemcpyAsync(ps, d_ps, np_ * NOUT * 4, cudaMemcpyDeviceToHost, st));
-  if (p_raw) IA3_CUDA(cudaMemcpyAsync(p_raw, d_praw, np_ * NP * 8, cudaMemcpyDeviceToHost, st));
-  if (success) IA3_CUDA(cudaMemcpyAsync(success, d_s, np_, cudaMemcpyDeviceToHost, st));
-  if (nfev) IA3_CUDA(cudaMemcpyAsync(nfev, d_nf, np_ * 4, cudaMemcpyDeviceToHost, st));
-  if (info) IA3_CUDA(cudaMemcpyAsync(info, d_in, np_ * 4, cudaMemcpyDeviceToHost, st));
-  if (rec) IA3_CUDA(cudaMemcpyAsync(rec, d_rec, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+  size_t oo[6];
+  for (int i = 0; i < 6; ++i) {
+    oo[i] = o;
+    if (out_dst[i] && small_copy(hp + o, out_src[i], out_sz[i], st)) return -1;
+    o += al(out_sz[i]);
+  }
   IA3_CUDA(cudaStreamSynchronize(st));
-  void* ptrs[] = {d_off, d_val, d_co, d_cen, d_tmp, d_rec, d_ps, d_praw, d_s, d_nf, d_in};
-  for (void* p : ptrs) dev_free(p);
+  for (int i = 0; i < 6; ++i) if (out_dst[i]) memcpy(out_dst[i], hp + oo[i], out_sz[i]);
   return 0;
+}
+
+static inline long long cell_key(long long a, long long b, long long c) {
+  return ((a + (1LL << 20)) << 42) | ((b + (1LL << 20)) << 21) | (c + (1LL << 20));
 }
 
 int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3_moment_cfg* cfg, double* out) {
@@ -1235,11 +1383,12 @@ int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   cudaStream_t st = s->stream;
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t b_cen = (size_t)n * 24, b_ns = (size_t)(n + 1) * 4, b_ni = std::max<size_t>(nbr_idx.size(), 1) * 4, b_off = offs.size(), b_out = (size_t)n * 96;
+  Scoped sc;
   void* h = nullptr;
-  if (host_alloc(&h, al(b_cen) + al(b_ns) + al(b_ni) + al(b_off) + al(b_out))) return -1;
+  if (sc.halloc(&h, al(b_cen) + al(b_ns) + al(b_ni) + al(b_off) + al(b_out))) return -1;
   double* d_cen = nullptr; int* d_ns = nullptr; int* d_ni = nullptr; int8_t* d_off = nullptr; double* d_out = nullptr;
-  if (dev_alloc((void**)&d_cen, b_cen) || dev_alloc((void**)&d_ns, b_ns) || dev_alloc((void**)&d_ni, b_ni) ||
-      dev_alloc((void**)&d_off, b_off) || dev_alloc((void**)&d_out, b_out)) return -1;
+  if (sc.dalloc(&d_cen, b_cen) || sc.dalloc(&d_ns, b_ns) || sc.dalloc(&d_ni, b_ni) ||
+      sc.dalloc(&d_off, b_off) || sc.dalloc(&d_out, b_out)) return -1;
   char* hp = static_cast<char*>(h);
   size_t off = 0;
   auto put = [&](void* d, const void* src, size_t bytes) -> int {
@@ -1260,8 +1409,6 @@ int ia3_moment_fit(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   if (small_copy(ho, d_out, b_out, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   memcpy(out, ho, b_out);
-  host_free(h);
-  dev_free(d_cen); dev_free(d_ns); dev_free(d_ni); dev_free(d_off); dev_free(d_out);
   return 0;
 }
 
@@ -1274,19 +1421,21 @@ int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_
   memset(&fp, 0, sizeof(fp));
   fp.min_w2 = cfg->min_w * cfg->min_w; fp.max_w2 = cfg->max_w * cfg->max_w; fp.delta = delta_center;
   fp.weight_sigma = 0.0; fp.personality = cfg->personality;
-  cudaStream_t st;
-  if (global_stream(&st)) return -1;
+  ScopedStream ss;
+  if (ss.get()) return -1;
+  cudaStream_t st = ss.st;
+  Scoped sc;
   double* d_p; double* d_c; float* d_co; double* d_out;
-  if (dev_alloc((void**)&d_p, 80) || dev_alloc((void**)&d_c, 24) || dev_alloc((void**)&d_co, (size_t)m * 12) ||
-      dev_alloc((void**)&d_out, (size_t)m * 8)) return -1;
-  IA3_CUDA(cudaMemcpyAsync(d_p, p_raw, 80, cudaMemcpyHostToDevice, st));
-  IA3_CUDA(cudaMemcpyAsync(d_c, center, 24, cudaMemcpyHostToDevice, st));
-  IA3_CUDA(cudaMemcpyAsync(d_co, coords, (size_t)m * 12, cudaMemcpyHostToDevice, st));
+  void* h = nullptr;
+  const size_t b_co = (size_t)m * 12, b_out = (size_t)m * 8, o_co = 512, o_out = o_co + (b_co + 255) / 256 * 256;
+  if (sc.dalloc(&d_p, 80) || sc.dalloc(&d_c, 24) || sc.dalloc(&d_co, b_co) || sc.dalloc(&d_out, b_out) || sc.halloc(&h, o_out + b_out)) return -1;
+  char* hp = static_cast<char*>(h);
+  memcpy(hp, p_raw, 80); memcpy(hp + 256, center, 24); memcpy(hp + o_co, coords, b_co);
+  if (small_copy(d_p, hp, 80, st) || small_copy(d_c, hp + 256, 24, st) || small_copy(d_co, hp + o_co, b_co, st)) return -1;
   if (launch_eval_f0(fp, d_p, d_c, d_co, m, d_out, st)) return -1;
-  IA3_DRAIN(st);
-  IA3_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  if (small_copy(hp + o_out, d_out, b_out, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
-  dev_free(d_p); dev_free(d_c); dev_free(d_co); dev_free(d_out);
+  memcpy(out, hp + o_out, b_out);
   return 0;
 }
 

@@ -213,57 +213,82 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // (T01) and 8-15 x 8-15 (T11) of the 16x16 padded product.  6 accumulator registers per lane instead
 // of 130, and the cross-lane reduction is part of the MMA.  Same products as the scalar path (float32
 // Jacobian entries widened to FP64), different summation order.
+// One batch of 32 voxels: the lanes stage [J | f] of their voxel in `gt`, then three 8x8 FP64 tensor-core
+// tiles accumulate G^T G over the batch's eight 4-voxel slices, STARTING FROM ZERO.  t[0..5] = this lane's
+// entries of T00 (rows/columns 0-7), T01 (0-7 x 8-15), T11 (8-15 x 8-15).  The running sums are formed
+// by adding whole batch tiles in batch order (pass_fused_mma below, pass_cta in fit_kernels.cu): the
+// result does not depend on how many warps share the batches of one spot.
+template <typename T, typename Vox>
+__device__ __forceinline__ void mma_batch_tile(const VoxConsts<T>& vc, const Vox& vox, int k0, int lane, double* gt, double (&t)[6],
+                                               int& nbad, double agiant) {
+  const int g = lane >> 2, q = lane & 3;
+  const int k = k0 + lane;
+  float J[NP];
+  double r = 0.0;
+  if (k < vox.m) {
+    T X0, X1, X2, d, res;
+    vox.get(k, X0, X1, X2, d);
+    eval_jac<T>(vc, X0, X1, X2, d, res, J);
+    r = (double)res;
+    if (!(fabs(r) < agiant)) nbad += 1;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) J[i] = 0.f;
+  }
+  __syncwarp();                                  // the previous batch's fragments have been read
+#pragma unroll
+  for (int i = 0; i < NP; ++i) gt[i * GRAM_PITCH + lane] = (double)J[i];
+  gt[NP * GRAM_PITCH + lane] = r;
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < 6; ++e) t[e] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const double f0 = gt[g * GRAM_PITCH + 4 * c + q];                           // column g, voxel 4c + q of the batch
+    const double f1 = (g < 3) ? gt[(8 + g) * GRAM_PITCH + 4 * c + q] : 0.0;     // columns 8, 9 and f; 11-15 are padding
+    dmma884(t[0], t[1], f0, f0);
+    dmma884(t[2], t[3], f0, f1);
+    dmma884(t[4], t[5], f1, f1);
+  }
+}
+
+// scatter the upper triangle / the J^T f column of the three accumulated tiles to the packed layout
+// lm_factor reads; returns (f, f) = |f|^2 on every lane
+__device__ __forceinline__ double mma_scatter(const double (&a)[6], int lane, double* Ag_out) {
+  static_assert(NP == 10, "tile bookkeeping below assumes 10 parameters + the residual column");
+  const int g = lane >> 2, q = lane & 3;
+  const int j0 = 2 * q, j1 = j0 + 1;
+  if (g <= j0) Ag_out[tri(g, j0)] = a[0];
+  if (g <= j1) Ag_out[tri(g, j1)] = a[1];
+  const int ja = 8 + j0, jb = ja + 1;
+  if (ja < NP) Ag_out[tri(g, ja)] = a[2]; else if (ja == NP) Ag_out[NTRI + g] = a[2];
+  if (jb < NP) Ag_out[tri(g, jb)] = a[3]; else if (jb == NP) Ag_out[NTRI + g] = a[3];
+  const int i = 8 + g;
+  if (i < NP) {
+    if (ja < NP) { if (i <= ja) Ag_out[tri(i, ja)] = a[4]; } else if (ja == NP) Ag_out[NTRI + i] = a[4];
+    if (jb < NP) { if (i <= jb) Ag_out[tri(i, jb)] = a[5]; } else if (jb == NP) Ag_out[NTRI + i] = a[5];
+  }
+  return __shfl_sync(0xffffffffu, a[4], 9);      // (f, f): lane 9 = row 8 + 2, column 8 + 2
+}
+
+// pass_fused on one warp: the normal-equation sums as G^T G with G = [J | f] (m x 11).  The 65 sums
+// used to be 65 FP64 accumulators per lane plus a 65-entry butterfly reduction; here three 8x8 FP64
+// tensor-core tiles hold them (6 accumulator registers per lane) and the cross-lane reduction is part of
+// the MMA.  Same products as the scalar path (float32 Jacobian entries widened to FP64), different
+// summation order.
 template <typename T, typename Exec, typename Vox>
 __device__ __forceinline__ double pass_fused_mma(Exec& ex, const VoxConsts<T>& vc, const Vox& vox, double* Ag_out, double* gt) {
-  static_assert(NP == 10, "tile bookkeeping below assumes 10 parameters + the residual column");
   const double agiant = 1.304e19 / (double)vox.m;
   const int lane = ex.lane();
-  const int g = lane >> 2, q = lane & 3;
-  double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c11a = 0.0, c11b = 0.0;
+  double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   int nbad = 0;
   for (int k0 = 0; k0 < vox.m; k0 += 32) {
-    const int k = k0 + lane;
-    float J[NP];
-    double r = 0.0;
-    if (k < vox.m) {
-      T X0, X1, X2, d, res;
-      vox.get(k, X0, X1, X2, d);
-      eval_jac<T>(vc, X0, X1, X2, d, res, J);
-      r = (double)res;
-      if (!(fabs(r) < agiant)) nbad += 1;
-    } else {
+    double t[6];
+    mma_batch_tile<T>(vc, vox, k0, lane, gt, t, nbad, agiant);
 #pragma unroll
-      for (int i = 0; i < NP; ++i) J[i] = 0.f;
-    }
-    ex.sync();                                   // the previous batch's fragments have been read
-#pragma unroll
-    for (int i = 0; i < NP; ++i) gt[i * GRAM_PITCH + lane] = (double)J[i];
-    gt[NP * GRAM_PITCH + lane] = r;
-    ex.sync();
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const double f0 = gt[g * GRAM_PITCH + 4 * c + q];                           // column g, voxel 4c + q of the batch
-      const double f1 = (g < 3) ? gt[(8 + g) * GRAM_PITCH + 4 * c + q] : 0.0;     // columns 8, 9 and f; 11-15 are padding
-      dmma884(c00a, c00b, f0, f0);
-      dmma884(c01a, c01b, f0, f1);
-      dmma884(c11a, c11b, f1, f1);
-    }
+    for (int e = 0; e < 6; ++e) acc[e] += t[e];
   }
-  // scatter the upper triangle / the J^T f column to the packed layout lm_factor reads
-  {
-    const int j0 = 2 * q, j1 = j0 + 1;
-    if (g <= j0) Ag_out[tri(g, j0)] = c00a;
-    if (g <= j1) Ag_out[tri(g, j1)] = c00b;
-    const int ja = 8 + j0, jb = ja + 1;
-    if (ja < NP) Ag_out[tri(g, ja)] = c01a; else if (ja == NP) Ag_out[NTRI + g] = c01a;
-    if (jb < NP) Ag_out[tri(g, jb)] = c01b; else if (jb == NP) Ag_out[NTRI + g] = c01b;
-    const int i = 8 + g;
-    if (i < NP) {
-      if (ja < NP) { if (i <= ja) Ag_out[tri(i, ja)] = c11a; } else if (ja == NP) Ag_out[NTRI + i] = c11a;
-      if (jb < NP) { if (i <= jb) Ag_out[tri(i, jb)] = c11b; } else if (jb == NP) Ag_out[NTRI + i] = c11b;
-    }
-  }
-  const double s2 = ex.bcast(c11a, 9);           // (f, f): lane 9 = row 8 + 2, column 8 + 2
+  const double s2 = mma_scatter(acc, lane, Ag_out);
   nbad = ex.allsum_int(nbad);
   if (nbad == 0) return sqrt(s2);
   return pass_residual<T>(ex, vc, vox, (double*)0);
@@ -325,11 +350,29 @@ IA3_HD void build_consts_par(Exec& ex, const FitParams& fp, const double* cen_es
 }
 
 // Everything that is live at the top of lmder's outer loop: a run can be suspended there and resumed
-// later (by another kernel launch) without changing a single bit of its trajectory.
-struct LMPause {
-  LMState st;
+// later (by another kernel launch, by another number of warps) without changing a single bit of its
+// trajectory.  lm_outer recomputes the factorisation (R, ipvt, acn, qtf, B0, rq ...) from the sums, so
+// only the iterate, the scaling, four scalars, the counters and the sums themselves are kept: 728 bytes.
+struct LMLive {
+  double x[NP], diag[NP];
   double Ag[NTRI + NP];
+  double fnorm, xnorm, delta, par;
+  int iter, nfev, njev, info;
 };
+// i-th 8-byte word of the live state, read from (st, Ag) / written back to them
+constexpr int LMLIVE_WORDS = (int)(sizeof(LMLive) / 8);
+IA3_HD void lm_live_save(const LMState& st, const double* Ag, LMLive& out) {
+  for (int i = 0; i < NP; ++i) { out.x[i] = st.x[i]; out.diag[i] = st.diag[i]; }
+  for (int i = 0; i < NTRI + NP; ++i) out.Ag[i] = Ag[i];
+  out.fnorm = st.fnorm; out.xnorm = st.xnorm; out.delta = st.delta; out.par = st.par;
+  out.iter = st.iter; out.nfev = st.nfev; out.njev = st.njev; out.info = st.info;
+}
+IA3_HD void lm_live_restore(const LMLive& in, LMState& st, double* Ag) {
+  for (int i = 0; i < NP; ++i) { st.x[i] = in.x[i]; st.diag[i] = in.diag[i]; }
+  for (int i = 0; i < NTRI + NP; ++i) Ag[i] = in.Ag[i];
+  st.fnorm = in.fnorm; st.xnorm = in.xnorm; st.delta = in.delta; st.par = in.par;
+  st.iter = in.iter; st.nfev = in.nfev; st.njev = in.njev; st.info = in.info;
+}
 enum { LM_START_FRESH = 0, LM_START_CONTINUE = 1 };
 
 // Runs leastsq from sh.x0 (LM_START_FRESH) or continues the run whose state is in sh.st / sh.Ag

@@ -252,12 +252,14 @@ def _fit_fov_image(im, channel, seeds=None,
                   fitting_args={},
                   remove_boundary_points=True, verbose=True, _stack=None, _front_done=None):
     """spot_tools/fitting.py:169-262.  `_stack` (not in the reference): a `_lib.Stack` that already holds
-    `im` in HBM; `_front_done`: called once the image is no longer needed on the device."""
+    `im` in HBM -- it keeps its image (only the seed stage's scratch volumes are handed back); `_front_done`:
+    called once the image is no longer needed on the device."""
     th_seed = float(th_seed)
     if verbose:
         print(f"-- start fitting spots in channel:{channel}, ", end='')
         t0 = time.time()
     stack = _stack
+    own_stack = _stack is None
     if stack is None and isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype in (np.uint16, np.float32):
         stack = _lib.Stack(im)     # one upload shared by the seed and the fit stage
     if seeds is None:
@@ -273,7 +275,7 @@ def _fit_fov_image(im, channel, seeds=None,
                                _stack=stack if 'sel_center' not in seeding_kwargs else None,
                                **seeding_kwargs)
             if stack is not None:
-                stack.trim(1)          # the seed stage's work volumes go back to the other stacks in flight
+                stack.trim(1)          # the seed stage's scratch volumes go back to the other stacks in flight (never the image)
         if verbose:
             print(f"{len(_seeds)} seeded with th={th_seed}, ", end='')
     else:
@@ -290,13 +292,12 @@ def _fit_fov_image(im, channel, seeds=None,
             print(f"{len(_seeds)} selected by mask, ", end='')
 
     fitter = Fitting_v4.iter_fit_seed_points(im, _seeds.T, radius_fit=fit_radius, _stack=stack, **fitting_args)
-    fitter.firstfit()
+    fitter._fit_all()          # firstfit() + repeatfit() as one device run
     _need_image = normalize_local or normalize_background
-    if stack is not None and not _need_image:
-        stack.trim(2)          # repeatfit only touches the sparse work volume, not the image
+    if stack is not None and own_stack and not _need_image:
+        stack.trim(2)          # only a stack created here: a caller's stack keeps its image for the caller's next call
     if _front_done is not None:
         _front_done()
-    fitter.repeatfit()
     _spots = fitter._ps_array()                 # == np.array(fitter.ps)
     _spots = _spots[np.sum(np.isnan(_spots), axis=1) == 0]
     if remove_boundary_points:
@@ -340,8 +341,7 @@ def get_centers(im, seeds=None, th_seed=150,
                           return_h=False, verbose=verbose,
                           **seed_kwargs)
     fitter = Fitting_v4.iter_fit_seed_points(im, seeds.T, radius_fit=fit_radius)
-    fitter.firstfit()
-    fitter.repeatfit()
+    fitter._fit_all()                           # firstfit() + repeatfit()
     pfits = fitter._ps_array()                  # == np.array(fitter.ps)
     if len(pfits) > 0:
         centers = pfits[:, 1:4]

@@ -42,8 +42,9 @@ int ia3_timer_start(void);
 int ia3_timer_stop(float* ms);
 
 /* ---- stacks ---------------------------------------------------------------------------- */
-/* Upload a host stack (pageable or pinned) -- one H2D copy per stack; seed and fit stages then
- * share the resident copy.  Replaces the implicit "im" argument of get_seeds / fit_fov_image /
+/* Upload a host stack -- one H2D pass per stack; seed and fit stages then share the resident copy.
+ * Pinned memory goes to the copy engine directly; pageable memory (a plain numpy array, what the
+ * reference's callers hold) is staged through pinned chunks by a few worker threads.  Replaces the implicit "im" argument of get_seeds / fit_fov_image /
  * iter_fit_seed_points (spot_tools/fitting.py:20,169; External/Fitting_v4.py:560). */
 int ia3_stack_create(const void* im, int dtype, int Z, int X, int Y, ia3_stack** out);
 /* Wrap a stack that is already in device memory (no copy, not owned). */
@@ -86,6 +87,9 @@ int ia3_seed_fetch(ia3_stack* s, int32_t* zxy, float* h, int64_t cap);
 /* Debug/parity taps: copy an intermediate volume back (which: 0 = foreground blur,
  * 1 = background blur), same dtype as the stack. */
 int ia3_seed_fetch_volume(ia3_stack* s, int which, void* out);
+/* Values of such a volume at n voxels given as flat C-order indices (External/Fitting_v3.py:276-283
+ * reads its two blurs at the candidate voxels only); out: n values of the stack's dtype. */
+int ia3_seed_gather_volume(ia3_stack* s, int which, const int64_t* flat_idx, int64_t n, void* out);
 
 /* ---- local background (fit_fov_image's normalize_local / normalize_background) ------------ */
 /* find_image_background (io_tools/load.py:642-686) for n boxes of a uint16 stack: mode of the
@@ -104,7 +108,7 @@ typedef struct {
   double init_w[3];     /* v4: scalar init_w replicated; v3: per-axis init_w (_sigma_zxy) */
   double weight_sigma;  /* v3 width prior (0 = off) */
   int maxfev;           /* 1000 (v4, Fitting_v4.py:388) / 1100 (v3, leastsq default) */
-  int eval_fp32;        /* 0: per-voxel model in FP64 (reference precision); 1: FP32 fast mode */
+  int eval_fp32;        /* reserved, must be 0 (the model is evaluated in FP64, the reference's precision) */
 } ia3_fit_cfg;
 
 /* iter_fit_seed_points.__init__ (Fitting_v4.py:560-588 / Fitting_v3.py:313-335):
@@ -119,24 +123,42 @@ int ia3_fit_destroy(ia3_fit* f);
 int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties);
 int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap);
 int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n);
-/* firstfit, step 2: all fits in one launch + ordered subtraction of the reconstructions
+/* firstfit / repeatfit on the device, without a host round trip per sweep (Fitting_v4.py:590-683,
+ * Fitting_v3.py:337-421).  phases: 1 = firstfit, 2 = repeatfit (firstfit must have run), 3 = both in one
+ * go.  The per-seed rule of the reference's loop is evaluated where a seed's visit ends: a seed is
+ * visited in sweep k+1 iff sum((centre_k - centre_{k-1})^2) >= max_dist_th2 (in the dtype
+ * np.array(centers_fit) has in the reference), and at most n_max_iter + 1 sweeps are made; a visit
+ * starts as soon as the visits the reference orders before it, and whose output it reads, are done.
+ * Outputs (each pointer may be NULL): final rows of ps / p_raw / success / nfev / info; converged and
+ * dists as after the last sweep; n_visits = sweeps in which the seed was visited (n_iter is their
+ * maximum); success_old / centers_old = the seed's success flag / centre before its last visit. */
+typedef struct {
+  float* ps; double* p_raw; uint8_t* success; int32_t* nfev; int32_t* info;   /* n x 11, n x 10, n, n, n */
+  uint8_t* converged; double* dists; int32_t* n_visits;                       /* n each */
+  uint8_t* success_old; float* centers_old;                                   /* n, n x 3 */
+} ia3_fit_out;
+int ia3_fit_run(ia3_fit* f, int phases, double min_delta_center, double max_delta_center, double max_dist_th2,
+                int n_max_iter, const ia3_fit_out* out);
+/* firstfit alone (= ia3_fit_run(phases = 1)): all fits + ordered subtraction of the reconstructions
  * (Fitting_v4.py:606-639).  Outputs (each may be NULL): ps n x 11 float32 (NaN rows on
  * failure), p_raw n x 10 float64, success n, nfev n, info n. */
 int ia3_fit_first_run(ia3_fit* f, double delta_center, float* ps, double* p_raw, uint8_t* success,
                       int32_t* nfev, int32_t* info);
-/* one sweep of repeatfit over the seeds with active[i] != 0, in seed order (dependency levels
- * keep the reference's sequential Gauss-Seidel semantics, Fitting_v4.py:651-675).  Only rows of
- * active seeds are written. */
+/* ONE sweep of repeatfit over the seeds with active[i] != 0, in seed order, for callers that run the
+ * reference's loop themselves (Fitting_v4.py:651-675).  Only rows of active seeds change. */
 int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active, float* ps, double* p_raw,
                          uint8_t* success, int32_t* nfev, int32_t* info);
-/* lazily materialised attributes: which = 0 -> im_subtr snapshot taken after firstfit (only if
- * requested before repeatfit), 1 -> im_add; float64 volume of the stack's shape. */
+/* counters of the fit engine since ia3_fit_create: rounds, tasks, lmder runs, function evaluations, memo
+ * hits, speculative runs, speculative runs adopted, suspensions, team continuations, bricks */
+int ia3_fit_engine_stats(ia3_fit* f, int64_t* out, int cap);
+/* lazily materialised attributes: which = 0 -> im_subtr (rebuilt from firstfit's parameters), 1 -> im_add
+ * (current work volume); float64 volume of the stack's shape. */
 int ia3_fit_get_volume(ia3_fit* f, int which, double* out);
 /* ims_rec[i]: reconstruction over the clipped window of seed i (float64, <= K values);
  * also returns the window voxel coordinates (count x 3 int32) if zxy != NULL. */
 int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* count);
 int ia3_fit_num_levels(ia3_fit* f);
-float ia3_fit_last_ms(ia3_fit* f);        /* device time of the last first_run / repeat_sweep */
+float ia3_fit_last_ms(ia3_fit* f);        /* device time of the last ia3_fit_run / first_run / repeat_sweep */
 
 /* ---- standalone GaussianFit ------------------------------------------------------------ */
 /* A batch of independent GaussianFit(im, X, center, ...).fit() calls (Fitting_v4.py:165-396,

@@ -66,18 +66,16 @@ static int run(int personality, const double* values, const int* coords, int m, 
   bool suspended = run_lm<T>(ex, fp, cfg, cen, origin, vox, sh, cap, LM_START_FRESH);
   int rounds = 0;
   while (suspended) {
-    // what the device does between two launches (fit_kernels.cu: fit_one): park LMState + the normal
-    // equation sums, forget everything else, rebuild the prologue, continue
-    static LMPause park;
-    park.st = sh.st;
-    memcpy(park.Ag, sh.Ag, sizeof(park.Ag));
+    // what the device does between two launches (fit_kernels.cu: fit_one): park the live part of LMState + the normal
+    // equation sums (LMLive), forget everything else, rebuild the prologue, continue
+    static LMLive park;
+    lm_live_save(sh.st, sh.Ag, park);
     memset(static_cast<void*>(&sh), 0xA5, sizeof(sh));
     fp = fp_in;
     select10(ex, values, m, false, sh.small10);
     select10(ex, values, m, true, sh.large10);
     initial_guess(fp, sh.small10, sh.large10, init_w, sh.x0);
-    sh.st = park.st;
-    memcpy(sh.Ag, park.Ag, sizeof(park.Ag));
+    lm_live_restore(park, sh.st, sh.Ag);
     suspended = run_lm<T>(ex, fp, cfg, cen, origin, vox, sh, cap, LM_START_CONTINUE);
     ++rounds;
   }
