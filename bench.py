@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- spot-finding hot path (seed + firstfit + repeatfit) on B200.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W [--config C2]          # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...              # the reference's CPU path (oracle port)
 
-One "step" = fit_fov_image over one synthetic FOV stack (BASELINE.json configs[1]: 50 x 2048 x
-2048 uint16, 5000 planted spots, th_seed=300, max_num_seeds=None).  Steps are independent stacks, as in
-the reference's mp.Pool over (round, channel) images (classes/field_of_view.py:1129); --inflight D of them
-are in flight at once per GPU (D host threads, one CUDA stream per stack), so the copy of one stack
-overlaps the seed kernels of the next and the long tail of a third one's fit sweeps.  Prints ONE JSON
-line on rank 0.
-  value      spots fitted per second, stack already resident in HBM when the timed region starts
-  e2e        same metric through the public API (fit_fov_image on a pinned host stack): the H2D copy
-             of the stack and the D2H reads of candidates / results are inside the timed region
-  roofline   the seed stage's dominant kernel, one 61-tap exact Gaussian axis pass (k_gauss_strided<30>),
-             against the measured HBM copy peak; roofline_fit = the fit stage against the FP pipes
+One "step" = fit_fov_image over one synthetic FOV stack of the chosen BASELINE.json config (default C2 =
+configs[1]: 50 x 2048 x 2048 uint16, 5000 planted spots, th_seed=300, max_num_seeds=None).  Steps are
+independent stacks, as in the reference's mp.Pool over (round, channel) images
+(classes/field_of_view.py:1129); --inflight D of them are in flight at once per GPU (D host threads, one
+CUDA stream per stack).  Prints ONE JSON line on rank 0.
+  value         spots fitted per second, stack already resident in HBM when the timed region starts
+  e2e           same metric through the public API (fit_fov_image on a PINNED host stack): the H2D copy of
+                the stack and the D2H reads of candidates / results are inside the timed region
+  e2e_pageable  same, the stack being a plain (pageable) numpy array, as the reference's callers hold it
+  roofline      the seed stage against the measured HBM copy peak with SURVEY 8(d)'s algorithmic bytes
+                (2 B/voxel + 16 B/candidate) over the stage's device time; pass_frac = its dominant kernel
+                (one 61-tap axis pass, 4 B/voxel); roofline_fit = the fit stage against the FP pipes
   cpu_baseline  the oracle port (same scipy calls as the reference) on a bounded sample, 1 core
+  parity        this run's GPU result on a crop of the workload against the oracle (rows, comparable, max dev)
 Multi-GPU: one process per GPU (torchrun), every rank processes its own stacks (weak scaling), no
 data-path collective; the barrier / max-over-ranks reduction uses torch.distributed (NCCL).
 """
@@ -31,25 +33,42 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# one hardware queue per in-flight stack (the default 8 makes streams share queues, and a stack's long
-# fit tail then blocks unrelated stacks); must be set before the CUDA context exists
+# one hardware queue per in-flight stack (the default 8 makes streams share queues); must be set
+# before the CUDA context exists
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-SHAPE = (50, 2048, 2048)
-N_PLANTED = 5000
-TH_SEED = 300.0
-FIT_KW = dict(th_seed=TH_SEED, max_num_seeds=None, verbose=False)
-CPU_CROP = (50, 448, 448)      # bounded CPU sample: a crop of the same stack (same spot density)
+PROD_KW = dict(th_seed=600, max_num_seeds=4000, min_dynamic_seeds=50, remove_hot_pixel=True, normalize_local=True)
+PLAIN_KW = dict(th_seed=300.0, max_num_seeds=None)
+# BASELINE.json configs: shape, planted spots, height range, synth seed, fit_fov_image kwargs
+CONFIGS = {
+    "C1": dict(shape=(30, 512, 512), n=500, h=(600.0, 4000.0), seed=0, kw=PLAIN_KW,
+               text="C1: fit_fov_image(th_seed=300, max_num_seeds=None) on 30x512x512 uint16 stacks, 500 planted spots"),
+    "C2": dict(shape=(50, 2048, 2048), n=5000, h=(600.0, 4000.0), seed=1, kw=PLAIN_KW,
+               text="C2: fit_fov_image(th_seed=300, max_num_seeds=None) on one 50x2048x2048 uint16 FOV per step per GPU, "
+                    "5000 planted spots; seed stage + Fitting_v4 firstfit + repeatfit"),
+    "C3": dict(shape=(30, 2048, 2048), n=200, h=(600.0, 4000.0), seed=100, kw=PROD_KW,
+               text="C3: hybridization rounds of one FOV, 30x2048x2048 uint16, 200 planted spots per round, production kwargs "
+                    "fit_fov_image(th_seed=600, max_num_seeds=4000, min_dynamic_seeds=50, normalize_local=True)"),
+    "C4": dict(shape=(60, 2048, 2048), n=50000, h=(400.0, 3000.0), seed=4, kw=PLAIN_KW,
+               text="C4: dense RNA-FISH FOV 60x2048x2048 uint16, 50000 planted spots, fit_fov_image(th_seed=300, max_num_seeds=None) "
+                    "incl. Fitting_v4 neighbour-subtracted repeatfit"),
+    "C5": dict(shape=(30, 2048, 2048), n=2000, h=(600.0, 4000.0), seed=1000, kw=PROD_KW,
+               text="C5: experiment batch, 30x2048x2048 uint16 stacks, 2000 planted spots each, production kwargs "
+                    "fit_fov_image(th_seed=600, max_num_seeds=4000, min_dynamic_seeds=50, normalize_local=True)"),
+}
+CPU_CROP_XY = 448      # bounded CPU sample: a crop of the same stack (same spot density), full depth
 
 
 def _traffic():
     """dram__bytes_read + dram__bytes_write of the 61-tap pass from the committed ncu capture (per launch)"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            t = json.load(fh)["k_gauss_61tap_pass"]
-        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                t = json.load(fh)["k_gauss_61tap_pass"]
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+        except Exception:
+            continue
+    return None
 
 
 def _peaks():
@@ -94,57 +113,78 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def _dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+def _dist_setup():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _crop_shape(cfg, edge=CPU_CROP_XY):
+    Z, X, Y = cfg["shape"]
+    return (Z, min(edge, X), min(edge, Y))
+
+
+def _crop_planted(cfg, crop):
+    return max(4, int(round(cfg["n"] * np.prod(crop) / np.prod(cfg["shape"]))))
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(im_crop):
-    """The reference's CPU path (oracle port: same scipy/numpy calls) on one crop -> (#spots, seconds)."""
+def cpu_sample(im_crop, kw):
+    """The reference's CPU path (oracle port: same scipy/numpy calls) on one crop -> (spots, seconds)."""
     from oracle import fit_oracle
     t0 = time.perf_counter()
-    spots, seeds = fit_oracle.fit_fov_image_oracle(im_crop, th_seed=TH_SEED, max_num_seeds=None)
-    return len(spots), time.perf_counter() - t0
+    spots, seeds = fit_oracle.fit_fov_image_oracle(im_crop, **kw)
+    return spots, time.perf_counter() - t0
 
 
 def _cpu_worker(args):
-    seed, crop = args
+    seed, crop, n, h, kw = args
     from imageanalysis3_b200.synth import synth
-    n = max(4, int(round(N_PLANTED * np.prod(crop) / np.prod(SHAPE))))
-    im = synth(crop, n, seed)
-    return cpu_sample(im)
+    im = synth(crop, n, seed, h_range=h)
+    spots, dt = cpu_sample(im, kw)
+    return len(spots), dt
 
 
-def _reference_crop(steps, warmup, budget_s=150.0):
-    """Crop of the C2 stack (same spot density) one worker handles per step, sized so that the whole
-    --steps K --warmup W run takes about ``budget_s``: a 50x448x448 crop costs ~3 s with the pool busy."""
+def _reference_crop(cfg, steps, warmup, budget_s=150.0):
+    """Crop of the workload's stack (same spot density) one worker handles per step, sized so that the whole
+    --steps K --warmup W run takes about ``budget_s``: a 50x448x448 C2 crop costs ~3 s with the pool busy."""
     per_step = budget_s / max(1, steps + warmup)
-    edge = 448.0 * min(1.0, per_step / 3.0) ** 0.5
+    cost448 = 3.0 * (cfg["shape"][0] / 50.0) * max(1.0, cfg["n"] / np.prod(cfg["shape"]) / (5000 / (50 * 2048 * 2048.0)))
+    edge = 448.0 * min(1.0, per_step / cost448) ** 0.5
     edge = int(max(96, min(448, round(edge / 32.0) * 32)))
-    return (SHAPE[0], edge, edge)
+    return _crop_shape(cfg, edge)
 
 
 def run_reference(args):
-    rank, world, local = _dist_setup(args.gpus)
+    rank, world, local = _dist_setup()
     if rank != 0:
         return
     import multiprocessing as mp
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
     ctx = mp.get_context("fork")
-    crop = _reference_crop(args.steps, args.warmup)
+    crop = _reference_crop(cfg, args.steps, args.warmup)
+    n_crop = _crop_planted(cfg, crop)
     times, spots = [], []
+    full = None
     with ctx.Pool(procs) as pool:
+        # ONE worker also runs the workload's full-size stack once (C1 / C2 only: minutes beyond that), to pin the
+        # extrapolation from crops: its spots/s on one core is reported next to the crops' per-core rate
+        full_job = None
+        if args.full_check and args.config in ("C1", "C2"):
+            full_job = pool.apply_async(_cpu_worker, ((cfg["seed"], cfg["shape"], cfg["n"], cfg["h"], cfg["kw"]),))
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(1000 + it * procs + i, crop) for i in range(procs)], chunksize=1)
+            res = pool.map(_cpu_worker, [(1000 + it * procs + i, crop, n_crop, cfg["h"], cfg["kw"]) for i in range(procs)], chunksize=1)
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)
                 spots.append(sum(r[0] for r in res))
+        if full_job is not None:
+            try:
+                n_full, t_full = full_job.get(timeout=240)
+                full = {"spots": n_full, "seconds": t_full, "spots_per_s_one_core": n_full / t_full}
+            except Exception as exc:      # noqa: BLE001
+                full = {"unfinished": type(exc).__name__}
     T = float(np.sum(times))
     value = float(np.sum(spots)) / T
     vox = float(np.prod(crop)) * procs * args.steps
@@ -152,11 +192,13 @@ def run_reference(args):
         "impl": "reference", "metric": "spots_fitted_per_s", "value": value, "unit": "spots/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "stacks_per_s": vox / float(np.prod(SHAPE)) / T,
-        "config": {"workload": "C2: fit_fov_image on 50x2048x2048 uint16 FOV, 5000 planted spots, th_seed=300 "
-                               "(reference CPU path timed on crops of that workload)"},
+        "stacks_per_s": vox / float(np.prod(cfg["shape"])) / T,
+        "config": {"workload": cfg["text"],
+                   "sample": f"reference CPU path timed on {crop[0]}x{crop[1]}x{crop[2]} crops of that workload (same spot density), "
+                             f"one crop per worker per step; per-core rate of the crops {value / procs:.1f} spots/s",
+                   "full_stack_check": full},
         "cpu_baseline": {"value": value, "unit": "spots/s", "cores": procs, "kind": "port",
-                         "sample": f"{procs} process(es) x one {crop[0]}x{crop[1]}x{crop[2]} crop of the C2 stack per step "
+                         "sample": f"{procs} process(es) x one {crop[0]}x{crop[1]}x{crop[2]} crop of the {args.config} stack per step "
                                    f"(same spot density), multiprocessing.Pool like classes/field_of_view.py:1129"},
         "e2e": {"value": value, "unit": "spots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -165,8 +207,35 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def _parity(host_stack, cfg, fitting):
+    """GPU result on a crop of the benchmark stack against the oracle (also the cpu_baseline sample)."""
+    from oracle import fit_oracle
+    crop = _crop_shape(cfg)
+    x0 = min(800, host_stack.shape[1] - crop[1])
+    y0 = min(800, host_stack.shape[2] - crop[2])
+    sub = np.ascontiguousarray(host_stack[:crop[0], x0:x0 + crop[1], y0:y0 + crop[2]])
+    kw = {k: v for k, v in cfg["kw"].items()}
+    want, t_cpu = cpu_sample(sub, kw)
+    ok = np.asarray(fit_oracle.fit_fov_image_oracle.last_comparable, dtype=bool)
+    got = fitting.fit_fov_image(sub, '647', verbose=False, **kw)
+    par = {"sample": f"{crop[0]}x{crop[1]}x{crop[2]} crop of the benchmark stack", "rows": int(len(want)), "rows_gpu": int(len(got)),
+           "comparable": int(ok.sum()) if len(want) else 0}
+    if len(want) and got.shape == want.shape:
+        g, w = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+        par["max_dev_centre_px"] = float(np.abs(g[ok, 1:4] - w[ok, 1:4]).max()) if ok.any() else 0.0
+        cols = [0, 4, 5, 6, 7]
+        par["max_dev_rel"] = float((np.abs(g[ok][:, cols] - w[ok][:, cols]) / np.abs(w[ok][:, cols])).max()) if ok.any() else 0.0
+        par["max_dev_centre_px_exempt_rows"] = float(np.abs(g[~ok, 1:4] - w[~ok, 1:4]).max()) if (~ok).any() else 0.0
+        par["in_tolerance"] = bool(par["max_dev_centre_px"] <= 1e-3 and par["max_dev_rel"] <= 1e-4)
+    else:
+        par["in_tolerance"] = bool(len(want) == 0 and len(got) == 0)
+    return par, len(want), t_cpu, crop
+
+
 def run_ours(args):
-    rank, world, local = _dist_setup(args.gpus)
+    rank, world, local = _dist_setup()
+    cfg = CONFIGS[args.config]
+    SHAPE, KW = cfg["shape"], dict(cfg["kw"], verbose=False)
     os.environ.setdefault("IA3_DEVICE", str(local))
     from imageanalysis3_b200 import _lib
     _lib.init(local)          # before torch touches the device: the library asks for blocking-sync waits
@@ -180,23 +249,22 @@ def run_ours(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
             dist.init_process_group(backend)
-    from imageanalysis3_b200 import _lib
+    from imageanalysis3_b200 import sharding
     from imageanalysis3_b200.External import Fitting_v4
     from imageanalysis3_b200.spot_tools import fitting
     from imageanalysis3_b200.synth import synth_torch
     torch.cuda.set_device(local)
-    _lib.init(local)
     dev = torch.device("cuda", local)
 
-    from imageanalysis3_b200 import sharding
     D = max(1, args.inflight)
-    n_stacks = max(2, min(D, 4))   # distinct stacks, cycled (each 419 MB > 126 MB L2)
+    n_stacks = max(2, min(D, 4))   # distinct stacks, cycled (each >= 250 MB > 126 MB L2; C1: 16 MB, see config.l2)
+    nbytes = int(np.prod(SHAPE)) * 2
 
     def run_steps(fn, first, count):
         return sum(sharding.map_stacks(fn, range(first, first + count), inflight=D))
-    host, devt = [], []
+    host, devt, pageable = [], [], []
     for i in range(n_stacks):
-        d = synth_torch(SHAPE, N_PLANTED, 1 + rank * 16 + i, dev)
+        d = synth_torch(SHAPE, cfg["n"], cfg["seed"] + rank * 16 + i, dev, h_range=cfg["h"])
         h = torch.empty(SHAPE, dtype=torch.int16, pin_memory=True)
         h.copy_(d)
         host.append(h.numpy().view(np.uint16))
@@ -207,12 +275,13 @@ def run_ours(args):
         """hot path with the stack already in HBM: seed stage + host replay + firstfit + repeatfit"""
         d = devt[i % n_stacks]
         st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
-        spots = fitting.fit_fov_image(host[i % n_stacks], '647', _stack=st, **FIT_KW)
-        return len(spots)
+        return len(fitting.fit_fov_image(host[i % n_stacks], '647', _stack=st, **KW))
 
     def step_e2e(i):
-        spots = fitting.fit_fov_image(host[i % n_stacks], '647', **FIT_KW)
-        return len(spots)
+        return len(fitting.fit_fov_image(host[i % n_stacks], '647', **KW))
+
+    def step_pageable(i):
+        return len(fitting.fit_fov_image(pageable[i % len(pageable)], '647', **KW))
 
     def barrier():
         torch.cuda.synchronize()
@@ -221,7 +290,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- value: HBM-resident -------------------------------------------------------------------
-    run_steps(step_resident, 0, max(args.warmup, D))
+    run_steps(step_resident, 0, max(args.warmup, min(D, 8)))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -237,27 +306,32 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
 
-    # stage timings (CUDA events on the library stream) for the roofline: separate short loop
+    # stage timings (CUDA events on the stack's stream) for the roofline: separate short loop
     stage = {"gauss_fg": [], "gauss_bg": [], "rank": [], "compact": [], "seed_total": [], "n_cand": []}
-    for i in range(max(3, args.steps)):
+    th_floor = float(KW["th_seed"]) * 0.1
+    for i in range(max(3, min(args.steps, 8))):
         d = devt[i % n_stacks]
         st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
-        zxy, h, t = st.seed_candidates(fitting._gauss_half_kernel(0.75), fitting._gauss_half_kernel(7.5), 3, 0, 2.0, TH_SEED * 0.1)
+        zxy, h, t = st.seed_candidates(fitting._gauss_half_kernel(0.75), fitting._gauss_half_kernel(7.5), 3, 0, 2.0, th_floor)
         stage["gauss_fg"].append(t.ms_gauss_fg); stage["gauss_bg"].append(t.ms_gauss_bg); stage["rank"].append(t.ms_rank)
         stage["compact"].append(t.ms_compact); stage["seed_total"].append(t.ms_total); stage["n_cand"].append(len(zxy))
         st.close()
-    # fit-stage device time
+    # fit stage alone on one stack: device time of the engine run (events around it), wall, engine counters
     d = devt[0]
     st = _lib.Stack(device_ptr=d.data_ptr(), shape=SHAPE, dtype=np.uint16)
-    seeds = fitting.get_seeds(host[0], max_num_seeds=None, th_seed=TH_SEED, _stack=st)
-    f = Fitting_v4.iter_fit_seed_points(host[0], seeds.T, _stack=st)
-    f.firstfit(); first_ms = f._h.last_ms
-    t1 = time.perf_counter(); f.repeatfit(); repeat_wall = time.perf_counter() - t1
-    n_levels, n_iter = f._h.num_levels, f.n_iter
-    del f, st
+    seeds = fitting.get_seeds(host[0], max_num_seeds=KW["max_num_seeds"], th_seed=KW["th_seed"],
+                              min_dynamic_seeds=KW.get("min_dynamic_seeds", 1), _stack=st)
+    fit_alone = {}
+    if len(seeds):
+        f = Fitting_v4.iter_fit_seed_points(host[0], seeds.T, _stack=st)
+        t1 = time.perf_counter(); f._fit_all(); fit_wall = time.perf_counter() - t1
+        fit_alone = {"seeds": int(len(seeds)), "device_ms": f._h.last_ms, "wall_ms": 1e3 * fit_wall, "repeat_sweeps": int(f.n_iter),
+                     "dependency_levels": f._h.num_levels, "engine": f._h.engine_stats()}
+        del f
+    del st
 
-    # ---- e2e: public API, host buffers -----------------------------------------------------------
-    run_steps(step_e2e, 0, max(min(args.warmup, 3), D))
+    # ---- e2e: public API, pinned host buffers ------------------------------------------------------
+    run_steps(step_e2e, 0, max(min(args.warmup, 3), min(D, 8)))
     barrier()
     c0 = dict(_lib.COPIED)
     _lib.timer_start()
@@ -266,11 +340,37 @@ def run_ours(args):
     barrier()
     c1 = dict(_lib.COPIED)
     # latency of one stack with nothing else in flight (same public call)
-    _lib.timer_start()
-    step_e2e(0)
-    ms_latency = _lib.timer_stop()
+    lat = []
+    for _ in range(3):
+        _lib.timer_start()
+        step_e2e(0)
+        lat.append(_lib.timer_stop())
+    ms_latency = float(np.median(lat))
 
-    t_val = torch.tensor([ms_dev, ms_e2e, float(n_spots), float(n_e2e), float(launches)], dtype=torch.float64,
+    # ---- e2e from pageable memory (what a numpy caller holds) -------------------------------------
+    ms_pg, n_pg = None, 0
+    if not args.no_pageable:
+        pageable = [np.array(hh) for hh in host[:2]]        # plain numpy copies
+        k_pg = max(4, min(args.steps, 32))
+        run_steps(step_pageable, 0, min(k_pg, 4))
+        barrier()
+        _lib.timer_start()
+        n_pg = run_steps(step_pageable, 0, k_pg)
+        ms_pg = _lib.timer_stop() / k_pg
+        barrier()
+    # the PCIe floor of this box for one stack (pinned H2D copy, nothing else running)
+    hbuf = torch.from_numpy(host[0].view(np.int16))
+    dbuf = torch.empty_like(devt[0])
+    floor = []
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(); dbuf.copy_(hbuf, non_blocking=True); e1.record()
+        torch.cuda.synchronize()
+        floor.append(e0.elapsed_time(e1))
+    pcie_floor_ms = float(min(floor[1:]))
+
+    t_val = torch.tensor([ms_dev, ms_e2e, float(n_spots), float(n_e2e), float(launches), ms_pg or 0.0, pcie_floor_ms], dtype=torch.float64,
                          device=dev if (not use_dist or dist.get_backend() == "nccl") else "cpu")
     if use_dist and os.environ.get("IA3_BENCH_VERBOSE"):
         print(f"rank {rank}: {ms_dev / args.steps:.2f} ms/step resident, {ms_e2e / args.steps:.2f} ms/step e2e", file=sys.stderr, flush=True)
@@ -279,6 +379,8 @@ def run_ours(args):
         tsum = t_val.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_dev, ms_e2e = float(tmax[0]), float(tmax[1])
         n_spots, n_e2e, launches = float(tsum[2]), float(tsum[3]), float(tsum[4])
+        ms_pg = float(tmax[5]) if ms_pg is not None else None
+        pcie_floor_ms = float(tmax[6])
     if rank != 0:
         if use_dist:
             dist.destroy_process_group()
@@ -287,52 +389,59 @@ def run_ours(args):
     vox = float(np.prod(SHAPE))
     peak, peak_src = _peaks()
     bg_launch_ms = float(np.median(stage["gauss_bg"])) / 3.0
-    alg_bytes = 4.0 * vox                                  # one axis pass: read u16 + write u16 per voxel
-    achieved = alg_bytes / (bg_launch_ms * 1e-3) / 1e9
+    pass_bytes = 4.0 * vox                                  # one axis pass: read u16 + write u16 per voxel
+    pass_achieved = pass_bytes / (bg_launch_ms * 1e-3) / 1e9
     seed_ms_med = float(np.median(stage["seed_total"]))
-    stage_bytes = 2.0 * vox + 16.0 * float(np.median(stage["n_cand"]))
+    stage_bytes = 2.0 * vox + 16.0 * float(np.median(stage["n_cand"]))      # read each voxel once + write the candidates
+    stage_achieved = stage_bytes / (seed_ms_med * 1e-3) / 1e9
     fp64_inst = 32.0 * vox                                  # 1 DMUL + 30 DFMA + 1 DADD (offset + guard) per voxel
     fit_flops_per_spot = 1.67e6                             # model / Jacobian / normal equations per spot
+    fit_tflops = fit_flops_per_spot * n_spots / (ms_dev * 1e-3) / 1e12
+    peak_fp32 = 148 * 128 * 2 * 1.965e9 / 1e12
+    spots_per_stack = n_spots / (world * args.steps)
     line = {
         "metric": "spots_fitted_per_s", "value": n_spots / (ms_dev * 1e-3), "unit": "spots/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "stacks_per_s": world * args.steps / (ms_dev * 1e-3),
-        "config": {"workload": "C2: fit_fov_image(th_seed=300, max_num_seeds=None) on one 50x2048x2048 uint16 FOV per step per GPU, "
-                               "5000 planted spots; seed stage + Fitting_v4 firstfit + repeatfit",
-                   "l2": f"inputs larger than L2 (419 MB per stack, {n_stacks} stacks cycled)",
+        "config": {"workload": cfg["text"], "name": args.config,
+                   "l2": f"{n_stacks} distinct stacks of {nbytes / 1e6:.0f} MB cycled per GPU" +
+                         (" (larger than the 126 MB L2)" if nbytes > 126e6 else f"; working set of a step = stack + 3 work volumes = {4 * nbytes / 1e6:.0f} MB"),
                    "inflight": D, "latency_ms_one_stack_alone": ms_latency,
                    "host_cpu_ms_per_step": cpu_ms_per_step, "host_cores": os.cpu_count(),
-                   "spots_per_stack": n_spots / (world * args.steps), "fit_levels": n_levels, "repeat_sweeps": n_iter},
+                   "spots_per_stack": spots_per_stack, "fit_stage_one_stack_alone": fit_alone},
         "clocks": clocks,
         "e2e": {"value": n_e2e / (ms_e2e * 1e-3), "unit": "spots/s",
                 "h2d_bytes_per_step": (c1["h2d"] - c0["h2d"]) / args.steps, "d2h_bytes_per_step": (c1["d2h"] - c0["d2h"]) / args.steps,
-                "ms_per_step": ms_e2e / args.steps, "stacks_per_s": world * args.steps / (ms_e2e * 1e-3)},
+                "ms_per_step": ms_e2e / args.steps, "stacks_per_s": world * args.steps / (ms_e2e * 1e-3),
+                "pcie_floor_ms": pcie_floor_ms,
+                "note": "input = pinned host stacks; pcie_floor_ms = one stack's H2D copy alone on this box (max over ranks)"},
+        "e2e_pageable": None if ms_pg is None else {
+            "value": spots_per_stack * world / (ms_pg * 1e-3), "unit": "spots/s", "ms_per_step": ms_pg,
+            "note": "input = plain numpy arrays (pageable): staged through pinned chunks by worker threads (IA3_STAGE_THREADS, default 6)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": _traffic(),
-                     "kernel": "k_gauss_short<30,50> / k_gauss_strided<30> / k_gauss_contig<30> (one 61-tap bit-exact axis pass; 3 launches per stack, mean)",
-                     "launch_ms": bg_launch_ms, "peak_source": peak_src,
-                     "note": "exact uint16 semantics make this pass FP64-pipe / issue bound, not HBM bound: 32 FP64 + ~60 integer instructions per voxel; "
-                             "by time the dominant kernel of a step is k_fit<double> (latency bound, see roofline_fit and profiles/r01_ncu_launch_list_final.csv)",
-                     "fp64_inst_per_s": fp64_inst / (bg_launch_ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": stage_achieved, "peak": peak, "unit": "GB/s", "frac": stage_achieved / peak, "traffic": _traffic(),
+                     "kernel": "seed stage of one stack (6 bit-exact Gaussian axis passes + rank/flag pass + compaction), SURVEY 8(d) bytes: "
+                               "2 B/voxel + 16 B/candidate over the stage's device time",
+                     "launch_ms": seed_ms_med, "algorithmic_bytes": stage_bytes, "peak_source": peak_src,
+                     "traffic_note": "traffic = DRAM bytes of ONE 61-tap pass (ncu); the stage makes 6 passes + a 2-volume rank pass",
+                     "pass_frac": pass_achieved / peak, "pass_achieved_GBps": pass_achieved, "pass_launch_ms": bg_launch_ms,
+                     "pass_kernel": "k_gauss_short<30,Z> / k_gauss_strided<30> / k_gauss_contig<30>: one 61-tap axis pass, 4 B/voxel (mean of 3 launches)",
+                     "note": "exact uint16 semantics make the passes FP64-pipe / issue bound, not HBM bound: 32 FP64 + ~60 integer instructions per voxel",
                      "fp64_pipe_frac": fp64_inst / (bg_launch_ms * 1e-3) / (148 * 64 * 1.965e9),
-                     "seed_stage": {"ms": seed_ms_med, "algorithmic_bytes": stage_bytes,
-                                    "achieved_GBps": stage_bytes / (seed_ms_med * 1e-3) / 1e9,
-                                    "frac": stage_bytes / (seed_ms_med * 1e-3) / 1e9 / peak,
-                                    "ms_gauss_fg": float(np.median(stage["gauss_fg"])), "ms_gauss_bg": float(np.median(stage["gauss_bg"])),
-                                    "ms_rank": float(np.median(stage["rank"])), "ms_compact": float(np.median(stage["compact"]))},
-                     "fit_stage": {"firstfit_ms": first_ms, "repeatfit_wall_ms": repeat_wall * 1e3}},
-        "roofline_fit": {"bound": "fp64/fp32 pipes (latency bound: one warp per spot runs MINPACK's serial iterations)",
-                         "achieved": fit_flops_per_spot * n_spots / (ms_dev * 1e-3) / 1e12, "unit": "TFLOP/s",
-                         "peak_fp32": 148 * 128 * 2 * 1.965e9 / 1e12, "peak_fp64": 148 * 64 * 2 * 1.965e9 / 1e12,
-                         "algorithmic_flops_per_spot": fit_flops_per_spot},
+                     "ms_gauss_fg": float(np.median(stage["gauss_fg"])), "ms_gauss_bg": float(np.median(stage["gauss_bg"])),
+                     "ms_rank": float(np.median(stage["rank"])), "ms_compact": float(np.median(stage["compact"]))},
+        "roofline_fit": {"bound": "fp32/fp64 pipes (SURVEY 8(d): 1.67 MFLOP per spot against the FP32 FMA peak)",
+                         "achieved": fit_tflops, "unit": "TFLOP/s", "peak": peak_fp32, "frac": fit_tflops / peak_fp32,
+                         "peak_fp64": 148 * 64 * 2 * 1.965e9 / 1e12, "algorithmic_flops_per_spot": fit_flops_per_spot,
+                         "note": "whole-step spots/s x 1.67 MFLOP; the fit is a serial lmder chain per spot evaluated in FP64 like the reference"},
         "wall_ms_per_step": 1e3 * wall / args.steps,
     }
     if not args.no_cpu:
-        crop = np.ascontiguousarray(host[0][:CPU_CROP[0], 800:800 + CPU_CROP[1], 800:800 + CPU_CROP[2]])
-        n_cpu, t_cpu = cpu_sample(crop)
+        par, n_cpu, t_cpu, crop = _parity(host[0], cfg, fitting)
+        line["parity"] = par
         line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "spots/s", "cores": 1, "kind": "port",
-                                "sample": f"one {CPU_CROP[0]}x{CPU_CROP[1]}x{CPU_CROP[2]} crop of the same stack: {n_cpu} spots in {t_cpu:.1f} s "
+                                "sample": f"one {crop[0]}x{crop[1]}x{crop[2]} crop of the same stack: {n_cpu} spots in {t_cpu:.1f} s "
                                           "(oracle port = the reference's scipy/numpy calls, single thread as in the reference)"}
     print(json.dumps(line), flush=True)
     if use_dist:
@@ -342,11 +451,15 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--inflight", type=int, default=64, help="stacks in flight per GPU (host threads / CUDA streams)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-input leg")
+    ap.add_argument("--no-full-check", dest="full_check", action="store_false", help="reference arm: skip the one full-size stack")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("IA3_BENCH_INFLIGHT", "32")),
+                    help="stacks in flight per GPU (host threads / CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -205,9 +205,11 @@ class IterFitBase:
         self.info = h.info.copy()
         self.n_iter = int(h.n_visits.max()) if n else 0
         self.converged = h.converged.astype(bool)
-        self.dists = h.dists.copy()
         # state at the start of the last sweep: seeds visited in it held success_old / centers_old
         last = h.n_visits == self.n_iter
+        # the reference recomputes dists for every seed after each sweep: a seed that was not visited in the
+        # last one has old == new there, i.e. 0
+        self.dists = np.where(last, h.dists, 0.0)
         self.success_old = np.where(last, h.success_old.astype(bool), self._succ)
         had_fit = np.where(last & (self.n_iter == 1), h.success_old.astype(bool), self._has_fit)
         old = np.where(last[:, None], h.centers_old, self._ps[:, 1:4])

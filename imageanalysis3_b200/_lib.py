@@ -343,11 +343,20 @@ class FitHandle:
         _count("d2h", self._result_bytes())
         _count("h2d", self.n)
 
-    def engine_stats(self):
-        out = np.zeros(10, dtype=np.int64)
-        _check(load().ia3_fit_engine_stats(self._h, _ptr(out), 10))
+    def engine_stats(self, trace=False):
+        out = np.zeros(16 + 1024, dtype=np.int64)
+        _check(load().ia3_fit_engine_stats(self._h, _ptr(out), len(out)))
         keys = ("rounds", "tasks", "lm_runs", "evals", "memo_hits", "spec_runs", "spec_hits", "parked", "team_tasks", "bricks")
-        return dict(zip(keys, (int(v) for v in out)))
+        st = dict(zip(keys, (int(v) for v in out[:10])))
+        if out[15] > 0:          # IA3_FIT_PROF build: cycles of the team kernel's phases per evaluation
+            st["team_cycles_per_eval"] = {k: round(float(out[10 + i]) / float(out[15]), 1)
+                                          for i, k in enumerate(("outer", "lmpar", "consts", "pass", "judge"))}
+        if trace:
+            nr = min(st["rounds"], 512)
+            w = out[16:16 + 2 * nr:2]
+            ns = out[17:17 + 2 * nr:2]
+            st["trace"] = [(int(x >> 16), int(x & 0xffff), round(float(t - ns[0]) * 1e-6, 3)) for x, t in zip(w, ns)]
+        return st
 
     def _result_bytes(self):
         return self.ps.nbytes + self.p_raw.nbytes + self.success.nbytes + self.nfev.nbytes + self.info.nbytes

@@ -29,9 +29,12 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: a developer build with extra -D flags into libia3b200_<variant>.so (select it with
+    the IA3_LIB environment variable); the product library is the plain build."""
     nvcc = _nvcc()
-    bdir = os.path.join(HERE, "_build")
+    bdir = os.path.join(HERE, "_build" if not variant else os.path.join("_build", variant))
+    lib = LIB if not variant else os.path.join(HERE, f"libia3b200_{variant}.so")
     os.makedirs(bdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
     headers.append(os.path.join(HERE, "..", "include", "ia3b200.h"))
@@ -42,7 +45,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
         if force or not _newer(obj, [sp] + headers):
             cmd = [nvcc, "-c", sp, "-o", obj, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-                   "-Xptxas", "-v" if verbose else "-O3"] + ARCH
+                   "-Xptxas", "-v" if verbose else "-O3"] + ARCH + [f"-D{d}" for d in defines]
             jobs.append(cmd)
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=len(jobs)) as ex:
@@ -51,14 +54,16 @@ def build(force=False, verbose=False):
                     sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr + "\n")
                 if res.returncode != 0:
                     raise RuntimeError("nvcc failed for " + cmd[2])
-    if jobs or force or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fPIC", "-lcudart"]
+    if jobs or force or not os.path.exists(lib):
+        cmd = [nvcc, "-shared", "-o", lib] + objs + ARCH + ["-Xcompiler", "-fPIC", "-lcudart"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var[0] if var else None, defines=defs))

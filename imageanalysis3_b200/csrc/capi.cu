@@ -1166,12 +1166,18 @@ int ia3_fit_engine_stats(ia3_fit* f, int64_t* out, int cap) {
   if (ensure_device()) return -1;
   if (!f || !out) { set_error("null argument"); return -1; }
   cudaStream_t st = f->s->stream;
-  if (small_copy(f->h_ctl(), f->d.ctl, sizeof(EngineCtl), st)) return -1;
+  Scoped sc;
+  void* h = nullptr;
+  if (sc.halloc(&h, sizeof(EngineCtl))) return -1;
+  if (small_copy(h, f->d.ctl, sizeof(EngineCtl), st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
-  const EngineCtl& c = *f->h_ctl();
-  const int64_t v[10] = {c.st_rounds, c.st_tasks, c.st_lm_runs, (int64_t)c.st_evals, c.st_memo_hits, c.st_spec_runs, c.st_spec_hits,
-                         c.st_parked, c.st_team_tasks, c.n_bricks};
-  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
+  const EngineCtl& c = *static_cast<const EngineCtl*>(h);
+  std::vector<int64_t> v = {c.st_rounds, c.st_tasks, c.st_lm_runs, (int64_t)c.st_evals, c.st_memo_hits, c.st_spec_runs, c.st_spec_hits,
+                            c.st_parked, c.st_team_tasks, c.n_bricks};
+  for (int q = 0; q < 6; ++q) v.push_back((int64_t)c.prof[q]);                       // 10..15
+  const int nr = std::min(c.st_rounds, 512);
+  for (int r = 0; r < nr; ++r) { v.push_back((int64_t)c.trace_work[r]); v.push_back((int64_t)c.trace_ns[r]); }   // 16 + 2 r
+  for (int i = 0; i < cap; ++i) out[i] = i < (int)v.size() ? v[i] : -1;
   return 0;
 }
 

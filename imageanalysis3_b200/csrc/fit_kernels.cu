@@ -367,6 +367,7 @@ __global__ void k_engine_init(FitDev d) {
     c->cap_team_now = d.cap_team_short; c->done = 0; c->all_ok0 = 1; c->all_ok1 = 1;
     c->st_lm_runs = c->st_memo_hits = c->st_spec_runs = c->st_spec_hits = c->st_parked = c->st_team_tasks = c->st_tasks = c->st_rounds = 0;
     c->st_evals = 0ull;
+    for (int q = 0; q < 8; ++q) c->prof[q] = 0ull;
   }
   if (i >= d.n) return;
   d.stage[i] = -2; d.fin[i] = 0; d.busy[i] = 0; d.conv[i] = 0; d.specst[i] = 0; d.succ_prev[i] = 0;
@@ -446,7 +447,14 @@ __global__ void __launch_bounds__(256) k_sched(FitDev d, int round, int phases, 
       const int nb = *(volatile int*)&c->n_bulk[pr];
       c->cap_team_now = (nb == 0) ? d.cap_team_long : d.cap_team_short;
       if (!al) { c->done = 1; *(volatile int*)d.h_done = 1; __threadfence_system(); }
-      else c->st_rounds += 1;
+      else {
+        const int slot = c->st_rounds & 511;
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+        c->trace_work[slot] = ((unsigned)min(nb, 65535) << 16) | (unsigned)min(*(volatile int*)&c->n_team[pr], 65535);
+        c->trace_ns[slot] = ns;
+        c->st_rounds += 1;
+      }
     }
   }
 }
@@ -530,12 +538,22 @@ __device__ __forceinline__ double pass_cta(WarpExec& ex, SpotShared<double>& sh,
 
 // lmder, driven by warp 0; the other warps of the CTA only join the voxel passes.  Same control flow
 // as run_lm (fit_spot.h).  Returns true if the run was suspended after `cap` evaluations.
+#ifdef IA3_FIT_PROF
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADD(i, a, b) do { if (TW > 1 && threadIdx.x == 0) prof_acc[i] += (unsigned long long)((b) - (a)); } while (0)
+#else
+#define PROF_T(v) do {} while (0)
+#define PROF_ADD(i, a, b) do {} while (0)
+#endif
 template <int TW, typename Vox>
 __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, const LMConfig& cfg, const double* cen,
                                            const double* origin, const Vox& vox, SpotShared<double>& sh, CtaScratch& cs,
-                                           double* gram_w, double* part, int cap, int start) {
+                                           double* gram_w, double* part, int cap, int start, unsigned long long* prof_out) {
   const int warp = threadIdx.x >> 5;
   LMState& st = sh.st;
+#ifdef IA3_FIT_PROF
+  unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   if (start == LM_START_FRESH) {
     if (warp == 0) build_consts_par<double>(ex, fp, cen, origin, sh.x0, sh);
     cta_sync<TW>();
@@ -547,6 +565,7 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
   bool suspended = false;
   for (;;) {
     // sh.Ag holds J^T J, J^T f at st.x (x0, or the trial point that was just accepted)
+    PROF_T(t0);
     if (warp == 0) {
       int go = 1;
       __syncwarp();
@@ -555,28 +574,37 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
       if (ex.lane() == 0) cs.go = go;
     }
     cta_sync<TW>();
+    PROF_T(t1);
+    PROF_ADD(0, t0, t1);
     const int go = cs.go;
     if (go == 2) { suspended = true; break; }
     if (go == 0) break;
     int action;
     for (;;) {
-      if (warp == 0) {
-        lm_propose(ex, st);
-        build_consts_par<double>(ex, fp, cen, origin, st.xt, sh);
-      }
+      PROF_T(t2);
+      if (warp == 0) lm_propose(ex, st);
+      PROF_T(t3);
+      if (warp == 0) build_consts_par<double>(ex, fp, cen, origin, st.xt, sh);
       cta_sync<TW>();
+      PROF_T(t4);
       const double fn1 = pass_cta<TW>(ex, sh, vox, gram_w, part);     // lm_outer has consumed the old sums
+      PROF_T(t5);
       if (warp == 0) {
         const int a = lm_judge(ex, st, cfg, fn1);
         if (ex.lane() == 0) cs.action = a;
       }
       cta_sync<TW>();
+      PROF_T(t6);
+      PROF_ADD(1, t2, t3); PROF_ADD(2, t3, t4); PROF_ADD(3, t4, t5); PROF_ADD(4, t5, t6); PROF_ADD(5, 0, 1);
       action = cs.action;
       if (action != LM_RETRY) break;
     }
     if (action == LM_DONE) break;
   }
   cta_sync<TW>();
+#ifdef IA3_FIT_PROF
+  if (TW > 1 && threadIdx.x == 0) for (int q = 0; q < 6; ++q) atomicAdd(&prof_out[q], prof_acc[q]);
+#endif
   return suspended;
 }
 
@@ -746,7 +774,7 @@ __device__ void process_task(const FitDev& d, unsigned task, unsigned char* base
   }
 
   bool suspended = false;
-  if (!hit) suspended = run_lm_cta<TW>(ex, fp, d.lm, c, origin, vox, sh, cs, gram_w, part, cap, start);
+  if (!hit) suspended = run_lm_cta<TW>(ex, fp, d.lm, c, origin, vox, sh, cs, gram_w, part, cap, start, ctl->prof);
   if (suspended) {
     if (warp == 0) {
       LMLive* g = d.live + slot;

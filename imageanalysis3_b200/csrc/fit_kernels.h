@@ -56,6 +56,11 @@ struct EngineCtl {
   // statistics (ia3_fit_engine_stats)
   int st_lm_runs, st_memo_hits, st_spec_runs, st_spec_hits, st_parked, st_team_tasks, st_tasks, st_rounds;
   unsigned long long st_evals;
+  // per-round trace (ring of 512): (n_bulk << 16 | n_team), and the device clock in ns when the round's k_sched ended
+  unsigned trace_work[512];
+  unsigned long long trace_ns[512];
+  // cycle counters of the team kernel's phases (IA3_FIT_PROF builds): outer, lmpar, consts, pass, judge, evals
+  unsigned long long prof[8];
 };
 
 struct FitDev {

@@ -329,14 +329,14 @@ def test_remaining_argument_paths_match_fixture(lib, golden_fits):
     assert c.shape == g["centers_noclose"].shape and np.abs(c - g["centers_noclose"]).max() <= 1e-3
 
 
-_SUSPEND_SCRIPT = r'''
+_ENGINE_SCRIPT = r'''
 import sys
 import numpy as np
 sys.path.insert(0, ".")
 from imageanalysis3_b200.External import Fitting_v3, Fitting_v4
 from imageanalysis3_b200.spot_tools import fitting
 from imageanalysis3_b200.synth import synth
-im = synth((30, 128, 128), 400, 31, h_range=(500.0, 3000.0))       # crowded: many long LM runs
+im = synth((30, 128, 128), 400, 31, h_range=(500.0, 3000.0))       # crowded: many long LM runs, overlapping windows
 seeds = fitting.get_seeds(im, max_num_seeds=None, th_seed=200.0)
 out = {}
 for name, mod in (("v4", Fitting_v4), ("v3", Fitting_v3)):
@@ -347,26 +347,72 @@ for name, mod in (("v4", Fitting_v4), ("v3", Fitting_v3)):
     out[name + "_ps"] = np.array(f.ps)
     out[name + "_nfev"] = np.array(f.nfev)
     out[name + "_n_iter"] = f.n_iter
+    out[name + "_converged"] = f.converged
+    out[name + "_dists"] = f.dists
+    g = mod.iter_fit_seed_points(im, seeds.T)
+    g._fit_all()                                # one device run, with speculation
+    out[name + "_all_ps"] = np.array(g.ps)
+    out[name + "_all_n_iter"] = g.n_iter
+    out[name + "_all_converged"] = g.converged
+    st = g._h.engine_stats()
+    out[name + "_stats"] = np.array([st["parked"], st["team_tasks"], st["memo_hits"], st["spec_hits"]])
 np.savez(sys.argv[1], **out)
 '''
 
 
-def test_suspended_fits_continue_bit_identically(lib, tmp_path):
-    """IA3_FIT_CAP: k_fit parks a run after that many function evaluations and the continuation service
-    finishes it (capi.cu).  cap = 3 suspends nearly every fit several times; the results must be the
-    very same bits as with suspension switched off."""
+def test_engine_schedule_does_not_change_a_bit(lib, tmp_path):
+    """The fit engine may suspend a run after any number of evaluations, continue it with one warp or
+    with a team of warps, skip a re-fit whose inputs are those of the seed's previous visit (memo) and
+    start the first repeat visit of isolated seeds speculatively: none of that may change a single bit.
+    Reference configuration: no suspension, no memo, no speculation (every visit runs lmder from
+    scratch on one warp).  Aggressive configuration: suspend every 3 evaluations, team continuation after
+    9, memo and speculation on."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfgs = {"plain": dict(IA3_FIT_CAP="0", IA3_FIT_MEMO="0", IA3_FIT_SPEC="0"),
+            "busy": dict(IA3_FIT_CAP="3", IA3_FIT_TEAM_AFTER="9", IA3_FIT_TEAM_CAP="5", IA3_FIT_TEAM_CAP_LONG="7", IA3_FIT_MEMO="1",
+                         IA3_FIT_SPEC="1", IA3_FIT_CHUNK="3"),
+            "default": {}}
     res = {}
-    for cap in (0, 3):
-        path = str(tmp_path / f"cap{cap}.npz")
-        subprocess.run([sys.executable, "-c", _SUSPEND_SCRIPT, path], cwd=root, check=True, timeout=300,
-                       env={**os.environ, "IA3_FIT_CAP": str(cap)})
-        res[cap] = np.load(path)
-    assert res[0]["v4_nfev"].max() > 50                       # the image does contain long runs
-    for key in res[0].files:
-        a, b = res[0][key], res[3][key]
-        assert a.shape == b.shape and a.dtype == b.dtype, key
-        assert np.array_equal(a, b, equal_nan=True), key
+    for tag, env in cfgs.items():
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", _ENGINE_SCRIPT, path], cwd=root, check=True, timeout=600, env={**os.environ, **env})
+        res[tag] = np.load(path)
+    assert res["plain"]["v4_nfev"].max() > 50                       # the image does contain long runs
+    assert res["plain"]["v4_stats"][:3].sum() == 0
+    assert (res["busy"]["v4_stats"] > 0).all(), res["busy"]["v4_stats"]     # every mechanism was exercised
+    for tag in ("busy", "default"):
+        for key in res["plain"].files:
+            if key.endswith("_stats"):
+                continue
+            a, b = res["plain"][key], res[tag][key]
+            assert a.shape == b.shape and a.dtype == b.dtype, (tag, key)
+            assert np.array_equal(a, b, equal_nan=True), (tag, key)
+    for name in ("v4", "v3"):                                        # one run == firstfit(); repeatfit()
+        r = res["plain"]
+        assert np.array_equal(r[name + "_ps"], r[name + "_all_ps"], equal_nan=True)
+        assert r[name + "_n_iter"] == r[name + "_all_n_iter"] and np.array_equal(r[name + "_converged"], r[name + "_all_converged"])
+
+
+def test_device_convergence_rule_equals_host_loop(lib, golden_fits):
+    """repeatfit's per-seed rule evaluated on the device (ia3_fit_run) against the reference's loop run on the
+    host with one device sweep per iteration (ia3_fit_repeat_sweep): same rows, n_iter, converged, dists and
+    the *_old attributes, also with a seed that never gets a fit (float64 distance arithmetic)."""
+    from imageanalysis3_b200.External import Fitting_v4
+    g = golden_fits
+    for seeds in (g["seeds"], g["edge_seeds"]):
+        a = Fitting_v4.iter_fit_seed_points(g["im"], seeds.T)
+        a.firstfit(); a.repeatfit()
+        b = Fitting_v4.iter_fit_seed_points(g["im"], seeds.T)
+        b.firstfit(); b._repeatfit_host_loop()
+        c = Fitting_v4.iter_fit_seed_points(g["im"], seeds.T)
+        c._fit_all()
+        for other in (b, c):
+            assert np.array_equal(a._ps, other._ps, equal_nan=True)
+            assert a.n_iter == other.n_iter and np.array_equal(a.converged, other.converged) and np.array_equal(a.dists, other.dists)
+            assert np.array_equal(a.success_old, other.success_old)
+            assert a.centers_fit_old.dtype == other.centers_fit_old.dtype
+            assert np.array_equal(a.centers_fit_old, other.centers_fit_old, equal_nan=True)
+            assert np.array(a.ps).dtype == np.array(other.ps).dtype
