@@ -42,6 +42,26 @@ static int acquire_stream(cudaStream_t* out) {
   IA3_CUDA(cudaStreamCreateWithFlags(out, cudaStreamNonBlocking));
   return 0;
 }
+// Fit rounds are many short kernels on a dependent chain; the seed stage of the other stacks in flight is a few
+// long kernels that fill every SM.  Fit streams get the highest priority, so a round's CTAs are placed as soon
+// as an SM slot frees instead of waiting for a whole seed kernel to drain (a round would otherwise pick up
+// ~1 ms of queueing, fifty times per stack).
+static std::vector<cudaStream_t> g_hi_stream_pool;
+static int acquire_stream_hi(cudaStream_t* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_hi_stream_pool.empty()) { *out = g_hi_stream_pool.back(); g_hi_stream_pool.pop_back(); return 0; }
+  }
+  int lo = 0, hi = 0;
+  IA3_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  IA3_CUDA(cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, hi));
+  return 0;
+}
+static void release_stream_hi(cudaStream_t st) {
+  if (!st) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_hi_stream_pool.push_back(st);
+}
 static cudaStream_t g_upload_stream = nullptr;
 static std::mutex g_upload_mu;
 static int upload_stream(cudaStream_t* out) {
@@ -742,10 +762,16 @@ static const int g_team_cap = std::max(1, env_int("IA3_FIT_TEAM_CAP", 32));
 static const int g_team_cap_long = std::max(1, env_int("IA3_FIT_TEAM_CAP_LONG", 160));
 static const int g_memo_on = env_int("IA3_FIT_MEMO", 1) != 0;
 static const int g_spec_on = env_int("IA3_FIT_SPEC", 1) != 0;
-static const int g_chunk = std::max(1, env_int("IA3_FIT_CHUNK", 8));
+static const int g_chunk = std::max(1, env_int("IA3_FIT_CHUNK", 4));
+// CTAs per launch: the first two rounds of a run hold one task per seed, later ones a few % of that
+static const int g_grid_bulk = std::max(1, env_int("IA3_FIT_GRID", 148 * 16));
+static const int g_grid_bulk_late = std::max(1, env_int("IA3_FIT_GRID_LATE", 148 * 3));
+static const int g_grid_team = std::max(1, env_int("IA3_FIT_GRID_TEAM", 148));
+static const int g_grid_team_late = std::max(1, env_int("IA3_FIT_GRID_TEAM_LATE", 74));
 
 struct ia3_fit {
   ia3_stack* s = nullptr;
+  cudaStream_t st = nullptr;                      // high-priority stream of the fit rounds (the stack's own stream carries upload + seed stage)
   ia3_fit_cfg cfg;
   FitDev d;
   int64_t n = 0;
@@ -754,8 +780,7 @@ struct ia3_fit {
   bool prepared = false, started = false, first_done = false;
   int64_t n_ties = 0;
   int ties_prefetched = 0;
-  cudaStream_t st2 = nullptr;                     // team kernels of a round run beside the one-warp kernel
-  cudaEvent_t ev_s = nullptr, ev_t = nullptr, ev_chunk[2] = {nullptr, nullptr}, e0 = nullptr, e1 = nullptr;
+  cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, e0 = nullptr, e1 = nullptr;
   void* arena = nullptr;                          // all per-seed device arrays
   int* d_nbr_idx = nullptr; int* d_dep_idx = nullptr;
   int* d_tie_spot = nullptr; int* d_tie_k = nullptr;
@@ -793,7 +818,7 @@ static void release_event_bs(cudaEvent_t e) {
 }
 
 static int build_neighbours(ia3_fit* f) {
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   const size_t nc = (size_t)f->grid.ncell;
   int* cnt = f->d_cells;
   int* start = cnt + nc;
@@ -823,10 +848,12 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
       if (i == 0 || v < lo3[a]) lo3[a] = v;
       if (i == 0 || v > hi3[a]) hi3[a] = v;
     }
+  IA3_CUDA(cudaStreamSynchronize(s->stream));      // everything queued on the stack (upload, seed stage) is done before the fit reads the image
+  cudaStream_t st = nullptr;
+  if (acquire_stream_hi(&st)) return -1;
   ia3_fit* f = new ia3_fit();
-  f->s = s; f->cfg = *cfg; f->n = n;
+  f->s = s; f->cfg = *cfg; f->n = n; f->st = st;
   f->centers.assign(centers_zxy, centers_zxy + 3 * n);
-  cudaStream_t st = s->stream;
   const int r = cfg->radius;
   // window offsets: np.indices([2r]*3) - r, kept where d^2 <= r^2, C order (Fitting_v4.py:580-583)
   for (int a = -r; a < r; ++a) for (int b = -r; b < r; ++b) for (int c = -r; c < r; ++c)
@@ -847,8 +874,8 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   g.ncell = (long long)g.g[0] * g.g[1] * g.g[2];
 
 #define FAIL() do { ia3_fit_destroy(f); return -1; } while (0)
-  if (acquire_stream(&f->st2) || acquire_event_bs(&f->ev_chunk[0]) || acquire_event_bs(&f->ev_chunk[1]) ||
-      acquire_event(&f->ev_s) || acquire_event(&f->ev_t) || acquire_event(&f->e0) || acquire_event(&f->e1)) FAIL();
+  if (acquire_event_bs(&f->ev_chunk[0]) || acquire_event_bs(&f->ev_chunk[1]) ||
+      acquire_event(&f->e0) || acquire_event(&f->e1)) FAIL();
   if (host_alloc(&f->h_pin, kPinBytes)) FAIL();
   memset(f->h_pin, 0, 1024);
 
@@ -924,13 +951,12 @@ int ia3_fit_destroy(ia3_fit* f) {
   IA3_STAT("ia3_fit_destroy");
   if (!f) return 0;
   if (g_device >= 0) cudaSetDevice(g_device);
-  if (f->s && f->s->stream) cudaStreamSynchronize(f->s->stream);
-  if (f->st2) cudaStreamSynchronize(f->st2);
+  if (f->st) cudaStreamSynchronize(f->st);
   void* ptrs[] = {f->arena, f->d_nbr_idx, f->d_dep_idx, f->d_tie_spot, f->d_tie_k, f->d_vol, f->d_cells, f->d_keep};
   for (void* p : ptrs) dev_free(p);
-  release_event(f->ev_s); release_event(f->ev_t); release_event(f->e0); release_event(f->e1);
+  release_event(f->e0); release_event(f->e1);
   release_event_bs(f->ev_chunk[0]); release_event_bs(f->ev_chunk[1]);
-  release_stream(f->st2);
+  release_stream_hi(f->st);
   host_free(f->h_pin); host_free(f->h_stage); host_free(f->h_up); host_free(f->h_keep);
   delete f;
   return 0;
@@ -941,7 +967,7 @@ int ia3_fit_first_prepare(ia3_fit* f, int64_t* n_ties) {
   if (ensure_device()) return -1;
   if (!f) { set_error("null argument"); return -1; }
   if (f->prepared) { if (n_ties) *n_ties = f->n_ties; return 0; }
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   FitDev& d = f->d;
   for (int attempt = 0; attempt < 4; ++attempt) {
     IA3_CUDA(cudaMemsetAsync(&d.ctl->tie_count, 0, sizeof(int), st));
@@ -992,9 +1018,9 @@ int ia3_fit_first_ties(ia3_fit* f, int32_t* spot, int32_t* zxy, int64_t cap) {
   if (n > f->ties_prefetched) {
     if (reserve_pinned(&f->h_stage, &f->stage_cap, 2 * sizeof(int) * (size_t)n)) return -1;
     int* a = static_cast<int*>(f->h_stage);
-    if (small_copy(a, f->d_tie_spot, sizeof(int) * (size_t)n, f->s->stream) ||
-        small_copy(a + n, f->d_tie_k, sizeof(int) * (size_t)n, f->s->stream)) return -1;
-    IA3_CUDA(cudaStreamSynchronize(f->s->stream));
+    if (small_copy(a, f->d_tie_spot, sizeof(int) * (size_t)n, f->st) ||
+        small_copy(a + n, f->d_tie_k, sizeof(int) * (size_t)n, f->st)) return -1;
+    IA3_CUDA(cudaStreamSynchronize(f->st));
     sp = a; kk = a + n;
   }
   for (int64_t i = 0; i < n; ++i) {
@@ -1018,7 +1044,7 @@ int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
     if (dev_alloc((void**)&f->d_keep, (size_t)n)) return -1;
     f->keep_cap = (size_t)n;
   }
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   // the copy is asynchronous: the flags get a pinned buffer of their own, which nothing else writes
   if (reserve_pinned(&f->h_keep, &f->hkeep_cap, (size_t)n)) return -1;
   memcpy(f->h_keep, keep, (size_t)n);
@@ -1033,22 +1059,23 @@ int ia3_fit_first_resolve(ia3_fit* f, const uint8_t* keep, int64_t n) {
 // the host's look at the done flag, so the device never waits for the host; the rounds still queued
 // when the flag is seen find empty work lists.
 static int engine_run(ia3_fit* f, int phases, int sweep_cap) {
-  cudaStream_t st = f->s->stream, st2 = f->st2;
+  cudaStream_t st = f->st;
   const FitDev& d = f->d;
   if (f->n == 0) return 0;
   *(volatile int*)f->h_done() = 0;
   IA3_CUDA(cudaMemsetAsync(&d.ctl->done, 0, sizeof(int), st));
+  int rounds_done = 0;
   for (int chunk = 0;; ++chunk) {
     if (chunk > 100000) { set_error("fit engine did not finish"); return -1; }
     for (int r = 0; r < g_chunk; ++r) {
-      if (launch_sched(d, f->round, phases, sweep_cap, st)) return -1;
-      IA3_CUDA(cudaEventRecord(f->ev_s, st));
-      IA3_CUDA(cudaStreamWaitEvent(st2, f->ev_s, 0));
-      if (launch_fit_round(d, f->round, true, st2)) return -1;
-      IA3_CUDA(cudaEventRecord(f->ev_t, st2));
-      if (launch_fit_round(d, f->round, false, st)) return -1;
-      IA3_CUDA(cudaStreamWaitEvent(st, f->ev_t, 0));
+      // one stream per stack: with dozens of stacks in flight every extra stream shares a hardware queue
+      // with another stack's, and a cross-stream wait parked in such a queue holds that stack back too
+      const bool early = rounds_done < 2;
+      if (launch_sched(d, f->round, phases, sweep_cap, st) ||
+          launch_fit_round(d, f->round, true, early ? g_grid_team : g_grid_team_late, st) ||
+          launch_fit_round(d, f->round, false, early ? g_grid_bulk : g_grid_bulk_late, st)) return -1;
       ++f->round;
+      ++rounds_done;
     }
     IA3_CUDA(cudaEventRecord(f->ev_chunk[chunk & 1], st));
     if (chunk >= 1) {
@@ -1062,7 +1089,7 @@ static int engine_run(ia3_fit* f, int phases, int sweep_cap) {
 
 static int engine_start(ia3_fit* f) {
   if (f->started) return 0;
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   if (!f->prepared && ia3_fit_first_prepare(f, nullptr)) return -1;
   if (launch_engine_reset(f->d, st) || launch_member_stats(f->d, st) || launch_init_window(f->d, st)) return -1;
   f->started = true;
@@ -1070,7 +1097,7 @@ static int engine_start(ia3_fit* f) {
 }
 
 static int fetch_results(ia3_fit* f, const ia3_fit_out* o) {
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   const size_t n = (size_t)f->n;
   if (n == 0 || !o) return 0;
   // device -> pinned staging (copy kernels queued behind the rounds), one wait, then plain memcpy
@@ -1102,7 +1129,7 @@ int ia3_fit_run(ia3_fit* f, int phases, double min_delta_center, double max_delt
   if ((phases & 1) && f->first_done) phases &= ~1;
   if ((phases & 2) && !(phases & 1) && !f->first_done) { set_error("firstfit has not run"); return -1; }
   if ((phases & 1) && !f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   FitDev& d = f->d;
   if (phases & 1) d.delta_first = min_delta_center;
   if (phases & 2) {
@@ -1136,7 +1163,7 @@ int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active,
   IA3_STAT("ia3_fit_repeat_sweep");
   if (ensure_device()) return -1;
   if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   FitDev& d = f->d;
   const size_t n = (size_t)f->n;
   if (d.delta_repeat != delta_center && f->gsweep > 0) IA3_CUDA(cudaMemsetAsync(d.memo_valid, 0, std::max<size_t>(n, 1), st));
@@ -1165,7 +1192,7 @@ int ia3_fit_repeat_sweep(ia3_fit* f, double delta_center, const uint8_t* active,
 int ia3_fit_engine_stats(ia3_fit* f, int64_t* out, int cap) {
   if (ensure_device()) return -1;
   if (!f || !out) { set_error("null argument"); return -1; }
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   Scoped sc;
   void* h = nullptr;
   if (sc.halloc(&h, sizeof(EngineCtl))) return -1;
@@ -1175,6 +1202,14 @@ int ia3_fit_engine_stats(ia3_fit* f, int64_t* out, int cap) {
   std::vector<int64_t> v = {c.st_rounds, c.st_tasks, c.st_lm_runs, (int64_t)c.st_evals, c.st_memo_hits, c.st_spec_runs, c.st_spec_hits,
                             c.st_parked, c.st_team_tasks, c.n_bricks};
   for (int q = 0; q < 6; ++q) v.push_back((int64_t)c.prof[q]);                       // 10..15
+  if (getenv("IA3_LW_PROF")) {
+    unsigned long long lp[16];
+    if (lw_prof_read(lp) == 0) {
+      fprintf(stderr, "lm_warp cycles (process total): factor steps %llu, factor B0+store %llu, outer rest %llu, GN %llu, parl %llu, "
+                      "damped solve %llu (its Cholesky %llu) x %llu; factor calls %llu, propose calls %llu, team evals %llu\n", lp[0], lp[1], lp[2], lp[3], lp[4], lp[5], lp[6], lp[7],
+              lp[8], lp[9], (unsigned long long)c.prof[5]);
+    }
+  }
   const int nr = std::min(c.st_rounds, 512);
   for (int r = 0; r < nr; ++r) { v.push_back((int64_t)c.trace_work[r]); v.push_back((int64_t)c.trace_ns[r]); }   // 16 + 2 r
   for (int i = 0; i < cap; ++i) out[i] = i < (int)v.size() ? v[i] : -1;
@@ -1185,7 +1220,7 @@ int ia3_fit_get_volume(ia3_fit* f, int which, double* out) {
   if (ensure_device()) return -1;
   if (!f || !f->first_done) { set_error("firstfit has not run"); return -1; }
   if (!f->s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   Scoped sc;
   double* tmp = nullptr;
   if (sc.dalloc(&tmp, f->s->nvox * 8)) return -1;
@@ -1225,9 +1260,9 @@ int ia3_fit_get_rec(ia3_fit* f, int64_t i, double* rec, int32_t* zxy, int32_t* c
   if (!f || i < 0 || i >= f->n) { set_error("bad seed index"); return -1; }
   const int K = f->d.K;
   std::vector<double> full(K);
-  IA3_CUDA(cudaStreamSynchronize(f->s->stream));
-  IA3_CUDA(cudaMemcpyAsync(full.data(), f->d.rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost, f->s->stream));
-  IA3_CUDA(cudaStreamSynchronize(f->s->stream));
+  IA3_CUDA(cudaStreamSynchronize(f->st));
+  IA3_CUDA(cudaMemcpyAsync(full.data(), f->d.rec + (size_t)i * K, sizeof(double) * K, cudaMemcpyDeviceToHost, f->st));
+  IA3_CUDA(cudaStreamSynchronize(f->st));
   int m = 0;
   for (int k = 0; k < K; ++k) {
     int v[3];
@@ -1251,7 +1286,7 @@ int ia3_fit_num_levels(ia3_fit* f) {
   const size_t n = (size_t)f->n;
   const size_t pool = (size_t)std::max(f->h_ctl()->pool_o, 1);
   std::vector<int> ds(n), dc(n), di(pool);
-  cudaStream_t st = f->s->stream;
+  cudaStream_t st = f->st;
   if (cudaStreamSynchronize(st) != cudaSuccess ||
       cudaMemcpy(ds.data(), f->d.dep_start, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
       cudaMemcpy(dc.data(), f->d.dep_cnt, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||

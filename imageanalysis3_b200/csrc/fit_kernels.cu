@@ -18,6 +18,7 @@
 #include "ia3_device.h"
 #include "fit_kernels.h"
 #include "fit_spot.h"
+#include "lm_warp.h"
 
 namespace ia3 {
 
@@ -538,6 +539,18 @@ __device__ __forceinline__ double pass_cta(WarpExec& ex, SpotShared<double>& sh,
 
 // lmder, driven by warp 0; the other warps of the CTA only join the voxel passes.  Same control flow
 // as run_lm (fit_spot.h).  Returns true if the run was suspended after `cap` evaluations.
+#ifndef IA3_LM_WARP
+#define IA3_LM_WARP 1            // 1: register / shuffle algebra of lm_warp.h; 0: the generic shared-memory algebra of lm_core.h
+#endif
+#if IA3_LM_WARP
+#define LM_OUTER(ex, st, cfg, A, g) lw::outer(st, cfg, A, g)
+#define LM_PROPOSE(ex, st) lw::propose(st)
+#define LM_JUDGE(ex, st, cfg, fn) lw::judge(st, cfg, fn)
+#else
+#define LM_OUTER(ex, st, cfg, A, g) lm_outer(ex, st, cfg, A, g)
+#define LM_PROPOSE(ex, st) lm_propose(ex, st)
+#define LM_JUDGE(ex, st, cfg, fn) lm_judge(ex, st, cfg, fn)
+#endif
 #ifdef IA3_FIT_PROF
 #define PROF_T(v) const long long v = clock64()
 #define PROF_ADD(i, a, b) do { if (TW > 1 && threadIdx.x == 0) prof_acc[i] += (unsigned long long)((b) - (a)); } while (0)
@@ -570,7 +583,7 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
       int go = 1;
       __syncwarp();
       if (cap > 0 && st.nfev - nfev_entry >= cap) go = 2;
-      else if (!lm_outer(ex, st, cfg, sh.Ag, sh.Ag + NTRI)) go = 0;
+      else if (!LM_OUTER(ex, st, cfg, sh.Ag, sh.Ag + NTRI)) go = 0;
       if (ex.lane() == 0) cs.go = go;
     }
     cta_sync<TW>();
@@ -582,7 +595,7 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
     int action;
     for (;;) {
       PROF_T(t2);
-      if (warp == 0) lm_propose(ex, st);
+      if (warp == 0) LM_PROPOSE(ex, st);
       PROF_T(t3);
       if (warp == 0) build_consts_par<double>(ex, fp, cen, origin, st.xt, sh);
       cta_sync<TW>();
@@ -590,7 +603,7 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
       const double fn1 = pass_cta<TW>(ex, sh, vox, gram_w, part);     // lm_outer has consumed the old sums
       PROF_T(t5);
       if (warp == 0) {
-        const int a = lm_judge(ex, st, cfg, fn1);
+        const int a = LM_JUDGE(ex, st, cfg, fn1);
         if (ex.lane() == 0) cs.action = a;
       }
       cta_sync<TW>();
@@ -1026,6 +1039,16 @@ int launch_member_stats(const FitDev& d, cudaStream_t st) {
   return 0;
 }
 
+int lw_prof_read(unsigned long long* out16) {
+#ifdef IA3_FIT_PROF
+  IA3_CUDA(cudaMemcpyFromSymbol(out16, lw::g_lw_prof, sizeof(unsigned long long) * 16));
+  return 0;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  return 0;
+#endif
+}
+
 int launch_engine_reset(const FitDev& d, cudaStream_t st) {
   k_engine_init<<<(unsigned)((std::max<long long>(d.n, 1) + 255) / 256), 256, 0, st>>>(d);
   IA3_LAUNCH_CHECK();
@@ -1039,7 +1062,12 @@ int launch_sched(const FitDev& d, int round, int phases, int sweep_cap, cudaStre
   return 0;
 }
 
-int launch_fit_round(const FitDev& d, int round, bool team, cudaStream_t st) {
+// grid_hint: upper bound of the CTAs worth launching (the kernels claim tasks from a list until it is
+// empty, so any grid is correct).  A CTA that finds the list empty exits at once, but launching and
+// retiring it still occupies the GPU's work distributor, which every stack in flight shares: the first
+// rounds of a run (one task per seed) get a grid for the whole GPU, later rounds (a few % of the seeds)
+// a small one.
+int launch_fit_round(const FitDev& d, int round, bool team, int grid_hint, cudaStream_t st) {
   if (d.n == 0) return 0;
   constexpr int kMaxDynSmem = 227 * 1024 - 2048;
   const int smem1 = engine_smem_bytes(d.K, 1), smemT = engine_smem_bytes(d.K, TEAM_WARPS);
@@ -1054,13 +1082,9 @@ int launch_fit_round(const FitDev& d, int round, bool team, cudaStream_t st) {
       once_err = cudaFuncSetAttribute(k_fit_round<TEAM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   });
   IA3_CUDA(once_err);
-  if (team) {
-    const unsigned grid = (unsigned)std::min<long long>(2 * d.n, 148 * 2);
-    k_fit_round<TEAM_WARPS><<<grid, TEAM_WARPS * 32, smemT, st>>>(d, round);
-  } else {
-    const unsigned grid = (unsigned)std::min<long long>(2 * d.n, 148 * 16);
-    k_fit_round<1><<<grid, 32, smem1, st>>>(d, round);
-  }
+  const long long want = std::max<long long>(1, std::min<long long>(2 * d.n, grid_hint));
+  if (team) k_fit_round<TEAM_WARPS><<<(unsigned)want, TEAM_WARPS * 32, smemT, st>>>(d, round);
+  else k_fit_round<1><<<(unsigned)want, 32, smem1, st>>>(d, round);
   IA3_LAUNCH_CHECK();
   return 0;
 }

@@ -127,8 +127,9 @@ int launch_member_stats(const FitDev& d, cudaStream_t st);
 // one engine round.  phases: bit 0 firstfit (F, B), bit 1 repeatfit (R), bit 2 speculation (S);
 // sweep_cap: no R visit beyond this sweep number (host-driven sweep-by-sweep mode)
 int launch_sched(const FitDev& d, int round, int phases, int sweep_cap, cudaStream_t st);
-int launch_fit_round(const FitDev& d, int round, bool team, cudaStream_t st);
+int launch_fit_round(const FitDev& d, int round, bool team, int grid_hint, cudaStream_t st);
 int launch_engine_reset(const FitDev& d, cudaStream_t st);
+int lw_prof_read(unsigned long long* out16);    // IA3_FIT_PROF builds: cycle counters of lm_warp.h since process start
 
 struct MomentDev {                    // fast_fit_big_image / gfit_fast (Fitting_v4.py:433-556)
   const void* im; int im_dtype;

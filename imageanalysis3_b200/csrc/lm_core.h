@@ -52,6 +52,9 @@ struct LMState {
   int ipvt[NP];
   double fnorm, fnorm1, xnorm, delta, par, gnorm, pnorm;
   int iter, nfev, njev, info;
+  int pos[NP];         // lm_warp.h: position of column l in the pivot order (inverse of ipvt)
+  int nsing;           // lm_warp.h: first position with a zero pivot (NP if none)
+  int pad_;
 };
 
 IA3_HD double enorm_n(const double* v, int n) {

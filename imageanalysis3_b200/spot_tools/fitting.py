@@ -209,11 +209,9 @@ def _neighbor_slices(coord, crop_size, shape):
 # copies of the stack in HBM, and letting all of them seed at once only inflates the allocation pool
 # (cudaMalloc while other stacks' kernels run stalls every stream).
 _SEED_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_SEED_INFLIGHT", "6"))))
-# Stacks between "upload started" and "firstfit done" (they hold the 400 MB image in HBM and a place in
-# the upload queue).  repeatfit is a chain of short kernels separated by waits for a few long LM runs:
-# many stacks have to be in it at once to keep the GPU busy, but they need only their sparse work
-# volume -- so callers can keep 100+ stacks in flight while only this many are in the heavy front part.
-_ADMIT_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_ADMIT_INFLIGHT", "24"))))
+# Stacks between "upload started" and "fit done" (they hold their image in HBM and a place in the upload
+# queue): callers may keep more host threads than this in flight, the rest wait here.
+_ADMIT_GATE = threading.BoundedSemaphore(max(1, int(os.environ.get("IA3_ADMIT_INFLIGHT", "64"))))
 
 
 def fit_fov_image(im, channel, *args, **kwargs):
