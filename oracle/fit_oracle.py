@@ -300,10 +300,16 @@ def window(radius):
 
 
 def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_delta_center=2.5, n_max_iter=10,
-             max_dist_th=0.1, min_w=0.5, max_w=4., init_w=None, weight_sigma=0, do_repeat=True):
+             max_dist_th=0.1, min_w=0.5, max_w=4., init_w=None, weight_sigma=0, do_repeat=True,
+             origin=None, full_shape=None, tree=None, global_index=None):
     """firstfit (+ repeatfit) -> dict(ps=list, success, converged, n_iter, dists, first_ps, nfev_first, im_add,
     nfev_max / cond_max = per seed, the largest number of MINPACK function evaluations / Jacobian condition
-    number over its fits (inf if one of them ended with ier = 5), well_posed, comparable = see comparable_mask)."""
+    number over its fits (inf if one of them ended with ier = 5), well_posed, comparable = see comparable_mask).
+
+    origin / full_shape / tree / global_index (oracle/parallel.py): ``im`` is the crop of a larger stack starting at
+    ``origin``; coordinates stay those of the full stack (no arithmetic changes), windows are clipped against
+    ``full_shape``, firstfit's nearest-seed rule asks ``tree`` (built over ALL seeds of the stack) and compares with
+    ``global_index[i]``.  The seeds given must be closed under "windows can interact"."""
     if init_w is None:
         init_w = 1.5 if version == 4 else SIGMA_ZXY
     cen = np.asarray(centers_3xn).T
@@ -313,9 +319,14 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
             raise ValueError(f"{n} points have been seeded, exit.")
         raise AttributeError("'iter_fit_seed_points' object has no attribute 'im_subtr'")
     off = window(radius_fit)
-    shape = np.array(im.shape)[:, None]
+    org = np.zeros(3, dtype=np.int64) if origin is None else np.asarray(origin, dtype=np.int64)
+    shape = np.array(im.shape if full_shape is None else full_shape)[:, None]
     work = np.array(im, dtype=float)
-    tree = cKDTree(cen) if version == 4 else None
+    if version == 4 and tree is None:
+        tree = cKDTree(cen)
+    gidx = np.arange(n) if global_index is None else np.asarray(global_index)
+    if origin is not None and version != 4:
+        raise ValueError("crops are supported for the v4 nearest-seed rule only")
     mk = lambda v, X, c, d: _Problem(v, X, c, version, d, min_w, max_w, init_w, weight_sigma)
     ps, cfit, ok_l, recs, nfevs, conds = [], [], [], [], [], []
     coarse = np.zeros(n, dtype=bool)               # a fit of this seed ended with a last step > the tolerance
@@ -325,16 +336,19 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
         v = off + np.array([int(c[0]), int(c[1]), int(c[2])])[:, None]
         return v[:, ((v >= 0) & (v < shape)).all(0)]
 
+    def at(a, v):                                  # a[v] with v in full-stack coordinates
+        return a[v[0] - org[0], v[1] - org[1], v[2] - org[2]]
+
     for i, c in enumerate(cen):
         full = ball(c)
         if version == 4:
             _, nn = tree.query(full.T, distance_upper_bound=radius_fit * 2)
-            mine = full[:, nn == i]
+            mine = full[:, nn == gidx[i]]
         else:
             near = np.argmin(cdist(full.T, cen), axis=-1)
             me = np.argmin(cdist([c], cen)[0, :])
             mine = full[:, near == me]
-        pr = mk(im[mine[0], mine[1], mine[2]], mine, [c[0], c[1], c[2]], min_delta_center)
+        pr = mk(at(im, mine), mine, [c[0], c[1], c[2]], min_delta_center)
         ok, nat, q, nfev, _ = pr.solve()
         ok_l.append(ok)
         nfevs.append(nfev)
@@ -345,7 +359,7 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
             coarse[i] = True
         if ok:
             rec = pr.gauss(q, full)
-            work[full[0], full[1], full[2]] -= rec
+            work[full[0] - org[0], full[1] - org[1], full[2] - org[2]] -= rec
             ps.append(nat); cfit.append(nat[1:4]); recs.append(rec)
         else:
             ps.append([np.nan] * 11); cfit.append([np.nan] * 3); recs.append(np.nan)
@@ -362,7 +376,7 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
             if done[i]:
                 continue
             full = ball(c)
-            vals = work[full[0], full[1], full[2]]
+            vals = at(work, full)
             if ok_old[i]:
                 vals = recs[i] + vals
             pr = mk(vals, full, [c[0], c[1], c[2]], max_delta_center)
@@ -379,7 +393,7 @@ def iter_fit(im, centers_3xn, version=4, radius_fit=5, min_delta_center=1., max_
             if ok:
                 rec = pr.gauss(q)
                 ps[i], cfit[i], recs[i] = nat, nat[1:4], rec
-                work[full[0], full[1], full[2]] = vals - rec
+                work[full[0] - org[0], full[1] - org[1], full[2] - org[2]] = vals - rec
         both = (np.array(ok_l) & ok_old) > 0
         dists[~both] = 0
         dists[both] = np.sum((cf_old[both] - np.array(cfit)[both]) ** 2, axis=-1)
@@ -436,14 +450,20 @@ def local_backgrounds(im, spots, fit_radius=5, **background_args):
 
 def fit_fov_image_oracle(im, th_seed=300, max_num_seeds=500, fit_radius=5, remove_boundary_points=True,
                          seed_backend="scipy", seeds=None, normalize_background=False, normalize_local=False,
-                         background_args={}, **seed_kw):
-    """spot_tools/fitting.py:169-262."""
+                         background_args={}, procs=1, **seed_kw):
+    """spot_tools/fitting.py:169-262.  procs > 1: the fits of independent groups of seeds run in a process
+    pool (oracle/parallel.py; same results, the reference's loop is sequential only where windows interact)."""
     if seeds is None:
         seeds = seed_oracle.get_seeds_oracle(im, max_num_seeds=max_num_seeds, th_seed=float(th_seed),
                                              backend=seed_backend, **seed_kw)
     if len(seeds) == 0:
         return np.array([]), seeds
-    res = iter_fit(im, seeds.T, version=4, radius_fit=fit_radius)
+    if procs > 1:
+        from . import parallel
+        res = parallel.iter_fit_parallel(im, seeds.T, procs=procs, radius_fit=fit_radius)
+    else:
+        res = iter_fit(im, seeds.T, version=4, radius_fit=fit_radius)
+    fit_fov_image_oracle.last_result = res
     spots = np.array(res['ps'])
     ok = np.sum(np.isnan(spots), axis=1) == 0
     spots, cmp_ok = spots[ok], res['comparable'][ok]

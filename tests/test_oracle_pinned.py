@@ -176,3 +176,21 @@ def test_reference_sensitivity_probe_flags_slow_crawls():
     # the probe on its own: seed 583's slowest fit moves by > 1e-4 under the one-ulp perturbation
     sig = np.array([np.asarray(r, float) for r in o["ps"]])[583, 5:8]
     assert (np.abs(sig - 4.0) < 1e-3).any()
+
+
+def test_parallel_oracle_equals_sequential():
+    """oracle/parallel.py (independent groups of seeds over a process pool, used for the full-size GPU parity
+    tests) gives exactly the sequential oracle's numbers"""
+    from imageanalysis3_b200.synth import synth
+    from oracle import parallel
+    im = synth((30, 256, 256), 120, 17)
+    seeds = seed_oracle.get_seeds_oracle(im, th_seed=300, backend="c")
+    a = fit_oracle.iter_fit(im, seeds.T, version=4)
+    b = parallel.iter_fit_parallel(im, seeds.T, procs=2)
+    assert b["n_components"] > 20
+    pa = np.array([np.asarray(r, dtype=np.float64) for r in a["ps"]])
+    pb = np.array([np.asarray(r, dtype=np.float64) for r in b["ps"]])
+    assert np.array_equal(pa, pb, equal_nan=True)
+    assert a["n_iter"] == b["n_iter"]
+    for k in ("converged", "comparable", "dists", "nfev_max"):
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
