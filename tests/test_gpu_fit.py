@@ -112,7 +112,8 @@ def test_dense_overlapping_spots_keep_sequential_semantics(lib):
     f.firstfit()
     assert f._h.num_levels >= 3
     cmp_ok = o["comparable"]
-    assert cmp_ok.mean() > 0.8       # 8x denser than BASELINE's dense config: a tenth of the blobs crawl
+    assert cmp_ok.mean() > 0.6       # 8x denser than BASELINE's dense config: a tenth of the blobs crawl and take their
+                                     # direct window neighbours out of the tolerance comparison
     assert_spots_close(f.ps, o["first_ps"], "dense firstfit", cmp_ok)
     if cmp_ok.all():
         assert np.allclose(f.im_subtr, o["im_subtr"], rtol=0, atol=1e-6)
