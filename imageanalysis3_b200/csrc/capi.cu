@@ -645,7 +645,8 @@ int ia3_seed_run(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, i
   if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
   if (s->dtype == IA3_DTYPE_U16) return seed_run_t<uint16_t>(s, cfg, n_candidates, t);
   if (s->dtype == IA3_DTYPE_F32) return seed_run_t<float>(s, cfg, n_candidates, t);
-  set_error("seed stage supports uint16 and float32 stacks");
+  if (s->dtype == IA3_DTYPE_F64) return seed_run_t<double>(s, cfg, n_candidates, t);
+  set_error("bad stack dtype");
   return -1;
 }
 

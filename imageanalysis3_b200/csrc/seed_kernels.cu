@@ -36,6 +36,10 @@ template <> __device__ __forceinline__ uint16_t store_cast<uint16_t>(double acc)
   return (uint16_t)__double2int_rz(acc);   // C cast double -> npy_uint16: truncation
 }
 template <> __device__ __forceinline__ float store_cast<float>(double acc) { return __double2float_rn(acc); }
+template <> __device__ __forceinline__ double store_cast<double>(double acc) { return acc; }   // float64 stacks: no rounding between passes
+// shared-memory tile element of the general kernel: float holds uint16 / float32 inputs exactly
+template <typename Tin> struct TileOf { using type = float; };
+template <> struct TileOf<double> { using type = double; };
 
 constexpr size_t kMaxDynSmem = 227 * 1024;   // opt-in maximum per CTA on sm_100a
 constexpr int LINES = 128;   // lines per block = threads per block
@@ -47,12 +51,14 @@ template <int R, typename Tin, bool INNER1>
 __global__ void __launch_bounds__(LINES, 2)
 k_gauss_axis(const Tin* __restrict__ in, Tin* __restrict__ out, int L, long long inner, long long n_lines,
              int TL, GaussW gw) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw_g[];
+  using TileT = typename TileOf<Tin>::type;
+  TileT* smem = reinterpret_cast<TileT*>(smem_raw_g);
   constexpr int CH = (R > 32) ? 4 : CHMAX;
   const int r = (R > 0) ? R : gw.r;
   const int span = TL + 2 * r;
   const int pitch = span | 1;
-  float* tile = smem;
+  TileT* tile = smem;
   const int tid = threadIdx.x;
   const int a0 = blockIdx.y * TL;
   const long long l0 = (long long)blockIdx.x * LINES;
@@ -68,11 +74,11 @@ k_gauss_axis(const Tin* __restrict__ in, Tin* __restrict__ out, int L, long long
     if (interior) {
       const Tin* s2 = src + (long long)(a0 - r) * inner;
 #pragma unroll 4
-      for (int a = 0; a < span; ++a) tile[tid * pitch + a] = ok ? (float)s2[(long long)a * inner] : 0.f;
+      for (int a = 0; a < span; ++a) tile[tid * pitch + a] = ok ? (TileT)s2[(long long)a * inner] : (TileT)0;
     } else {
       for (int a = 0; a < span; ++a) {
         const int sidx = reflect_idx(a0 - r + a, L);
-        tile[tid * pitch + a] = ok ? (float)src[(long long)sidx * inner] : 0.f;
+        tile[tid * pitch + a] = ok ? (TileT)src[(long long)sidx * inner] : (TileT)0;
       }
     }
   } else {
@@ -82,9 +88,9 @@ k_gauss_axis(const Tin* __restrict__ in, Tin* __restrict__ out, int L, long long
       if (l >= n_lines) break;
       const Tin* row = in + l * (long long)L;
       if (interior) {
-        for (int a = lane; a < span; a += 32) tile[ll * pitch + a] = (float)row[a0 - r + a];
+        for (int a = lane; a < span; a += 32) tile[ll * pitch + a] = (TileT)row[a0 - r + a];
       } else {
-        for (int a = lane; a < span; a += 32) tile[ll * pitch + a] = (float)row[reflect_idx(a0 - r + a, L)];
+        for (int a = lane; a < span; a += 32) tile[ll * pitch + a] = (TileT)row[reflect_idx(a0 - r + a, L)];
       }
     }
     ok = (l0 + tid) < n_lines;
@@ -95,7 +101,7 @@ k_gauss_axis(const Tin* __restrict__ in, Tin* __restrict__ out, int L, long long
   Tin* otile = reinterpret_cast<Tin*>(smem + LINES * pitch);
   const int opitch = (sizeof(Tin) == 2) ? (TL + 2) : (TL + 1);
 
-  const float* my = tile + tid * pitch;
+  const TileT* my = tile + tid * pitch;
   const int nvalid = ok ? min(TL, L - a0) : 0;
   for (int c = 0; c < nvalid; c += CH) {
     double acc[CH];
@@ -113,7 +119,7 @@ k_gauss_axis(const Tin* __restrict__ in, Tin* __restrict__ out, int L, long long
     } else {
 #pragma unroll
       for (int o = 0; o < CH; ++o) {
-        const float* ctr = my + c + o + r;
+        const TileT* ctr = my + c + o + r;
         double a = __dmul_rn((double)ctr[0], gw.w[0]);
         for (int j = r; j >= 1; --j) a = __dadd_rn(a, __dmul_rn(__dadd_rn((double)ctr[-j], (double)ctr[j]), gw.w[j]));
         acc[o] = a;
@@ -633,10 +639,10 @@ template <int R, typename Tin, bool INNER1>
 static int launch_axis(const Tin* in, Tin* out, int L, long long inner, long long n_lines, const GaussW& gw,
                        cudaStream_t st) {
   const int r = (R > 0) ? R : gw.r;
-  int TL = 64;
+  int TL = (sizeof(Tin) == 8 && r > 32) ? 32 : 64;          // float64 tiles are twice as large
   if (L < TL) TL = ((L + CHMAX - 1) / CHMAX) * CHMAX;
   const int span = TL + 2 * r, pitch = span | 1;
-  size_t smem = (size_t)LINES * pitch * sizeof(float);
+  size_t smem = (size_t)LINES * pitch * sizeof(typename TileOf<Tin>::type);
   if (INNER1) smem += (size_t)LINES * (TL + 2) * sizeof(Tin);
   auto kern = k_gauss_axis<R, Tin, INNER1>;
   // always the same (maximum) value: concurrent host threads launch the same instantiation with
@@ -706,6 +712,7 @@ int gaussian_filter_exact(const Tin* in, Tin* bufA, Tin* bufB, int Z, int X, int
 }
 template int gaussian_filter_exact<uint16_t>(const uint16_t*, uint16_t*, uint16_t*, int, int, int, const GaussW&, cudaStream_t);
 template int gaussian_filter_exact<float>(const float*, float*, float*, int, int, int, const GaussW&, cudaStream_t);
+template int gaussian_filter_exact<double>(const double*, double*, double*, int, int, int, const GaussW&, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------
 // Rank filters + candidate mask.  scipy's maximum_filter/minimum_filter(size=s) with reflect
@@ -744,7 +751,18 @@ __device__ __forceinline__ void load10<float>(const float* row, int y0, int Y, b
   }
 }
 
+template <>
+__device__ __forceinline__ void load10<double>(const double* row, int y0, int Y, bool vec, double* v) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) v[i] = row[min(max(y0 - 1 + i, 0), Y - 1)];
+}
+
 template <typename Tin> struct DiffT;
+template <> struct DiffT<double> {
+  // spot_tools/fitting.py:106: float32(max_im) - float32(min_im)
+  static __device__ __forceinline__ double diff(double a, double b) { return (double)__fsub_rn(__double2float_rn(a), __double2float_rn(b)); }
+  static __device__ __forceinline__ bool nonzero(double a) { return a != 0.0; }
+};
 template <> struct DiffT<uint16_t> {
   static __device__ __forceinline__ double diff(uint16_t a, uint16_t b) { return (double)((int)a - (int)b); }
   static __device__ __forceinline__ bool nonzero(uint16_t a) { return a != 0; }
@@ -1108,8 +1126,10 @@ int seed_emit(const Tin* fg, const Tin* bg, const SeedDims& d, int variant, cons
 }
 template int seed_flags<uint16_t>(const uint16_t*, const uint16_t*, const SeedDims&, int, uint8_t*, int*, long long*, cudaStream_t);
 template int seed_flags<float>(const float*, const float*, const SeedDims&, int, uint8_t*, int*, long long*, cudaStream_t);
+template int seed_flags<double>(const double*, const double*, const SeedDims&, int, uint8_t*, int*, long long*, cudaStream_t);
 template int seed_emit<uint16_t>(const uint16_t*, const uint16_t*, const SeedDims&, int, const uint8_t*, const long long*, int32_t*, float*, cudaStream_t);
 template int seed_emit<float>(const float*, const float*, const SeedDims&, int, const uint8_t*, const long long*, int32_t*, float*, cudaStream_t);
+template int seed_emit<double>(const double*, const double*, const SeedDims&, int, const uint8_t*, const long long*, int32_t*, float*, cudaStream_t);
 
 int seed_flag_threads() { return FLAG_THREADS; }
 
