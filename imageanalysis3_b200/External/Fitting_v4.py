@@ -113,3 +113,123 @@ def fast_fit_big_image(im, centers_zxy, radius_fit=4, avoid_neigbors=True, recen
     rows = iter(_lib.gaussfit_batch(cfg, 2.5, vals, coords, np.array(cens).reshape(-1, 3))[0]) if vals else iter(())
     ps = [np.array([np.nan] * 11) if e else next(rows) for e in empty]
     return np.array(ps)
+
+
+# ---- the remaining public names of the reference module -----------------------------
+def _cov_matrices(t, p, w_1, w_2, w_3):
+    """inverse covariance of the rotated Gaussian with sin(theta) = t, sin(phi) = p and widths w_i"""
+    t2, p2 = t * t, p * p
+    ct2, cp2 = 1 - t2, 1 - p2
+    ct, cp = np.sqrt(ct2), np.sqrt(cp2)
+    s1, s2, s3 = 1. / (w_1 * w_1), 1. / (w_2 * w_2), 1. / (w_3 * w_3)
+    a = cp2 * ct2 * s1 + t2 * s2 + p2 * ct2 * s3
+    b = cp2 * t2 * s1 + ct2 * s2 + p2 * t2 * s3
+    c = p2 * s1 + cp2 * s3
+    d = ct * t * (cp2 * s1 - s2 + p2 * s3)
+    e = p * cp * ct * (s3 - s1)
+    f = p * cp * t * (s3 - s1)
+    return a, b, c, d, e, f
+
+
+def _adjugate_over_det(a, b, c, d, e, f):
+    det = a * b * c - c * d ** 2 - b * e ** 2 + 2 * d * e * f - a * f ** 2
+    adj = np.array([[b * c - f ** 2, -(c * d) + e * f, -(b * e) + d * f],
+                    [-(c * d) + e * f, a * c - e ** 2, d * e - a * f],
+                    [-(b * e) + d * f, d * e - a * f, a * b - d ** 2]])
+    return adj, det
+
+
+def to_sigmas(t, p, w_1, w_2, w_3):
+    """covariance matrix and its inverse from t = sin(theta), p = sin(phi) and the three widths
+    (External/Fitting_v4.py:685-704) -> (sigma, sigma_inv)"""
+    a, b, c, d, e, f = _cov_matrices(t, p, w_1, w_2, w_3)
+    adj, det = _adjugate_over_det(a, b, c, d, e, f)
+    return adj / det, np.array([[a, d, e], [d, b, f], [e, f, c]])
+
+
+def to_sigmas_abc(a, b, c, d, e, f):
+    """(sigma, sigma_inv, det) of the symmetric matrix [[a, d, e], [d, b, f], [e, f, c]] (:705-710)"""
+    adj, det = _adjugate_over_det(a, b, c, d, e, f)
+    adj = np.array([[b * c - f * f, -(c * d) + e * f, -(b * e) + d * f], [-(c * d) + e * f, a * c - e * e, d * e - a * f],
+                    [-(b * e) + d * f, d * e - a * f, a * b - d * d]])
+    return np.array([[a, d, e], [d, b, f], [e, f, c]]), adj / det, det
+
+
+def gfit_fast(im_, X_, bk_f=0.1, reconstruct=False, plt_val=False, compare_with_fitting=False):
+    """Moment estimate of ONE spot from its voxel values im_ (m,) and coordinates X_ (3, m) (:433-491, without the
+    matplotlib branches) -> [h, z, x, y, background, cov_zz, cov_xx, cov_yy, cov_zx, cov_zy, cov_xy, eps].
+    A few hundred numbers: plain numpy, like the reference; whole seed lists go through fast_fit_big_image (device)."""
+    if plt_val:
+        raise NotImplementedError("plt_val=True only draws matplotlib figures in the reference")
+    out = np.array([np.nan] * 12)
+    if len(im_) == 0:
+        return out
+    X_ = np.asarray(X_)
+    bk = np.sort(im_)[int(len(im_) * bk_f)]
+    wts = im_ - bk
+    wts[wts < 0] = 0
+    h = np.max(wts)
+    wts = wts / np.sum(wts)
+    mu = np.sum(X_ * wts, -1)
+    dev = X_.T - mu
+    cov = np.sum(np.array([[dev[:, i] * dev[:, j] for i in range(3)] for j in range(3)]) * wts, -1)
+    [[a, d, e], [d, b, f], [e, f, c]] = cov
+    eps = np.nan
+    if reconstruct:
+        icov = inv_sigma(cov)
+        model = h * np.exp(-np.sum(np.dot(dev, icov) * dev, -1) * 0.5) + bk
+        eps = np.mean(np.abs(im_ - model))
+    return np.array([h, mu[0], mu[1], mu[2], bk, a, b, c, d, e, f, eps])
+
+
+def gker(gaus=[3, 3, 3], exp=8):
+    """normalised float32 outer product of scipy.signal.windows.gaussian(int(g * exp), g) (:11-16)"""
+    from scipy.signal.windows import gaussian
+    sz = [int(g * exp) for g in gaus]
+    k = np.outer(np.outer(gaussian(sz[0], gaus[0]), gaussian(sz[1], gaus[1])), gaussian(sz[2], gaus[2])).reshape(sz)
+    return (k / np.sum(k)).astype(np.float32)
+
+
+def fft_gaussian_fast(arr, gaus=[3, 3, 3], exp=8):
+    """Gaussian blur of the reference's FFT path (:66-70: reflect() padding, 'valid' convolution with gker) evaluated
+    on the device as three direct FP64 passes.  The reference multiplies single-precision FFTs, so the two agree to
+    ~1e-6 relative, not bit for bit."""
+    from .. import _lib
+    st = _lib.Stack(np.asarray(arr))
+    out = st.fft_gaussian(gaus, exp)
+    st.close()
+    return out
+
+
+def _sorted_centers(shape, idx, h, max_num):
+    z, x, y = np.unravel_index(idx, shape)
+    order = np.argsort(h)[::-1]
+    cen = np.array([z[order], x[order], y[order], h[order]])
+    return cen[:, :max_num] if max_num is not None else cen
+
+
+def get_seed_points_base(im_sm, gfilt_size=5, filt_size=3, th_seed=3., max_num=None):
+    """Seeds of the log-ratio image log(im) - log(fft_gaussian_fast(im, [gfilt_size] * 3)): local maxima within
+    filt_size that stand th_seed standard deviations out (:72-92) -> ((4, N) [z, x, y, h] brightest first, std)."""
+    from .. import _lib
+    st = _lib.Stack(np.asarray(im_sm))
+    idx, h, std = st.seed_logratio(gfilt_size, filt_size, th_seed)
+    st.close()
+    return _sorted_centers(np.shape(im_sm), idx, h, max_num), std
+
+
+def get_seed_points_base_v2(im_sm, gfilt_size=5, filt_size=3, th_seed=3., max_num=None):
+    """Seeds of im - cv2.blur(im, (gfilt_size, gfilt_size)) per slice: voxels above th_seed standard deviations that
+    are >= their filt_size^3 neighbours, neighbours taken modulo the shape (:95-126) -> ((4, N) float32 [z, x, y, h]
+    brightest first, std).  The blur is bit-identical to cv2's; std is reduced in FP64 on the device (numpy: float32
+    pairwise), which moves the cutoff by ~1e-7 relative."""
+    from .. import _lib
+    if gfilt_size == 0:
+        raise NotImplementedError("gfilt_size=0 (no normalisation) is not available on the device")
+    st = _lib.Stack(np.asarray(im_sm))
+    idx, h, std = st.seed_v2(gfilt_size, filt_size, th_seed)
+    st.close()
+    z, x, y = np.unravel_index(idx, np.shape(im_sm))
+    order = np.argsort(h)[::-1]
+    cen = np.array([z[order], x[order], y[order], h[order]])       # int64 and float32 rows -> float64, like the reference
+    return (cen[:, :max_num] if max_num is not None else cen), std

@@ -27,7 +27,7 @@ class SeedCfg(C.Structure):
     _fields_ = [("w_fg", C.POINTER(C.c_double)), ("r_fg", C.c_int),
                 ("w_bg", C.POINTER(C.c_double)), ("r_bg", C.c_int),
                 ("filt_size", C.c_int), ("variant", C.c_int),
-                ("edge", C.c_double), ("h_min", C.c_double)]
+                ("edge", C.c_double), ("h_min", C.c_double), ("two_d", C.c_int)]
 
 
 class SeedTiming(C.Structure):
@@ -57,6 +57,7 @@ EXPORTS = [
     "ia3_timer_start", "ia3_timer_stop",
     "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
     "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_seed_gather_volume", "ia3_box_background",
+    "ia3_seed_v2", "ia3_fft_gaussian", "ia3_seed_logratio", "ia3_stack_histogram",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
     "ia3_fit_first_resolve", "ia3_fit_run", "ia3_fit_first_run", "ia3_fit_repeat_sweep", "ia3_fit_engine_stats", "ia3_fit_get_volume",
     "ia3_fit_get_rec", "ia3_fit_num_levels", "ia3_fit_last_ms", "ia3_gaussfit_batch", "ia3_gauss_eval", "ia3_moment_fit",
@@ -100,6 +101,10 @@ def load():
     lib.ia3_seed_fetch_volume.argtypes = [vp, i32, vp]
     lib.ia3_seed_gather_volume.argtypes = [vp, i32, vp, i64, vp]
     lib.ia3_box_background.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.ia3_stack_histogram.argtypes = [vp, vp]
+    lib.ia3_seed_v2.argtypes = [vp, i32, i32, dbl, P(dbl), vp, vp, i64, P(i64)]
+    lib.ia3_fft_gaussian.argtypes = [vp, vp, i32, vp]
+    lib.ia3_seed_logratio.argtypes = [vp, dbl, i32, dbl, P(dbl), vp, vp, i64, P(i64)]
     lib.ia3_fit_create.argtypes = [vp, vp, i64, P(FitCfg), P(vp)]
     lib.ia3_fit_destroy.argtypes = [vp]
     lib.ia3_fit_first_prepare.argtypes = [vp, P(i64)]
@@ -200,7 +205,7 @@ class Stack:
         _check(load().ia3_stack_trim(self._h, int(what)))
 
     # ---- seed stage --------------------------------------------------------------------------
-    def seed_candidates(self, w_fg, w_bg, filt_size, variant, edge, h_min):
+    def seed_candidates(self, w_fg, w_bg, filt_size, variant, edge, h_min, two_d=False):
         """Runs the device seed stage; returns (zxy int32 (n,3) in C order, h float32 (n,), timing)."""
         lib = load()
         cfg = SeedCfg()
@@ -219,6 +224,7 @@ class Stack:
         cfg.variant = int(variant)
         cfg.edge = float(edge)
         cfg.h_min = float(h_min)
+        cfg.two_d = int(bool(two_d))
         n = C.c_int64(0)
         t = SeedTiming()
         _check(lib.ia3_seed_run(self._h, C.byref(cfg), C.byref(n), C.byref(t)))
@@ -246,6 +252,54 @@ class Stack:
         cfg = MomentCfg(int(radius), int(bool(avoid_neighbors)), int(bool(recenter)), float(bk_f))
         _check(load().ia3_moment_fit(self._h, _ptr(cen), len(cen), C.byref(cfg), _ptr(out)))
         _count("h2d", cen.nbytes)
+        _count("d2h", out.nbytes)
+        return out
+
+    def histogram(self):
+        """counts of every uint16 value (65536,) uint64"""
+        out = np.zeros(65536, dtype=np.uint64)
+        _check(load().ia3_stack_histogram(self._h, _ptr(out)))
+        _count("d2h", out.nbytes)
+        return out
+
+    def seed_v2(self, gfilt_size, filt_size, th_seed):
+        """Fitting_v4.get_seed_points_base_v2 on the device -> (flat C-order indices, im_norm values, std), in C order"""
+        cap = 1 << 20
+        while True:
+            idx = np.empty(cap, dtype=np.int64)
+            h = np.empty(cap, dtype=np.float32)
+            std, n = C.c_double(0), C.c_int64(0)
+            rc = load().ia3_seed_v2(self._h, int(gfilt_size), int(filt_size), float(th_seed), C.byref(std), _ptr(idx), _ptr(h), cap, C.byref(n))
+            if rc == -2 and cap < (1 << 24):
+                cap = 1 << 24
+                continue
+            _check(rc)
+            break
+        order = np.argsort(idx[:n.value], kind="stable")
+        _count("d2h", 12 * n.value)
+        return idx[:n.value][order], h[:n.value][order], np.float32(std.value)
+
+    def seed_logratio(self, gfilt_size, filt_size, th_seed):
+        """Fitting_v4.get_seed_points_base on the device -> (flat indices, im_diff values, std), in C order"""
+        cap = 1 << 20
+        while True:
+            idx = np.empty(cap, dtype=np.int64)
+            h = np.empty(cap, dtype=np.float64)
+            std, n = C.c_double(0), C.c_int64(0)
+            rc = load().ia3_seed_logratio(self._h, float(gfilt_size), int(filt_size), float(th_seed), C.byref(std), _ptr(idx), _ptr(h), cap, C.byref(n))
+            if rc == -2 and cap < (1 << 24):
+                cap = 1 << 24
+                continue
+            _check(rc)
+            break
+        order = np.argsort(idx[:n.value], kind="stable")
+        _count("d2h", 16 * n.value)
+        return idx[:n.value][order], h[:n.value][order], float(std.value)
+
+    def fft_gaussian(self, gaus, exp=8):
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gaus, dtype=np.float64), (3,)))
+        out = np.empty(self.shape, dtype=np.float64)
+        _check(load().ia3_fft_gaussian(self._h, _ptr(g), int(exp), _ptr(out)))
         _count("d2h", out.nbytes)
         return out
 

@@ -19,6 +19,7 @@
 #include "fit_spot.h"
 #include "ia3_device.h"
 #include "seed_kernels.h"
+#include "aux_kernels.h"
 
 namespace ia3 {
 
@@ -584,7 +585,7 @@ static int seed_run_t(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidat
     memset(&gw, 0, sizeof(gw));
     gw.r = r;
     for (int j = 0; j <= r; ++j) gw.w[j] = w[j];
-    if (gaussian_filter_exact<Tin>(im, reinterpret_cast<Tin*>(*buf), reinterpret_cast<Tin*>(s->scratch), s->Z, s->X, s->Y, gw, st)) return -1;
+    if (gaussian_filter_exact<Tin>(im, reinterpret_cast<Tin*>(*buf), reinterpret_cast<Tin*>(s->scratch), s->Z, s->X, s->Y, gw, st, cfg->two_d != 0)) return -1;
     *fin = *buf;
     return 0;
   };
@@ -603,7 +604,8 @@ static int seed_run_t(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidat
   d.s1 = d.fs / 2; d.s2 = d.fs - d.s1 - 1;
   d.edge_on = (cfg->variant == 0 && cfg->edge > 0) ? 1 : 0;
   d.lo = (int)std::ceil(cfg->edge);
-  d.hiZ = (int)std::floor((double)s->Z - cfg->edge);
+  d.loZ = cfg->two_d ? -(1 << 30) : d.lo;
+  d.hiZ = cfg->two_d ? (1 << 30) : (int)std::floor((double)s->Z - cfg->edge);
   d.hiX = (int)std::floor((double)s->X - cfg->edge);
   d.hiY = (int)std::floor((double)s->Y - cfg->edge);
   d.h_min = cfg->h_min;
@@ -643,6 +645,7 @@ int ia3_seed_run(ia3_stack* s, const ia3_seed_cfg* cfg, int64_t* n_candidates, i
   if (ensure_device()) return -1;
   if (!s || !cfg) { set_error("null argument"); return -1; }
   if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (cfg->two_d && s->Z != 1) { set_error("two_d: the image must be held as a one-plane stack"); return -1; }
   if (s->dtype == IA3_DTYPE_U16) return seed_run_t<uint16_t>(s, cfg, n_candidates, t);
   if (s->dtype == IA3_DTYPE_F32) return seed_run_t<float>(s, cfg, n_candidates, t);
   if (s->dtype == IA3_DTYPE_F64) return seed_run_t<double>(s, cfg, n_candidates, t);
@@ -1304,6 +1307,165 @@ int ia3_fit_num_levels(ia3_fit* f) {
   return nl;
 }
 float ia3_fit_last_ms(ia3_fit* f) { return f ? f->last_ms : 0.f; }
+
+// ---- alternative seeders of Fitting_v4 (a12) ----------------------------------------------------
+}  // extern "C"
+
+// np.std(volume) in FP64: two passes (mean, then squared deviations)
+template <typename T>
+static int volume_std(const T* v, long long n, double* d_acc, void* h_pin, cudaStream_t st, double* mean_out, double* std_out) {
+  double* h = static_cast<double*>(h_pin);
+  if (launch_moments<T>(v, n, 0.0, d_acc, st) || small_copy(h, d_acc, 16, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  const double mean = h[0] / (double)n;
+  if (launch_moments<T>(v, n, mean, d_acc, st) || small_copy(h, d_acc, 16, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  *mean_out = mean;
+  *std_out = std::sqrt(h[1] / (double)n);
+  return 0;
+}
+
+template <typename Tin>
+static int fft_gaussian_dev(ia3_stack* s, const double* gaus, int expo, double* d_a, double* d_b, Scoped& sc) {
+  // gker (Fitting_v4.py:11-16): outer product of scipy.signal.gaussian(int(g * exp), g) windows over its sum
+  cudaStream_t st = s->stream;
+  const Tin* im = reinterpret_cast<const Tin*>(s->d_im);
+  const int dims[3] = {s->Z, s->X, s->Y};
+  for (int a = 0; a < 3; ++a) {
+    const int nt = (int)(gaus[a] * expo);
+    if (nt < 2 || nt > 4096 || nt / 2 > dims[a]) { set_error("fft_gaussian: window does not fit the stack"); return -1; }
+    std::vector<double> w(nt);
+    double sum = 0.0;
+    for (int k = 0; k < nt; ++k) { const double x = k - (nt - 1) / 2.0; w[k] = std::exp(-0.5 * (x / gaus[a]) * (x / gaus[a])); sum += w[k]; }
+    for (double& v : w) v /= sum;
+    void* h = nullptr; double* d_w = nullptr;
+    if (sc.halloc(&h, sizeof(double) * nt) || sc.dalloc(&d_w, sizeof(double) * nt)) return -1;
+    memcpy(h, w.data(), sizeof(double) * nt);
+    if (small_copy(d_w, h, sizeof(double) * nt, st)) return -1;
+    int rc;
+    if (a == 0) rc = launch_fir_axis<Tin>(im, d_a, s->Z, s->X, s->Y, 0, d_w, nt, st);
+    else if (a == 1) rc = launch_fir_axis<double>(d_a, d_b, s->Z, s->X, s->Y, 1, d_w, nt, st);
+    else rc = launch_fir_axis<double>(d_b, d_a, s->Z, s->X, s->Y, 2, d_w, nt, st);
+    if (rc) return -1;
+  }
+  return 0;          // result in d_a
+}
+
+extern "C" {
+
+int ia3_stack_histogram(ia3_stack* s, uint64_t* counts) {
+  if (ensure_device()) return -1;
+  if (!s || !counts) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (s->dtype != IA3_DTYPE_U16) { set_error("ia3_stack_histogram supports uint16 stacks"); return -1; }
+  Scoped sc;
+  unsigned long long* d_h = nullptr; void* h = nullptr;
+  const size_t bytes = 65536 * sizeof(unsigned long long);
+  if (sc.dalloc(&d_h, bytes) || sc.halloc(&h, bytes)) return -1;
+  cudaStream_t st = s->stream;
+  if (launch_hist_u16((const uint16_t*)s->d_im, (long long)s->nvox, d_h, st) || small_copy(h, d_h, bytes, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  memcpy(counts, h, bytes);
+  return 0;
+}
+
+int ia3_seed_v2(ia3_stack* s, int gfilt_size, int filt_size, double th_seed, double* std_out, int64_t* flat_idx, float* h_out,
+                int64_t cap, int64_t* n_out) {
+  if (ensure_device()) return -1;
+  if (!s || !std_out || !n_out || (cap > 0 && (!flat_idx || !h_out))) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (gfilt_size < 0 || gfilt_size > 255 || filt_size < 1) { set_error("bad filter size"); return -1; }
+  cudaStream_t st = s->stream;
+  Scoped sc;
+  float* d_norm = nullptr; double* d_acc = nullptr; long long* d_idx = nullptr; float* d_h = nullptr; int* d_cnt = nullptr;
+  void* h = nullptr;
+  const size_t capc = (size_t)std::max<int64_t>(std::min<int64_t>(cap, (int64_t)1 << 24), 1);
+  if (sc.dalloc(&d_norm, s->nvox * 4) || sc.dalloc(&d_acc, 256) || sc.dalloc(&d_idx, capc * 8) || sc.dalloc(&d_h, capc * 4) || sc.dalloc(&d_cnt, 256) ||
+      sc.halloc(&h, 256 + capc * 12)) return -1;
+  const int sz = gfilt_size == 0 ? 1 : gfilt_size;         // a 1x1 box blur leaves im - im = 0: handled below
+  int rc;
+  if (s->dtype == IA3_DTYPE_U16) rc = launch_box_norm<uint16_t>((const uint16_t*)s->d_im, d_norm, s->Z, s->X, s->Y, sz, st);
+  else if (s->dtype == IA3_DTYPE_F32) rc = launch_box_norm<float>((const float*)s->d_im, d_norm, s->Z, s->X, s->Y, sz, st);
+  else rc = launch_box_norm<double>((const double*)s->d_im, d_norm, s->Z, s->X, s->Y, sz, st);
+  if (rc) return -1;
+  if (gfilt_size == 0) { set_error("gfilt_size = 0 (no normalisation) is not supported on the device"); return -1; }
+  double mean = 0.0, sd = 0.0;
+  if (volume_std<float>(d_norm, (long long)s->nvox, d_acc, h, st, &mean, &sd)) return -1;
+  const float std32 = (float)sd;
+  const float cutoff = std32 * (float)th_seed;              // np.float32 * python float -> float32
+  if (launch_v2_candidates(d_norm, s->Z, s->X, s->Y, cutoff, filt_size / 2, d_idx, d_h, d_cnt, (int)capc, st)) return -1;
+  if (small_copy(h, d_cnt, sizeof(int), st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  const int n = *static_cast<int*>(h);
+  *std_out = (double)std32;
+  *n_out = n;
+  if (n > cap) { set_error("ia3_seed_v2: more candidates than the caller's capacity"); return -2; }
+  if (n > 0) {
+    char* hp = static_cast<char*>(h) + 256;
+    if (small_copy(hp, d_idx, (size_t)n * 8, st) || small_copy(hp + capc * 8, d_h, (size_t)n * 4, st)) return -1;
+    IA3_CUDA(cudaStreamSynchronize(st));
+    memcpy(flat_idx, hp, (size_t)n * 8);
+    memcpy(h_out, hp + capc * 8, (size_t)n * 4);
+  }
+  return 0;
+}
+
+int ia3_fft_gaussian(ia3_stack* s, const double* gaus, int expo, double* out) {
+  if (ensure_device()) return -1;
+  if (!s || !gaus || !out) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  Scoped sc;
+  double* d_a = nullptr; double* d_b = nullptr;
+  if (sc.dalloc(&d_a, s->nvox * 8) || sc.dalloc(&d_b, s->nvox * 8)) return -1;
+  int rc;
+  if (s->dtype == IA3_DTYPE_U16) rc = fft_gaussian_dev<uint16_t>(s, gaus, expo, d_a, d_b, sc);
+  else if (s->dtype == IA3_DTYPE_F32) rc = fft_gaussian_dev<float>(s, gaus, expo, d_a, d_b, sc);
+  else rc = fft_gaussian_dev<double>(s, gaus, expo, d_a, d_b, sc);
+  if (rc) return -1;
+  IA3_CUDA(cudaStreamSynchronize(s->stream));
+  IA3_CUDA(cudaMemcpyAsync(out, d_a, s->nvox * 8, cudaMemcpyDeviceToHost, s->stream));
+  IA3_CUDA(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int ia3_seed_logratio(ia3_stack* s, double gfilt_size, int filt_size, double th_seed, double* std_out, int64_t* flat_idx, double* h_out,
+                      int64_t cap, int64_t* n_out) {
+  if (ensure_device()) return -1;
+  if (!s || !std_out || !n_out || (cap > 0 && (!flat_idx || !h_out))) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (filt_size < 1) { set_error("bad filter size"); return -1; }
+  cudaStream_t st = s->stream;
+  Scoped sc;
+  double* d_a = nullptr; double* d_b = nullptr; double* d_acc = nullptr; long long* d_idx = nullptr; double* d_h = nullptr; int* d_cnt = nullptr;
+  void* h = nullptr;
+  const size_t capc = (size_t)std::max<int64_t>(std::min<int64_t>(cap, (int64_t)1 << 24), 1);
+  if (sc.dalloc(&d_a, s->nvox * 8) || sc.dalloc(&d_b, s->nvox * 8) || sc.dalloc(&d_acc, 256) || sc.dalloc(&d_idx, capc * 8) || sc.dalloc(&d_h, capc * 8) ||
+      sc.dalloc(&d_cnt, 256) || sc.halloc(&h, 256 + capc * 16)) return -1;
+  const double gaus[3] = {gfilt_size, gfilt_size, gfilt_size};
+  int rc;
+  const long long n = (long long)s->nvox;
+  if (s->dtype == IA3_DTYPE_U16) rc = fft_gaussian_dev<uint16_t>(s, gaus, 8, d_a, d_b, sc) || launch_log_ratio<uint16_t>((const uint16_t*)s->d_im, d_a, d_b, n, st);
+  else if (s->dtype == IA3_DTYPE_F32) rc = fft_gaussian_dev<float>(s, gaus, 8, d_a, d_b, sc) || launch_log_ratio<float>((const float*)s->d_im, d_a, d_b, n, st);
+  else rc = fft_gaussian_dev<double>(s, gaus, 8, d_a, d_b, sc) || launch_log_ratio<double>((const double*)s->d_im, d_a, d_b, n, st);
+  if (rc) return -1;
+  double mean = 0.0, sd = 0.0;
+  if (volume_std<double>(d_b, n, d_acc, h, st, &mean, &sd)) return -1;
+  if (launch_lr_candidates(d_b, s->Z, s->X, s->Y, th_seed * sd, filt_size, d_idx, d_h, d_cnt, (int)capc, st)) return -1;
+  if (small_copy(h, d_cnt, sizeof(int), st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  const int nc = *static_cast<int*>(h);
+  *std_out = sd;
+  *n_out = nc;
+  if (nc > cap) { set_error("ia3_seed_logratio: more candidates than the caller's capacity"); return -2; }
+  if (nc > 0) {
+    char* hp = static_cast<char*>(h) + 256;
+    if (small_copy(hp, d_idx, (size_t)nc * 8, st) || small_copy(hp + capc * 8, d_h, (size_t)nc * 8, st)) return -1;
+    IA3_CUDA(cudaStreamSynchronize(st));
+    memcpy(flat_idx, hp, (size_t)nc * 8);
+    memcpy(h_out, hp + capc * 8, (size_t)nc * 8);
+  }
+  return 0;
+}
 
 // ---- standalone GaussianFit -----------------------------------------------------------------
 }  // extern "C"

@@ -701,18 +701,19 @@ static int dispatch_axis(const Tin* in, Tin* out, int L, long long inner, long l
 // in -> bufA (z pass) -> bufB (x pass) -> bufA (y pass); result in bufA.
 template <typename Tin>
 int gaussian_filter_exact(const Tin* in, Tin* bufA, Tin* bufB, int Z, int X, int Y, const GaussW& gw,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool skip_z) {
   if (gw.r > GaussW::MAXR) { set_error("gaussian radius too large (max 95)"); return -1; }
   const long long XY = (long long)X * Y;
   int rc;
-  if ((rc = dispatch_axis<Tin, false>(in, bufA, Z, XY, XY, gw, st))) return rc;
-  if ((rc = dispatch_axis<Tin, false>(bufA, bufB, X, Y, (long long)Z * Y, gw, st))) return rc;
+  // skip_z: a 2-D image held as a one-plane stack -- scipy filters its two axes only
+  if (!skip_z && (rc = dispatch_axis<Tin, false>(in, bufA, Z, XY, XY, gw, st))) return rc;
+  if ((rc = dispatch_axis<Tin, false>(skip_z ? in : bufA, bufB, X, Y, (long long)Z * Y, gw, st))) return rc;
   if ((rc = dispatch_axis<Tin, true>(bufB, bufA, Y, 1, (long long)Z * X, gw, st))) return rc;
   return 0;
 }
-template int gaussian_filter_exact<uint16_t>(const uint16_t*, uint16_t*, uint16_t*, int, int, int, const GaussW&, cudaStream_t);
-template int gaussian_filter_exact<float>(const float*, float*, float*, int, int, int, const GaussW&, cudaStream_t);
-template int gaussian_filter_exact<double>(const double*, double*, double*, int, int, int, const GaussW&, cudaStream_t);
+template int gaussian_filter_exact<uint16_t>(const uint16_t*, uint16_t*, uint16_t*, int, int, int, const GaussW&, cudaStream_t, bool);
+template int gaussian_filter_exact<float>(const float*, float*, float*, int, int, int, const GaussW&, cudaStream_t, bool);
+template int gaussian_filter_exact<double>(const double*, double*, double*, int, int, int, const GaussW&, cudaStream_t, bool);
 
 // ------------------------------------------------------------------------------------------
 // Rank filters + candidate mask.  scipy's maximum_filter/minimum_filter(size=s) with reflect
@@ -859,7 +860,7 @@ k_flags(const Tin* __restrict__ fg, const Tin* __restrict__ bg, SeedDims d, uint
     }
     if (VARIANT == 0 && d.edge_on) {
       // remove_edge_points (spot_tools/fitting.py:156-165): d <= c <= size - d, inclusive
-      if (z < d.lo || z > d.hiZ || x < d.lo || x > d.hiX) mask = 0;
+      if (z < d.loZ || z > d.hiZ || x < d.lo || x > d.hiX) mask = 0;
       else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { const int y = y0 + i; if (y < d.lo || y > d.hiY) mask &= ~(1u << i); }
@@ -996,7 +997,7 @@ k_flags_u16(const uint16_t* __restrict__ fg, const uint16_t* __restrict__ bg, Se
         }
         mask = m2;
         if (VARIANT == 0 && d.edge_on && mask) {
-          if (z < d.lo || z > d.hiZ || x < d.lo || x > d.hiX) mask = 0;
+          if (z < d.loZ || z > d.hiZ || x < d.lo || x > d.hiX) mask = 0;
           else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) { const int y = cy * 8 + i; if (y < d.lo || y > d.hiY) mask &= ~(1u << i); }

@@ -17,12 +17,12 @@ struct SeedDims {
   long long n_chunks;   // Z*X*cpr
   int n_blocks;
   int fs, s1, s2;       // rank filter size; window [i-s1, i+s2]
-  int edge_on, lo, hiZ, hiX, hiY;
+  int edge_on, lo, loZ, hiZ, hiX, hiY;
   double h_min;
 };
 
 template <typename Tin>
-int gaussian_filter_exact(const Tin* in, Tin* bufA, Tin* bufB, int Z, int X, int Y, const GaussW& gw, cudaStream_t st);
+int gaussian_filter_exact(const Tin* in, Tin* bufA, Tin* bufB, int Z, int X, int Y, const GaussW& gw, cudaStream_t st, bool skip_z = false);
 
 template <typename Tin>
 int seed_flags(const Tin* fg, const Tin* bg, const SeedDims& d, int variant, uint8_t* bits, int* counts,

@@ -36,14 +36,45 @@ def _effective_threshold(th, h_dtype):
     return float(np.asarray(th, dtype=h_dtype))
 
 
+def _score_from_counts(counts, per):
+    """scipy.stats.scoreatpercentile(a, per) for an integer array given as the counts of its values: the two order
+    statistics around per / 100 * (n - 1) and scipy's own interpolation arithmetic."""
+    if not (0 <= per <= 100):
+        raise ValueError("percentile must be in the range [0, 100]")
+    n = int(counts.sum())
+    idx = per / 100. * (n - 1)
+    i = int(idx)
+    cum = np.cumsum(counts.astype(np.int64))
+    a_i = int(np.searchsorted(cum, i, side='right'))
+    if i == idx:
+        return np.float64(a_i) / 1.0
+    a_j = int(np.searchsorted(cum, i + 1, side='right'))
+    w = np.array([(i + 1 - idx), (idx - i)], float)
+    return np.add.reduce(np.array([a_i, a_j], dtype=np.uint16) * w) / w.sum()
+
+
+def _percentile_span(im, stack, hi, lo):
+    """scoreatpercentile(im, hi) - scoreatpercentile(im, lo): from the device histogram when the stack is uint16 and
+    resident, else with scipy on the host"""
+    if stack is not None and stack.dtype == np.uint16 and im.dtype == np.uint16 and tuple(stack.shape) == tuple(im.shape):
+        counts = stack.histogram()
+        return _score_from_counts(counts, hi) - _score_from_counts(counts, lo)
+    from scipy.stats import scoreatpercentile
+    return scoreatpercentile(im, hi) - scoreatpercentile(im, lo)
+
+
 def _device_image(im):
-    """dtype handling of the seed stage: uint16 / float32 are native; narrower unsigned ints
-    widen losslessly (truncation per pass is value-preserving)."""
-    if im.dtype == np.uint16 or im.dtype == np.float32:
+    """dtype handling of the seed stage: uint16 / float32 / float64 are native.  Other integer types whose values fit
+    uint16 are narrowed: scipy filters in double and stores in the input's integer type by truncation, so the
+    filtered integers (and hence every seed) are the same in either type."""
+    if im.dtype in (np.uint16, np.float32, np.float64):
         return im
-    if im.dtype == np.uint8 or im.dtype == np.bool_:
-        return im.astype(np.uint16)
-    raise NotImplementedError(f"seed stage on the GPU supports uint16/uint8/float32 stacks, got {im.dtype}")
+    if im.dtype.kind in "uib":
+        if im.size == 0 or (im.min() >= 0 and im.max() <= 65535):
+            return im.astype(np.uint16)
+        raise NotImplementedError(f"integer stacks on the GPU must hold values in [0, 65535], got {im.dtype} "
+                                  f"with range [{im.min()}, {im.max()}]")
+    raise NotImplementedError(f"seed stage on the GPU supports integer, float32 and float64 stacks, got {im.dtype}")
 
 
 def get_seeds(im, max_num_seeds=None, th_seed=150,
@@ -78,8 +109,9 @@ def get_seeds(im, max_num_seeds=None, th_seed=150,
         stack = _stack
 
     if use_percentile:
-        from scipy.stats import scoreatpercentile
-        th0 = scoreatpercentile(im, th_seed_per) - scoreatpercentile(im, (100 - th_seed_per) / 2)
+        if _stack is None and sel_center is None and im.ndim == 3 and im.dtype == np.uint16:
+            _stack = stack = _lib.Stack(im)              # the percentile is taken over the FULL image (fitting.py:76)
+        th0 = _percentile_span(im, _stack, th_seed_per, (100 - th_seed_per) / 2)
     else:
         th0 = th_seed
     if verbose:
@@ -91,16 +123,20 @@ def get_seeds(im, max_num_seeds=None, th_seed=150,
     niters = int(dynamic_niters) if use_dynamic_th else 1
     ths = [th0 * (1 - it / niters) for it in range(niters)]
 
-    if sub.ndim != 3:
-        raise NotImplementedError("the GPU seed stage needs a 3D (Z, X, Y) stack")
+    if sub.ndim not in (2, 3):
+        raise NotImplementedError("the GPU seed stage needs a 2D (X, Y) image or a 3D (Z, X, Y) stack")
+    two_d = sub.ndim == 2
     if stack is None:
-        stack = _lib.Stack(_device_image(sub))
+        dev = _device_image(sub)
+        stack = _lib.Stack(dev[np.newaxis] if two_d else dev)      # a 2D image is held as a one-plane stack
     h_dtype = np.float32
     floor = min(_effective_threshold(t, h_dtype) for t in ths)
     zxy, hs_all, timing = stack.seed_candidates(
         _gauss_half_kernel(gfilt_size) if gfilt_size else None,
         _gauss_half_kernel(background_gfilt_size) if background_gfilt_size else None,
-        int(filt_size), 0, float(min_edge_distance) if min_edge_distance > 0 else 0.0, floor)
+        int(filt_size), 0, float(min_edge_distance) if min_edge_distance > 0 else 0.0, floor, two_d=two_d)
+    if two_d:
+        zxy = zxy[:, 1:]
 
     # dynamic threshold descent on the candidate list (fitting.py:113-125)
     for th in ths:
@@ -109,10 +145,12 @@ def get_seeds(im, max_num_seeds=None, th_seed=150,
             break
     if verbose and use_dynamic_th:
         print(f"->{th:.2f}", end=', ')
-    coords = tuple(zxy[sel, a].astype(np.int64) for a in range(3))
+    coords = tuple(zxy[sel, a].astype(np.int64) for a in range(ndim))
     hs = hs_all[sel]
     # hot pixels: (x, y) columns holding >= hot_pixel_th seeds (fitting.py:131-138)
     if remove_hot_pixel:
+        if two_d:
+            raise IndexError("tuple index out of range")     # the reference indexes _coords[2] here: 3D stacks only
         key = coords[1] * (int(sub.shape[2]) + 1) + coords[2]
         _, inv, cts = np.unique(key, return_inverse=True, return_counts=True)
         keep = cts[inv] < hot_pixel_th if len(key) else np.zeros(0, dtype=bool)
@@ -258,8 +296,8 @@ def _fit_fov_image(im, channel, seeds=None,
         t0 = time.time()
     stack = _stack
     own_stack = _stack is None
-    if stack is None and isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype in (np.uint16, np.float32):
-        stack = _lib.Stack(im)     # one upload shared by the seed and the fit stage
+    if stack is None and isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype.kind in "uibf" and im.dtype.itemsize >= (4 if im.dtype.kind == "f" else 1):
+        stack = _lib.Stack(_device_image(im))     # one upload shared by the seed and the fit stage
     if seeds is None:
         with _SEED_GATE:
             _seeds = get_seeds(im, max_num_seeds=max_num_seeds,

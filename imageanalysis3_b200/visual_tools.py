@@ -65,8 +65,16 @@ def get_seed_in_distance(im, center=None, num_seeds=0, seed_radius=30,
         raise ValueError('wrong input dimension of center!')
     _dim = np.shape(im)
     if seed_by_per:
-        ints = im[np.isnan(im) == False].astype(float)
-        _th_seed = scoreatpercentile(ints, th_seed_percentile) - scoreatpercentile(ints, 100 - th_seed_percentile)
+        if isinstance(im, np.ndarray) and im.dtype == np.uint16 and im.ndim == 3:
+            # order statistics of the whole image from the device histogram (exactly scipy's numbers)
+            from .spot_tools.fitting import _score_from_counts
+            _st = _lib.Stack(im)
+            _counts = _st.histogram()
+            _st.close()
+            _th_seed = _score_from_counts(_counts, th_seed_percentile) - _score_from_counts(_counts, 100 - th_seed_percentile)
+        else:
+            ints = im[np.isnan(im) == False].astype(float)
+            _th_seed = scoreatpercentile(ints, th_seed_percentile) - scoreatpercentile(ints, 100 - th_seed_percentile)
     else:
         _th_seed = th_seed
     if verbose:

@@ -56,6 +56,11 @@ int ia3_stack_destroy(ia3_stack* s);
  * the sparse work volume).  A later call that needs what was released fails with an error. */
 int ia3_stack_trim(ia3_stack* s, int what);
 
+/* counts[v] = number of voxels with value v of a uint16 stack (65536 entries).  The percentile thresholds of the
+ * seeders (scipy.stats.scoreatpercentile over the whole image: spot_tools/fitting.py:75-76, visual_tools.py:
+ * 1808-1811) are order statistics, which the host reads off this histogram exactly. */
+int ia3_stack_histogram(ia3_stack* s, uint64_t* counts);
+
 /* ---- seed stage ------------------------------------------------------------------------ */
 typedef struct {
   /* half kernels: w[j] = weight at distance j from the centre tap, j = 0..r (scipy
@@ -69,6 +74,7 @@ typedef struct {
   double edge;            /* variant 0: min_edge_distance (keep d <= c <= size-d); <=0 = off */
   double h_min;           /* keep candidates with h >= h_min (host folds >, >=, float32/float64
                              comparison semantics into this number) */
+  int two_d;              /* the stack is a 2-D image held as (1, X, Y): filters and edge test on x, y only */
 } ia3_seed_cfg;
 
 typedef struct {
@@ -90,6 +96,23 @@ int ia3_seed_fetch_volume(ia3_stack* s, int which, void* out);
 /* Values of such a volume at n voxels given as flat C-order indices (External/Fitting_v3.py:276-283
  * reads its two blurs at the candidate voxels only); out: n values of the stack's dtype. */
 int ia3_seed_gather_volume(ia3_stack* s, int which, const int64_t* flat_idx, int64_t n, void* out);
+
+/* ---- alternative seeders of External/Fitting_v4.py (no caller inside the reference) ------------- */
+/* get_seed_points_base_v2 (Fitting_v4.py:95-126): im_norm = float32(im) - cv2.blur(float32(im), (gfilt_size,
+ * gfilt_size)) per z-slice (bit-identical to cv2 4.13), std = np.std(im_norm) (FP64 on the device: agrees with
+ * numpy's float32 pairwise value to ~1e-7 relative), candidates = voxels with im_norm > float32(std) * th_seed that
+ * are >= all (2 (filt_size / 2) + 1)^3 neighbours taken modulo the shape.  flat_idx / h: C-order voxel indices and
+ * im_norm values, UNORDERED (the caller sorts); *n_out = number found (-2 is returned if it exceeds cap). */
+int ia3_seed_v2(ia3_stack* s, int gfilt_size, int filt_size, double th_seed, double* std_out, int64_t* flat_idx, float* h,
+                int64_t cap, int64_t* n_out);
+/* fft_gaussian_fast (Fitting_v4.py:66-70): the reference's reflect() padding and 'valid' convolution with the
+ * normalised int(gaus * exp)-tap Gaussian windows, evaluated directly in FP64 (the reference multiplies
+ * single-precision FFTs: agreement ~1e-6 relative); out = Z*X*Y float64 on the host. */
+int ia3_fft_gaussian(ia3_stack* s, const double* gaus3, int exp, double* out);
+/* get_seed_points_base (Fitting_v4.py:72-92): im_diff = log(im) - log(fft_gaussian_fast(im, [gfilt_size] * 3)),
+ * candidates = voxels equal to the maximum of their filt_size^3 neighbourhood with im_diff > th_seed * std(im_diff). */
+int ia3_seed_logratio(ia3_stack* s, double gfilt_size, int filt_size, double th_seed, double* std_out, int64_t* flat_idx, double* h,
+                      int64_t cap, int64_t* n_out);
 
 /* ---- local background (fit_fov_image's normalize_local / normalize_background) ------------ */
 /* find_image_background (io_tools/load.py:642-686) for n boxes of a uint16 stack: mode of the

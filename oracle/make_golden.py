@@ -158,5 +158,79 @@ def main():
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 
 
+def main_extra():
+    """tests/golden/extra_r2.npz: argument paths and functions that had no fixture in round 1 -- percentile
+    thresholds, find_matched_seeds, standalone Fitting_v3.GaussianFit, other input dtypes / 2-D images, and the
+    alternative seeders of Fitting_v4 (get_seed_points_base, get_seed_points_base_v2, fft_gaussian_fast)."""
+    warnings.simplefilter("ignore")
+    ns = ref_loader.load()
+    meta = dict(numpy=np.__version__, scipy=scipy.__version__, python=sys.version.split()[0])
+    try:
+        import cv2
+        meta["cv2"] = cv2.__version__
+    except ImportError:
+        cv2 = None
+    im = synth((20, 80, 96), 60, 11)
+    im[:, 30, 40] = 5000
+    out = dict(im=im, meta=np.array(repr(meta)))
+    # percentile thresholds (spot_tools/fitting.py:75-76, visual_tools.py:1808-1811)
+    out["seeds_percentile95"] = ns.fitting.get_seeds(im, use_percentile=True, th_seed_per=95)
+    out["seeds_percentile99_h"] = ns.fitting.get_seeds(im, use_percentile=True, th_seed_per=99.5, return_h=True)
+    out["fov_percentile"] = ns.fitting.fit_fov_image(im, '647', use_percentile=True, th_seed_per=99.5, max_num_seeds=30, verbose=False)
+    sp, _ = fit_oracle.fit_fov_image_oracle(im, max_num_seeds=30, use_percentile=True, th_seed_per=99.5)
+    assert np.array_equal(sp, out["fov_percentile"])
+    out["fov_percentile_comparable"] = fit_oracle.fit_fov_image_oracle.last_comparable
+    out["legacy_by_per"] = ns.visual.get_seed_in_distance(im, center=None, seed_by_per=True, th_seed_percentile=99.5, return_h=True)
+    out["legacy_by_per_center"] = ns.visual.get_seed_in_distance(im, center=[10, 40, 50], seed_by_per=True, th_seed_percentile=99.5,
+                                                                 num_seeds=5, return_h=True)
+    # find_matched_seeds (visual_tools.py:3081-3139)
+    ref = ns.visual.get_seed_in_distance(im, center=None, th_seed=300)[:25].astype(np.float64)
+    ref = ref + np.random.default_rng(7).uniform(-1.2, 1.2, size=ref.shape)
+    ref = np.concatenate([ref, [[3.0, 5.0, 5.0], [10.0, 30.0, 41.5]]])
+    out["matched_ref"] = ref
+    for tag, kw in (("default", {}), ("unique_d5", dict(keep_unique=True, search_distance=5)), ("th600", dict(th_seed=600, search_distance=2))):
+        m, f = ns.visual.find_matched_seeds(im, ref, verbose=False, **kw)
+        out[f"matched_{tag}"], out[f"matched_{tag}_found"] = m, f
+    # other input types of get_seeds: the filters keep the input's dtype (spot_tools/fitting.py:91-106)
+    out["seeds_i32"] = ns.fitting.get_seeds(im.astype(np.int32), th_seed=300)
+    out["seeds_i64_h"] = ns.fitting.get_seeds(im.astype(np.int64), th_seed=300, return_h=True, max_num_seeds=30)
+    imf64 = im.astype(np.float64) / 2.5
+    out["seeds_f64"] = ns.fitting.get_seeds(imf64, th_seed=120)
+    out["fov_f64"] = ns.fitting.fit_fov_image(imf64, '647', th_seed=120, max_num_seeds=20, verbose=False)
+    out["seeds_2d"] = ns.fitting.get_seeds(im[10], th_seed=300, remove_hot_pixel=False)
+    out["seeds_2d_f32_h"] = ns.fitting.get_seeds(im[10].astype(np.float32), th_seed=300, remove_hot_pixel=False, return_h=True)
+    # standalone Fitting_v3.GaussianFit (External/Fitting_v3.py:50-257)
+    seeds = ns.fitting.get_seeds(im, th_seed=300)
+    f = ns.Fitting_v3.iter_fit_seed_points(im, seeds.T)
+    c = seeds[0]
+    X = np.array([int(c[0]) + f.zb, int(c[1]) + f.xb, int(c[2]) + f.yb])
+    X = X[:, ((X >= 0) & (X < np.array(im.shape)[:, None])).all(0)]
+    out["gf3_X"] = X
+    for ws in (0, 1000):
+        g = ns.Fitting_v3.GaussianFit(im[X[0], X[1], X[2]], X, center=list(c), delta_center=2.5, weight_sigma=ws)
+        g.fit()
+        out[f"gf3_ws{ws}_p"], out[f"gf3_ws{ws}_rec"] = g.p, g.get_im()
+        o = fit_oracle.gaussian_fit(im[X[0], X[1], X[2]], X, center=list(c), version=3, delta_center=2.5, weight_sigma=ws)
+        assert np.array_equal(o["p"], g.p)
+    # alternative seeders of Fitting_v4 (External/Fitting_v4.py:66-126); pyfftw is stubbed with scipy.fft (ref_loader)
+    imf = im.astype(np.float32)
+    out["fftg_5"] = ns.Fitting_v4.fft_gaussian_fast(imf, gaus=[2.5, 5, 5])
+    c1, s1 = ns.Fitting_v4.get_seed_points_base(imf, gfilt_size=2.5, th_seed=3.)
+    out["lr_centers"], out["lr_std"] = c1, np.float64(s1)
+    c1, s1 = ns.Fitting_v4.get_seed_points_base(imf, gfilt_size=2.5, th_seed=4., filt_size=5, max_num=12)
+    out["lr_centers_f5_top12"] = c1
+    if cv2 is not None:
+        for tag, arr, kw in (("u16", im, dict(th_seed=3.)), ("f32_g7_f5", imf, dict(gfilt_size=7, filt_size=5, th_seed=2.5)),
+                             ("u16_top10", im, dict(th_seed=3., max_num=10))):
+            c2, s2 = ns.Fitting_v4.get_seed_points_base_v2(arr, **kw)
+            out[f"v2_{tag}_centers"], out[f"v2_{tag}_std"] = c2, np.float32(s2)
+        out["v2_norm_u16_g5"] = ns.Fitting_v4.normalzie_im(im, 5)[:3]          # first slices: pins the cv2.blur arithmetic
+    np.savez_compressed(os.path.join(OUT, "extra_r2.npz"), **out)
+    print("extra_r2.npz", os.path.getsize(os.path.join(OUT, "extra_r2.npz")), {k: np.shape(v) for k, v in out.items() if k != "meta"})
+
+
 if __name__ == "__main__":
-    main()
+    if "extra" in sys.argv[1:]:
+        main_extra()
+    else:
+        main()
