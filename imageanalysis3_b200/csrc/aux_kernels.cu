@@ -5,7 +5,7 @@
 //   k_box_norm        im_norm = float32(im) - cv2.blur(float32(im), (sz, sz)) per z-slice.  cv2.blur on CV_32F
 //                     accumulates the window in double (exact for 24-bit inputs), multiplies by the double
 //                     1 / sz^2 and rounds to float32; border = BORDER_REFLECT_101, anchor = sz / 2.  Measured
-//                     against cv2 4.13: bit-identical (oracle/make_golden.py asserts it on the fixtures).
+//                     against cv2 4.13: bit-identical (fixtures from the unmodified reference, tests/test_gpu_extra.py).
 //   k_fir_axis        one axis of fft_gaussian_fast (:66-70): the reflect() padding of the reference followed by a
 //                     'valid' convolution with the 40-tap window, evaluated directly in FP64 (the reference goes
 //                     through a single-precision FFT: parity is by tolerance).

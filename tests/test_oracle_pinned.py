@@ -172,7 +172,9 @@ def test_reference_sensitivity_probe_flags_slow_crawls():
     assert (o["cond_max"] < fit_oracle.COND_WELL_POSED).all()
     assert o["unstable"][583] and o["nfev_max"][583] > 100
     assert 1 <= o["unstable"].sum() <= 0.02 * len(seeds)
-    assert o["comparable"].mean() > 0.98
+    # a crawl takes the seeds whose windows overlap its own with it (comparable_mask): 1 % crawls -> 3 % of the rows
+    assert o["comparable"].mean() > 0.95
+    assert (~o["comparable"]).sum() > o["unstable"].sum()
     # the probe on its own: seed 583's slowest fit moves by > 1e-4 under the one-ulp perturbation
     sig = np.array([np.asarray(r, float) for r in o["ps"]])[583, 5:8]
     assert (np.abs(sig - 4.0) < 1e-3).any()
