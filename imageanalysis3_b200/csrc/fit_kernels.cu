@@ -546,7 +546,9 @@ __device__ __forceinline__ double pass_cta(WarpExec& ex, SpotShared<double>& sh,
 #define LM_OUTER(ex, st, cfg, A, g) lw::outer(st, cfg, A, g)
 #define LM_PROPOSE(ex, st) lw::propose(st)
 #define LM_JUDGE(ex, st, cfg, fn) lw::judge(st, cfg, fn)
+#define LM_CONSTS(ex, fp, cen, origin, x, sh) lw::build_consts<double>(fp, cen, origin, x, (sh).etab, (sh).scal, (sh).vc)
 #else
+#define LM_CONSTS(ex, fp, cen, origin, x, sh) build_consts_par<double>(ex, fp, cen, origin, x, sh)
 #define LM_OUTER(ex, st, cfg, A, g) lm_outer(ex, st, cfg, A, g)
 #define LM_PROPOSE(ex, st) lm_propose(ex, st)
 #define LM_JUDGE(ex, st, cfg, fn) lm_judge(ex, st, cfg, fn)
@@ -568,7 +570,7 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
   unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   if (start == LM_START_FRESH) {
-    if (warp == 0) build_consts_par<double>(ex, fp, cen, origin, sh.x0, sh);
+    if (warp == 0) LM_CONSTS(ex, fp, cen, origin, sh.x0, sh);
     cta_sync<TW>();
     const double fn0 = pass_cta<TW>(ex, sh, vox, gram_w, part);
     if (warp == 0) lm_init(ex, st, sh.x0, fn0);
@@ -597,7 +599,7 @@ __device__ __forceinline__ bool run_lm_cta(WarpExec& ex, const FitParams& fp, co
       PROF_T(t2);
       if (warp == 0) LM_PROPOSE(ex, st);
       PROF_T(t3);
-      if (warp == 0) build_consts_par<double>(ex, fp, cen, origin, st.xt, sh);
+      if (warp == 0) LM_CONSTS(ex, fp, cen, origin, st.xt, sh);
       cta_sync<TW>();
       PROF_T(t4);
       const double fn1 = pass_cta<TW>(ex, sh, vox, gram_w, part);     // lm_outer has consumed the old sums

@@ -21,6 +21,7 @@ struct SpotShared {
   VoxConsts<T> vc;
   double Ag[NTRI + NP];   // J^T J (packed upper triangle) followed by J^T f
   double etab[NEXP];      // exp table of the parameter transforms (one slot per lane)
+  double scal[NSCAL + 3]; // the division / square-root scalars of the parameter transforms (one per lane, lm_warp.h)
   double x0[NP];
   double small10[10], large10[10];
   double gram[(NP + 1) * GRAM_PITCH];   // device: [J | f] of the current batch of 32 voxels, column-major (pass_fused_mma)

@@ -82,49 +82,65 @@ IA3_HD double norm_w_fn(double w, double e /* exp(-|w|) */, double minw, double 
   return 0.5 * (maxw - minw) * e / (d * d);
 }
 
-// want_jac = false skips the Jacobian-only constants.  e[NEXP]: exp table at x (exp_slot_arg).
-IA3_HD void model_consts_e(const FitParams& fp, const double* cen_est, const double* x, const double* e, bool want_jac,
-                           ModelConsts& mc) {
-  const double h = x[1], xp = x[2], yp = x[3], zp = x[4];
-  const double w1 = x[5], w2 = x[6], w3 = x[7], pp = x[8], tp = x[9];
+// The parameter-only part of the model in two layers, so that a warp can spread the expensive bit over its lanes
+// (lm_warp.h: build_consts) while the serial form below evaluates exactly the same expressions:
+//   consts_scalar(k)   the 21 scalars that cost a division or a square root each -- k = 0 t, 1 p, 2..4 ws1..3,
+//                      5..7 centre, 8..10 norm_xp.., 11..13 norm_w1..3, 14 norm_p, 15 norm_t (from x and the exp
+//                      table only), 16..18 s_i = 1 / ws_i, 19 tc, 20 pc (from scalars 0..4)
+//   model_consts_tail  everything else: products and sums of those scalars
+constexpr int NSCAL = 21;
+constexpr int NSCAL_FIRST = 16;         // scalars 0..15 are independent of each other
+
+IA3_HD double consts_scalar(const FitParams& fp, const double* cen_est, const double* x, const double* e, const double* S, int k) {
   const bool v4 = (fp.personality == 4);
   const double d = fp.delta, minw = fp.min_w2, maxw = fp.max_w2, dws = maxw - minw;
-  double t, p, ws1, ws2, ws3;
-  if (v4) {
-    t = v4_sigmoid_guarded(tp, e[9], -1.0, 1.0, 2.0, -1.0);
-    p = v4_sigmoid_guarded(pp, e[8], -1.0, 1.0, 2.0, -1.0);
-    ws1 = v4_sigmoid_guarded(w1, e[5], minw, dws + minw, dws, minw);
-    ws2 = v4_sigmoid_guarded(w2, e[6], minw, dws + minw, dws, minw);
-    ws3 = v4_sigmoid_guarded(w3, e[7], minw, dws + minw, dws, minw);
-    // c = 2*delta/(1+exp(c_)) - delta + center_est   (left-to-right as written, :198)
-    const double LOGMAX = 709.782712893384;
-    const double raw[3] = {xp, yp, zp};
-    for (int i = 0; i < 3; ++i) {
-      if (raw[i] >= LOGMAX) mc.c[i] = -d + cen_est[i];
-      else if (raw[i] <= -LOGMAX) mc.c[i] = d + cen_est[i];
-      else mc.c[i] = 2.0 * d / (1.0 + e[2 + i]) - d + cen_est[i];
+  const double LOGMAX = 709.782712893384;
+  switch (k) {
+    case 0: return v4 ? v4_sigmoid_guarded(x[9], e[9], -1.0, 1.0, 2.0, -1.0) : 2.0 / (1.0 + e[9]) - 1.0;            // t
+    case 1: return v4 ? v4_sigmoid_guarded(x[8], e[8], -1.0, 1.0, 2.0, -1.0) : 2.0 / (1.0 + e[8]) - 1.0;            // p
+    case 2: case 3: case 4: {
+      const int i = k - 2;
+      return v4 ? v4_sigmoid_guarded(x[5 + i], e[5 + i], minw, dws + minw, dws, minw) : dws / (1.0 + e[5 + i]) + minw;
     }
-  } else {
-    t = 2.0 / (1.0 + e[9]) - 1.0;
-    p = 2.0 / (1.0 + e[8]) - 1.0;
-    ws1 = dws / (1.0 + e[5]) + minw;
-    ws2 = dws / (1.0 + e[6]) + minw;
-    ws3 = dws / (1.0 + e[7]) + minw;
-    const double e0 = e[2], e1 = e[3], e2 = e[4];             // exp(-xp), exp(-yp), exp(-zp)
-    mc.c[0] = 2.0 * d * e0 / (1.0 + e0) - d + cen_est[0];
-    mc.c[1] = 2.0 * d * e1 / (1.0 + e1) - d + cen_est[1];
-    mc.c[2] = 2.0 * d * e1 / (1.0 + e2) - d + cen_est[2];   // Fitting_v3.py:86 (sic)
+    case 5: case 6: case 7: {
+      const int i = k - 5;
+      if (v4) {      // c = 2*delta/(1+exp(c_)) - delta + center_est   (left-to-right as written, :198)
+        const double raw = x[2 + i];
+        if (raw >= LOGMAX) return -d + cen_est[i];
+        if (raw <= -LOGMAX) return d + cen_est[i];
+        return 2.0 * d / (1.0 + e[2 + i]) - d + cen_est[i];
+      }
+      // v3: e[2..4] = exp(-xp), exp(-yp), exp(-zp); the third centre mixes in exp(-yp)   (Fitting_v3.py:86, sic)
+      const double num = (i == 2) ? e[3] : e[2 + i];
+      return 2.0 * d * num / (1.0 + e[2 + i]) - d + cen_est[i];
+    }
+    case 8: case 9: case 10: { const double ex = e[11 + (k - 8)]; return -d * ex / ((1 + ex) * (1 + ex)); }
+    case 11: case 12: case 13: return norm_w_fn(x[5 + (k - 11)], e[14 + (k - 11)], minw, maxw);
+    case 14: { const double e_p = e[17]; return e_p / (1 + e_p * e_p); }
+    case 15: { const double e_t = e[18]; return e_t / (1 + e_t * e_t); }
+    case 16: case 17: case 18: return 1.0 / S[2 + (k - 16)];
+    case 19: return sqrt(1 - S[0] * S[0]);
+    default: return sqrt(1 - S[1] * S[1]);
   }
+}
+
+// want_jac = false skips the Jacobian-only constants.  e[NEXP]: exp table at x (exp_slot_arg); S: consts_scalar(0..20).
+IA3_HD void model_consts_tail(const FitParams& fp, const double* x, const double* e, const double* S, bool want_jac,
+                              ModelConsts& mc) {
+  const double w1 = x[5], w2 = x[6], w3 = x[7];
+  const bool v4 = (fp.personality == 4);
+  const double t = S[0], p = S[1];
+  mc.c[0] = S[5]; mc.c[1] = S[6]; mc.c[2] = S[7];
   const double p2 = p * p, t2 = t * t, tc2 = 1 - t2, pc2 = 1 - p2;
-  const double tc = sqrt(tc2), pc = sqrt(pc2);
-  const double s1 = 1.0 / ws1, s2 = 1.0 / ws2, s3 = 1.0 / ws3;
+  const double tc = S[19], pc = S[20];
+  const double s1 = S[16], s2 = S[17], s3 = S[18];
   mc.q[0] = pc2 * tc2 * s1 + t2 * s2 + p2 * tc2 * s3;
   mc.q[1] = pc2 * t2 * s1 + tc2 * s2 + p2 * t2 * s3;
   mc.q[2] = p2 * s1 + pc2 * s3;
   mc.q[3] = 2 * tc * t * (pc2 * s1 - s2 + p2 * s3);
   mc.q[4] = 2 * p * pc * tc * (s3 - s1);
   mc.q[5] = 2 * p * pc * t * (s3 - s1);
-  mc.h = h;
+  mc.h = x[1];
   mc.ebk_f = e[0];
   mc.pen = 0.0;
   if (!v4 && fp.weight_sigma > 0) {
@@ -133,15 +149,9 @@ IA3_HD void model_consts_e(const FitParams& fp, const double* cen_est, const dou
   }
   if (!want_jac) return;
   mc.ebk_j = e[10];
-  {
-    const double ex = e[11], ey = e[12], ez = e[13];
-    mc.ncen[0] = -d * ex / ((1 + ex) * (1 + ex));
-    mc.ncen[1] = -d * ey / ((1 + ey) * (1 + ey));
-    mc.ncen[2] = -d * ez / ((1 + ez) * (1 + ez));
-  }
-  const double nw1 = norm_w_fn(w1, e[14], minw, maxw), nw2 = norm_w_fn(w2, e[15], minw, maxw), nw3 = norm_w_fn(w3, e[16], minw, maxw);
-  const double e_p = e[17], norm_p = e_p / (1 + e_p * e_p);
-  const double e_t = e[18], norm_t = e_t / (1 + e_t * e_t);
+  mc.ncen[0] = S[8]; mc.ncen[1] = S[9]; mc.ncen[2] = S[10];
+  const double nw1 = S[11], nw2 = S[12], nw3 = S[13];
+  const double norm_p = S[14], norm_t = S[15];
   // order of the six monomials: xt2, yt2, zt2, xtyt, xtzt, ytzt
   // f6 (Fitting_v4.py:355)
   mc.a6[0] = -pc2 * tc2 * nw1; mc.a6[1] = -pc2 * t2 * nw1; mc.a6[2] = -p2 * nw1;
@@ -171,6 +181,16 @@ IA3_HD void model_consts_e(const FitParams& fp, const double* cen_est, const dou
     for (int i = 0; i < 3; ++i)
       mc.jpen[i] = (fp.init_wt[i] > wv[i] ? fp.weight_sigma : 0.0) - (fp.init_wt[i] < wv[i] ? fp.weight_sigma : 0.0);
   }
+}
+
+IA3_HD void model_consts_e(const FitParams& fp, const double* cen_est, const double* x, const double* e, bool want_jac,
+                           ModelConsts& mc) {
+  double S[NSCAL];
+  for (int k = 0; k < NSCAL; ++k) {
+    // the Jacobian-only scalars (8..15) read exp slots that are not filled when want_jac is false
+    S[k] = (!want_jac && k >= 8 && k < NSCAL_FIRST) ? 0.0 : consts_scalar(fp, cen_est, x, e, S, k);
+  }
+  model_consts_tail(fp, x, e, S, want_jac, mc);
 }
 
 
@@ -220,6 +240,15 @@ IA3_HDN void finish_consts(const FitParams& fp, const double* cen_est, const dou
                            const double* e, bool want_jac, VoxConsts<T>& vc) {
   ModelConsts mc;
   model_consts_e(fp, cen_est, x, e, want_jac, mc);
+  narrow_consts<T>(mc, origin, want_jac, vc);
+}
+
+// the cheap rest of build_consts given the exp table and the 21 scalars (lm_warp.h computes those over a warp's lanes)
+template <typename T>
+IA3_HDN void finish_consts_scalars(const FitParams& fp, const double* origin, const double* x, const double* e,
+                                   const double* S, bool want_jac, VoxConsts<T>& vc) {
+  ModelConsts mc;
+  model_consts_tail(fp, x, e, S, want_jac, mc);
   narrow_consts<T>(mc, origin, want_jac, vc);
 }
 

@@ -24,6 +24,7 @@
 // WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair (measured: 3x the cycles of the shuffles themselves).
 // Each function starts with __syncwarp() for the same reason (it is called under `if (warp == 0)`).
 #pragma once
+#include "gauss_model.h"
 #include "lm_core.h"
 
 #if defined(__CUDACC__)
@@ -49,6 +50,21 @@ __device__ __forceinline__ double max16(double v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLM, v, o, 16));
   return v;
+}
+
+// butterfly reduce-scatter step over the 16-lane halves: N per-lane partial sums -> ceil(N / 2), the other half goes
+// to the partner lane (xor O); after the steps 8, 4, 2, 1 every total sits in exactly one lane of each half
+template <int N, int O>
+__device__ __forceinline__ void rs_step16(double* v) {
+  const bool up = (threadIdx.x & O) != 0;
+#pragma unroll
+  for (int i = 0; i < (N + 1) / 2; ++i) {
+    const double a = v[2 * i];
+    const double b = (2 * i + 1 < N) ? v[2 * i + 1] : 0.0;
+    const double send = up ? a : b;
+    const double keep = up ? b : a;
+    v[i] = keep + __shfl_xor_sync(FULLM, send, O, 16);
+  }
 }
 
 // index of A[i][j] (either order) in the packed upper triangle
@@ -316,9 +332,14 @@ __device__ __noinline__ int judge(LMState& st, const LMConfig& cfg, double fnorm
   if (0.1 * fnorm1 < fnorm) { const double q = fnorm1 / fnorm; actred = 1.0 - q * q; }
   // |R p[ipvt]|: row i = sum over the columns (lanes) of R[i][column] * p[column]
   const double pl = act ? st.p[c] : 0.0;
-  double rp2 = 0.0;
+  double rowp[NP];
 #pragma unroll
-  for (int i = 0; i < NP; ++i) { const double row = sum16((act ? st.R[i][c] : 0.0) * pl); rp2 += row * row; }
+  for (int i = 0; i < NP; ++i) rowp[i] = (act ? st.R[i][c] : 0.0) * pl;
+  rs_step16<NP, 8>(rowp);
+  rs_step16<5, 4>(rowp);
+  rs_step16<3, 2>(rowp);
+  rs_step16<2, 1>(rowp);
+  const double rp2 = sum16(rowp[0] * rowp[0]);
   const double temp1 = sqrt(rp2) / fnorm;
   const double temp2 = (sqrt(par) * pnorm) / fnorm;
   const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
@@ -365,6 +386,61 @@ __device__ __noinline__ int judge(LMState& st, const LMConfig& cfg, double fnorm
   __syncwarp();
   if (info != 0) return LM_DONE;
   return accepted ? LM_ACCEPTED : LM_RETRY;
+}
+
+// Per-voxel constants at x by the whole warp: the 19 FP64 exps one per lane; then the 16 + 5 scalars that cost a
+// division or a square root (gauss_model.h: consts_scalar), one per lane -- every lane prepares its own numerator,
+// denominator and offsets with a few cheap selects and ALL lanes then run ONE division (a switch over the formulas
+// would execute sixteen divisions one after the other: divergence); then the products by lane 0.  Same operations
+// per scalar as the serial build_consts.  `etab`, `scal`: shared scratch.
+template <typename T>
+__device__ __forceinline__ void build_consts(const FitParams& fp, const double* cen_est, const double* origin, const double* x,
+                                             double* etab, double* scal, VoxConsts<T>& vc) {
+  const int lane = threadIdx.x & 31;
+  const bool v4 = (fp.personality == 4);
+  const double LOGMAX = 709.782712893384;
+  __syncwarp();
+  if (lane < NEXP) etab[lane] = (lane == 1) ? 0.0 : exp(exp_slot_arg(fp, x, lane));
+  __syncwarp();
+  {
+    const double d = fp.delta, minw = fp.min_w2, maxw = fp.max_w2, dws = maxw - minw;
+    double numer = 0.0, denom = 1.0, off1 = 0.0, off2 = 0.0, raw = 0.0, lo_val = 0.0, hi_val = 0.0;
+    bool guard = false;
+    if (lane < 2) {                       // t (x[9]), p (x[8]): 2 / (1 + e) - 1
+      const int j = 9 - lane;
+      numer = 2.0; denom = 1.0 + etab[j]; off1 = -1.0; raw = x[j]; lo_val = -1.0; hi_val = 1.0; guard = v4;
+    } else if (lane < 5) {                // ws_i: dws / (1 + e) + minw
+      const int j = 5 + (lane - 2);
+      numer = dws; denom = 1.0 + etab[j]; off1 = minw; raw = x[j]; lo_val = minw; hi_val = dws + minw; guard = v4;
+    } else if (lane < 8) {                // centre: 2 d / (1 + e) - d + c_est   (v3: 2 d e' / (1 + e), Fitting_v3.py:86)
+      const int i = lane - 5;
+      const double ce = cen_est[i];
+      numer = v4 ? 2.0 * d : 2.0 * d * ((i == 2) ? etab[3] : etab[2 + i]);
+      denom = 1.0 + etab[2 + i]; off1 = -d; off2 = ce; raw = x[2 + i]; lo_val = -d + ce; hi_val = d + ce; guard = v4;
+    } else if (lane < 11) {               // norm_xp..: -d e / ((1 + e) (1 + e))
+      const double ex = etab[11 + (lane - 8)];
+      numer = -d * ex; denom = (1 + ex) * (1 + ex);
+    } else if (lane < 14) {               // norm_w_i (Fitting_v4.py:369-375)
+      const double w = x[5 + (lane - 11)], e = etab[14 + (lane - 11)];
+      const double dd = (w > 0) ? maxw * e + minw : minw * e + maxw;
+      numer = 0.5 * (maxw - minw) * e; denom = dd * dd;
+    } else if (lane < 16) {               // norm_p, norm_t: e / (1 + e e)
+      const double e = etab[17 + (lane - 14)];
+      numer = e; denom = 1 + e * e;
+    }
+    double r = numer / denom;
+    r = r + off1;
+    r = r + off2;
+    if (guard && raw >= LOGMAX) r = lo_val;
+    if (guard && raw <= -LOGMAX) r = hi_val;
+    if (lane < NSCAL_FIRST) scal[lane] = r;
+  }
+  __syncwarp();
+  if (lane < 3) scal[16 + lane] = 1.0 / scal[2 + lane];
+  else if (lane < 5) scal[19 + (lane - 3)] = sqrt(1 - scal[lane - 3] * scal[lane - 3]);
+  __syncwarp();
+  if (lane == 0) finish_consts_scalars<T>(fp, origin, x, etab, scal, true, vc);
+  __syncwarp();
 }
 
 }  // namespace lw
