@@ -1,5 +1,6 @@
-// C ABI of libia3b200.so (declared in include/ia3b200.h): handles, host-side orchestration
-// (buffer management, neighbour lists, dependency levels) and kernel launches.
+// C ABI of libia3b200.so (declared in include/ia3b200.h): handles, host-side orchestration (pooled
+// streams / events / device and pinned blocks, image upload, the round loop of the fit engine) and
+// kernel launches.  Neighbour lists, dependency relations and the brick table are built on the device.
 #include <algorithm>
 #include <atomic>
 #include <chrono>

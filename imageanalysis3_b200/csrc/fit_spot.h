@@ -1,7 +1,8 @@
 // One GaussianFit.fit() for one spot, written once for two executors:
-//   * WarpExec (fit_kernels.cu): 32 lanes of the warp that owns the spot; voxels are strided
-//     over the lanes, sums are combined with shuffles, the 10x10 algebra runs on lane 0 with
-//     its state in shared memory;
+//   * WarpExec (fit_kernels.cu): the 32 lanes of a warp; a batch of 32 voxels is one voxel per lane,
+//     the normal-equation sums are FP64 tensor-core tiles (pass_fused_mma).  The fit engine drives lmder
+//     with the register / shuffle algebra of lm_warp.h; the standalone GaussianFit kernel
+//     (k_generic_fit) uses run_lm below with the generic shared-memory algebra of lm_core.h;
 //   * SerialExec (tests/hostsim): one "lane" on the CPU, used to debug the numerics in a
 //     container without a GPU.  It is test infrastructure, never a product fallback.
 // Follows GaussianFit.__init__ / fit / to_natural_paramaters of External/Fitting_v4.py:166-393

@@ -5,17 +5,30 @@
 // gaussian_filter on a uint16 stack runs three 1-D correlations (axes 0,1,2); each pass
 // accumulates in double as   acc = x[0]*w[0];  for j = r..1: acc += (x[-j] + x[+j]) * w[j]
 // (outermost pair first, multiply and add NOT fused) and stores (uint16)acc -- truncation --
-// before the next axis reads it; boundary = reflect.  The kernels below reproduce that
-// arithmetic operation for operation (__dmul_rn / __dadd_rn are never contracted to FMA), so
-// the filtered volumes, and therefore the seeds, are bit-identical to scipy's.  The price is
-// ~91 FP64 instructions per voxel for the sigma=7.5 (61-tap) passes: this stage is bound by the
-// FP64 pipe, not by HBM; DESIGN.md states both rooflines.
+// before the next axis reads it; boundary = reflect.  Every kernel below delivers the bits of that
+// arithmetic; the filtered volumes, and therefore the seeds, are bit-identical to scipy's.
 //
-// Layout of one pass: the volume is viewed as [outer][L][inner] with the filter axis of
-// length L in the middle.  A block owns 128 "lines" x TL axis positions; the (TL + 2r) x 128
-// input tile is staged in shared memory as float (exact for uint16 and float32 inputs) with an
-// odd pitch, one thread walks one line and produces 8 outputs per step from a register window
-// of 8 + 2r doubles (8.5 shared loads per output instead of 61).
+// Kernels, in the order a uint16 stack meets them (one launch per axis per blur):
+//   k_gauss_short<R,L>    z pass of the dataset depths (L = 30, 50): the whole line in registers, reflected tap
+//                         indices are compile-time constants
+//   k_gauss_strided<R>    x pass: a thread slides a register window of 2R + 8 inputs along its line, the lanes
+//                         of a warp are consecutive in y (every warp load / store is one 64-byte request)
+//   k_gauss_contig<R> /   y pass: same window along the contiguous axis / (7 taps) a warp owns 256 consecutive
+//   k_gauss_row<3>        outputs, halo values come from the neighbouring lanes by shuffle
+// These do NOT replay scipy's 91 FP64 operations per 61-tap output: window values are kept biased so that a pair
+// sum is one integer add that already is the high word of a double, the taps are accumulated with FMA (32 FP64
+// instructions per output), and the few outputs whose fast sum lies within a guard band of an integer (where
+// truncation could differ) are recomputed in scipy's operation order (exact_from_global).  See DESIGN.md 4.1.
+//   k_gauss_axis<R,T>     general tiled kernel, scipy's operation order throughout (__dmul_rn / __dadd_rn are never
+//                         contracted to FMA): float32 and float64 stacks, unusual radii, ragged shapes.  A block owns
+//                         128 lines x TL axis positions; the (TL + 2r) x 128 input tile sits in shared memory (float for
+//                         uint16 / float32 inputs -- exact --, double for float64) with an odd pitch, one thread
+//                         walks one line and produces 8 outputs per step from a register window of 8 + 2r doubles.
+//   k_flags_u16 / k_flags 3x3x3 (or any size) max / min rank filters, candidate mask, threshold, edge test
+//   k_count_bits, k_scan_counts, k_emit   ordered compaction (np.where order, no atomics)
+//   k_box_background, k_hist_accum        histogram-mode backgrounds (normalize_local / normalize_background)
+// Bound: the 61-tap passes are FP64-pipe / issue bound (measured 0.77-0.85 ms per C2 pass against 0.13 ms of HBM
+// time), DRAM traffic per pass = algorithmic; DESIGN.md states both rooflines.
 #include <mutex>
 #include "ia3_device.h"
 #include "seed_kernels.h"
