@@ -56,6 +56,7 @@ EXPORTS = [
     "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count", "ia3_debug_stats",
     "ia3_timer_start", "ia3_timer_stop",
     "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
+    "ia3_stack_alloc", "ia3_stack_fetch", "ia3_corr_hot_pixels", "ia3_corr_mix", "ia3_corr_warp",
     "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_seed_gather_volume", "ia3_box_background",
     "ia3_seed_v2", "ia3_fft_gaussian", "ia3_seed_logratio", "ia3_stack_histogram",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
@@ -96,6 +97,11 @@ def load():
     lib.ia3_stack_wrap_device.argtypes = [vp, i32, i32, i32, i32, P(vp)]
     lib.ia3_stack_destroy.argtypes = [vp]
     lib.ia3_stack_trim.argtypes = [vp, i32]
+    lib.ia3_stack_alloc.argtypes = [i32, i32, i32, i32, P(vp)]
+    lib.ia3_stack_fetch.argtypes = [vp, vp]
+    lib.ia3_corr_hot_pixels.argtypes = [vp, dbl, dbl, P(i64)]
+    lib.ia3_corr_mix.argtypes = [P(vp), i32, vp, vp, i32, vp]
+    lib.ia3_corr_warp.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.ia3_seed_run.argtypes = [vp, P(SeedCfg), P(i64), P(SeedTiming)]
     lib.ia3_seed_fetch.argtypes = [vp, vp, vp, i64]
     lib.ia3_seed_fetch_volume.argtypes = [vp, i32, vp]
@@ -168,7 +174,11 @@ class Stack:
         lib = load()
         self._h = C.c_void_p()
         self._keep = None
-        if device_ptr is not None:
+        if im is None and device_ptr is None:        # an owned, uninitialised stack (destination of the corrections)
+            self.shape = tuple(int(s) for s in shape)
+            self.dtype = np.dtype(dtype)
+            _check(lib.ia3_stack_alloc(_NP2DT[self.dtype], *self.shape, C.byref(self._h)))
+        elif device_ptr is not None:
             self.shape = tuple(int(s) for s in shape)
             self.dtype = np.dtype(dtype)
             _check(lib.ia3_stack_wrap_device(C.c_void_p(int(device_ptr)), _NP2DT[self.dtype], *self.shape, C.byref(self._h)))
@@ -253,6 +263,56 @@ class Stack:
         _check(load().ia3_moment_fit(self._h, _ptr(cen), len(cen), C.byref(cfg), _ptr(out)))
         _count("h2d", cen.nbytes)
         _count("d2h", out.nbytes)
+        return out
+
+    # ---- pre-processing (correct_fov_image's compute core) ----------------------------------------
+    def fetch(self):
+        """the resident image as a numpy array"""
+        out = np.empty(self.shape, dtype=self.dtype)
+        _check(load().ia3_stack_fetch(self._h, _ptr(out)))
+        _count("d2h", out.nbytes)
+        return out
+
+    def remove_hot_pixels(self, hot_th=4, hot_pix_th=0.5):
+        """corrections.Remove_Hot_Pixels in place -> number of hot columns found"""
+        n = C.c_int64(0)
+        _check(load().ia3_corr_hot_pixels(self._h, float(hot_th), float(hot_pix_th), C.byref(n)))
+        return int(n.value)
+
+    @staticmethod
+    def mix(ins, bleed=None, illum=None, out=None):
+        """out = illumination(bleed-through(ins)); bleed (len(ins), X, Y), illum (X, Y), both of one floating dtype"""
+        ins = list(ins)
+        out = Stack(shape=ins[0].shape, dtype=np.uint16) if out is None else out
+        dts = {np.asarray(a).dtype for a in (bleed, illum) if a is not None}
+        if len(dts) > 1 or (dts and next(iter(dts)) not in (np.dtype(np.float32), np.dtype(np.float64))):
+            raise TypeError("bleed-through and illumination profiles of one call are both float32 or both float64")
+        f64 = bool(dts) and next(iter(dts)) == np.dtype(np.float64)
+        bleed = None if bleed is None else np.ascontiguousarray(bleed)
+        illum = None if illum is None else np.ascontiguousarray(illum)
+        if bleed is not None and bleed.shape != (len(ins),) + tuple(ins[0].shape[1:]):
+            raise ValueError(f"bleed-through rows of shape {bleed.shape} do not match {len(ins)} stacks of {ins[0].shape}")
+        if illum is not None and illum.shape != tuple(ins[0].shape[1:]):
+            raise ValueError(f"illumination profile of shape {illum.shape} does not match stacks of {ins[0].shape}")
+        arr = (C.c_void_p * len(ins))(*[s._h for s in ins])
+        _check(load().ia3_corr_mix(arr, len(ins), _ptr(bleed), _ptr(illum), int(f64), out._h))
+        _count("h2d", (0 if bleed is None else bleed.nbytes) + (0 if illum is None else illum.nbytes))
+        return out
+
+    def warp(self, drift=None, chroma=None, out=None):
+        """map_coordinates(im, grid + chroma - drift, order 3, mode 'nearest') -> a new uint16 stack"""
+        out = Stack(shape=self.shape, dtype=np.uint16) if out is None else out
+        d = None if drift is None else np.ascontiguousarray(drift, dtype=np.float32)
+        cz = 0
+        if chroma is not None:
+            chroma = np.ascontiguousarray(chroma)
+            if chroma.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+                chroma = chroma.astype(np.float64)                           # what numpy promotes int64 + profile to
+            if chroma.ndim != 4 or chroma.shape[0] != 3 or tuple(chroma.shape[2:]) != tuple(self.shape[1:]):
+                raise ValueError(f"chromatic profile of shape {chroma.shape} does not match a stack of {self.shape}")
+            cz = chroma.shape[1]
+        _check(load().ia3_corr_warp(self._h, _ptr(d), _ptr(chroma), int(chroma is not None and chroma.dtype == np.float64), int(cz), out._h))
+        _count("h2d", 0 if chroma is None else chroma.nbytes)
         return out
 
     def histogram(self):

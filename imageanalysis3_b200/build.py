@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libia3b200.so")
-SOURCES = ["capi.cu", "seed_kernels.cu", "fit_kernels.cu", "aux_kernels.cu"]
+SOURCES = ["capi.cu", "seed_kernels.cu", "fit_kernels.cu", "aux_kernels.cu", "corr_kernels.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

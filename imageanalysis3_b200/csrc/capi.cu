@@ -21,6 +21,7 @@
 #include "ia3_device.h"
 #include "seed_kernels.h"
 #include "aux_kernels.h"
+#include "corr_kernels.h"
 
 namespace ia3 {
 
@@ -400,7 +401,7 @@ int ia3_timer_stop(float* ms) {
 // or registered with CUDA by the caller) is handed to the copy engine directly.
 constexpr size_t kStageChunk = (size_t)4 << 20;     // one DMA
 constexpr size_t kStageJob = (size_t)16 << 20;      // one queue entry (contiguous part of an image)
-struct StageJob { const char* src; char* dst; size_t bytes; std::atomic<int>* pending; std::atomic<int>* err; };
+struct StageJob { const char* src; char* dst; size_t bytes; std::atomic<int>* pending; std::atomic<int>* err; bool down = false; };
 static std::mutex& g_sq_mu = *new std::mutex;
 static std::condition_variable& g_sq_cv = *new std::condition_variable;
 static std::condition_variable& g_sq_done = *new std::condition_variable;
@@ -408,7 +409,7 @@ static std::vector<StageJob>& g_sq = *new std::vector<StageJob>;
 static size_t g_sq_head = 0;
 static std::once_flag g_sq_once;
 
-static void stage_worker(int device, cudaStream_t us) {
+static void stage_worker(int device, cudaStream_t us, cudaStream_t ds) {
   void* buf[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
   bool used[2] = {false, false};
@@ -425,6 +426,23 @@ static void stage_worker(int device, cudaStream_t us) {
       if (g_sq_head == g_sq.size()) { g_sq.clear(); g_sq_head = 0; }
     }
     cudaError_t e = ok ? cudaSuccess : cudaErrorMemoryAllocation;
+    if (j.down) {
+      // device -> pageable host: the DMA of one chunk runs while the previous one is copied out of its pinned buffer
+      for (int i = 0; i < 2 && e == cudaSuccess; ++i) if (used[i]) { e = cudaEventSynchronize(ev[i]); used[i] = false; }
+      size_t prev_off = 0, prev_nb = 0; int prev_k = -1;
+      for (size_t off = 0; off < j.bytes && e == cudaSuccess; off += kStageChunk) {
+        const size_t nb = std::min(kStageChunk, j.bytes - off);
+        e = cudaMemcpyAsync(buf[k], j.src + off, nb, cudaMemcpyDeviceToHost, ds);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[k], ds);
+        if (e == cudaSuccess && prev_k >= 0) { e = cudaEventSynchronize(ev[prev_k]); if (e == cudaSuccess) memcpy(j.dst + prev_off, buf[prev_k], prev_nb); }
+        prev_k = k; prev_off = off; prev_nb = nb;
+        k ^= 1;
+      }
+      if (e == cudaSuccess && prev_k >= 0) { e = cudaEventSynchronize(ev[prev_k]); if (e == cudaSuccess) memcpy(j.dst + prev_off, buf[prev_k], prev_nb); }
+      if (e != cudaSuccess) j.err->store(1);
+      if (j.pending->fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(g_sq_mu); g_sq_done.notify_all(); }
+      continue;
+    }
     for (size_t off = 0; off < j.bytes && e == cudaSuccess; off += kStageChunk) {
       const size_t nb = std::min(kStageChunk, j.bytes - off);
       if (used[k]) e = cudaEventSynchronize(ev[k]);            // the DMA that last read this chunk is done
@@ -446,6 +464,48 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice;
 }
 
+static cudaStream_t g_down_stream = nullptr;
+static int start_stage_workers() {
+  cudaStream_t us;
+  if (upload_stream(&us)) return -1;
+  std::call_once(g_sq_once, [us] {
+    int nthr = 6;
+    if (const char* ev = getenv("IA3_STAGE_THREADS")) nthr = atoi(ev);
+    nthr = std::max(1, std::min(nthr, 32));
+    if (cudaStreamCreateWithFlags(&g_down_stream, cudaStreamNonBlocking) != cudaSuccess) g_down_stream = us;
+    for (int i = 0; i < nthr; ++i) std::thread(stage_worker, g_device, us, g_down_stream).detach();
+  });
+  return 0;
+}
+
+// device -> host copy of a whole image; pageable destinations go through the staging workers
+static int download_image(const void* d_src, void* dst, size_t bytes, cudaStream_t st) {
+  IA3_CUDA(cudaStreamSynchronize(st));                              // the stack's kernels are done
+  if (is_pinned(dst)) {
+    IA3_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    IA3_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  if (start_stage_workers()) return -1;
+  std::atomic<int> pending{0}, err{0};
+  const int njobs = (int)((bytes + kStageJob - 1) / kStageJob);
+  pending.store(njobs);
+  {
+    std::lock_guard<std::mutex> lk(g_sq_mu);
+    for (int j = 0; j < njobs; ++j) {
+      const size_t off = (size_t)j * kStageJob;
+      g_sq.push_back(StageJob{static_cast<const char*>(d_src) + off, static_cast<char*>(dst) + off, std::min(kStageJob, bytes - off), &pending, &err, true});
+    }
+  }
+  g_sq_cv.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(g_sq_mu);
+    g_sq_done.wait(lk, [&] { return pending.load() == 0; });
+  }
+  if (err.load()) { set_error("image download failed in the staging workers"); return -1; }
+  return 0;
+}
+
 static int upload_image(ia3_stack* s, const void* im, size_t bytes) {
   cudaStream_t us;
   if (upload_stream(&us)) return -1;
@@ -456,12 +516,7 @@ static int upload_image(ia3_stack* s, const void* im, size_t bytes) {
     if (e == cudaSuccess) e = cudaEventRecord(s->ev[5], us);
   } else {
     IA3_STAT("  upload: pinned staging");
-    std::call_once(g_sq_once, [us] {
-      int nthr = 6;
-      if (const char* ev = getenv("IA3_STAGE_THREADS")) nthr = atoi(ev);
-      nthr = std::max(1, std::min(nthr, 32));
-      for (int i = 0; i < nthr; ++i) std::thread(stage_worker, g_device, us).detach();
-    });
+    if (start_stage_workers()) return -1;
     std::atomic<int> pending{0}, err{0};
     const int njobs = (int)((bytes + kStageJob - 1) / kStageJob);
     pending.store(njobs);
@@ -1641,6 +1696,123 @@ int ia3_gauss_eval(const ia3_fit_cfg* cfg, double delta_center, const double* p_
   if (small_copy(hp + o_out, d_out, b_out, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   memcpy(out, hp + o_out, b_out);
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- pre-processing: correct_fov_image's compute core (corr_kernels.cu) -----------------------
+extern "C" {
+
+int ia3_stack_alloc(int dtype, int Z, int X, int Y, ia3_stack** out) {
+  if (ensure_device()) return -1;
+  if (!out) { set_error("null argument"); return -1; }
+  ia3_stack* s = new ia3_stack();
+  if (stack_common(s, dtype, Z, X, Y)) { ia3_stack_destroy(s); return -1; }
+  if (dev_alloc(&s->d_im, s->nvox * dtype_size(dtype))) { ia3_stack_destroy(s); return -1; }
+  s->owns = true;
+  *out = s;
+  return 0;
+}
+
+int ia3_stack_fetch(ia3_stack* s, void* out) {
+  if (ensure_device()) return -1;
+  if (!s || !out) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  return download_image(s->d_im, out, s->nvox * dtype_size(s->dtype), s->stream);
+}
+
+static int corr_check(const ia3_stack* s, const char* who) {
+  if (!s) { set_error("null argument"); return -1; }
+  if (!s->d_im) { set_error("the stack's image was released (ia3_stack_trim)"); return -1; }
+  if (s->dtype != IA3_DTYPE_U16) { set_error(std::string(who) + " works on uint16 stacks (what the microscope files hold)"); return -1; }
+  return 0;
+}
+
+int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t* n_hot) {
+  IA3_STAT("ia3_corr_hot_pixels");
+  if (ensure_device()) return -1;
+  if (corr_check(s, "ia3_corr_hot_pixels")) return -1;
+  cudaStream_t st = s->stream;
+  Scoped sc;
+  const long long nxy = (long long)s->X * s->Y;
+  const int cap = 1 << 16;
+  int* d_cnt = nullptr; int* d_list = nullptr; int* d_n = nullptr; float* d_vals = nullptr; void* h = nullptr;
+  if (sc.dalloc(&d_cnt, (size_t)nxy * 4) || sc.dalloc(&d_list, (size_t)cap * 4) || sc.dalloc(&d_n, 256) || sc.halloc(&h, 256 + (size_t)cap * 4)) return -1;
+  if (launch_hot_count((const uint16_t*)s->d_im, s->Z, s->X, s->Y, (float)hot_th, d_cnt, st)) return -1;
+  if (launch_hot_select(d_cnt, nxy, hot_pix_th * (double)s->Z, d_list, d_n, cap, st)) return -1;
+  if (small_copy(h, d_n, sizeof(int), st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  const int n = *static_cast<int*>(h);
+  if (n_hot) *n_hot = n;
+  if (n == 0) return 0;
+  if (n > cap) { set_error("ia3_corr_hot_pixels: more than 65536 hot columns -- check hot_th"); return -1; }
+  int* hl = reinterpret_cast<int*>(static_cast<char*>(h) + 256);
+  if (small_copy(hl, d_list, (size_t)n * 4, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  std::sort(hl, hl + n);                                     // np.where order: the fix is sequential and in place
+  if (small_copy(d_list, hl, (size_t)n * 4, st)) return -1;
+  if (sc.dalloc(&d_vals, (size_t)n * s->Z * 4)) return -1;
+  if (launch_hot_fix((uint16_t*)s->d_im, s->Z, s->X, s->Y, d_list, n, d_vals, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void* illum, int profile_f64, ia3_stack* out) {
+  IA3_STAT("ia3_corr_mix");
+  if (ensure_device()) return -1;
+  if (!ins || n_in < 1 || n_in > 16 || !out) { set_error("bad argument"); return -1; }
+  if (corr_check(out, "ia3_corr_mix")) return -1;
+  for (int j = 0; j < n_in; ++j) {
+    if (corr_check(ins[j], "ia3_corr_mix")) return -1;
+    if (ins[j]->Z != out->Z || ins[j]->X != out->X || ins[j]->Y != out->Y) { set_error("ia3_corr_mix: stacks differ in shape"); return -1; }
+    if (bleed && ins[j] == out) { set_error("ia3_corr_mix: bleed-through mixing cannot run in place"); return -1; }
+  }
+  if (!bleed && n_in != 1) { set_error("ia3_corr_mix: several inputs need a bleed-through profile"); return -1; }
+  cudaStream_t st = out->stream;
+  Scoped sc;
+  const size_t es = profile_f64 ? 8 : 4, nxy = (size_t)out->X * out->Y;
+  const size_t b_bleed = bleed ? (size_t)n_in * nxy * es : 0, b_illum = illum ? nxy * es : 0;
+  char* d_prof = nullptr; const uint16_t** d_ptrs = nullptr; void* h = nullptr;
+  if (sc.dalloc(&d_prof, b_bleed + b_illum + 256) || sc.dalloc(&d_ptrs, 256) || sc.halloc(&h, 256)) return -1;
+  // the profiles are per-dataset constants: a caller that corrects many fields of view keeps them pinned, the copy
+  // below then runs at link speed; pageable arrays go through the driver's staging
+  if (bleed) IA3_CUDA(cudaMemcpyAsync(d_prof, bleed, b_bleed, cudaMemcpyHostToDevice, st));
+  if (illum) IA3_CUDA(cudaMemcpyAsync(d_prof + b_bleed, illum, b_illum, cudaMemcpyHostToDevice, st));
+  const uint16_t** hp = static_cast<const uint16_t**>(h);
+  for (int j = 0; j < n_in; ++j) hp[j] = (const uint16_t*)ins[j]->d_im;
+  if (small_copy(d_ptrs, hp, (size_t)n_in * sizeof(void*), st)) return -1;
+  int rc;
+  if (profile_f64) rc = launch_mix<double>(d_ptrs, n_in, bleed ? (const double*)d_prof : nullptr, illum ? (const double*)(d_prof + b_bleed) : nullptr,
+                                           (uint16_t*)out->d_im, (long long)nxy, (long long)out->nvox, st);
+  else rc = launch_mix<float>(d_ptrs, n_in, bleed ? (const float*)d_prof : nullptr, illum ? (const float*)(d_prof + b_bleed) : nullptr,
+                              (uint16_t*)out->d_im, (long long)nxy, (long long)out->nvox, st);
+  if (rc) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ia3_corr_warp(ia3_stack* in, const float* drift, const void* chroma, int chroma_f64, int chroma_z, ia3_stack* out) {
+  IA3_STAT("ia3_corr_warp");
+  if (ensure_device()) return -1;
+  if (corr_check(in, "ia3_corr_warp") || corr_check(out, "ia3_corr_warp")) return -1;
+  if (in == out) { set_error("ia3_corr_warp cannot run in place"); return -1; }
+  if (in->Z != out->Z || in->X != out->X || in->Y != out->Y) { set_error("ia3_corr_warp: stacks differ in shape"); return -1; }
+  if (chroma && chroma_z != 1 && chroma_z != in->Z) { set_error("ia3_corr_warp: the chromatic profile has 1 or Z planes per axis"); return -1; }
+  cudaStream_t st = out->stream;
+  Scoped sc;
+  const long long np_ = warp_padded_voxels(in->Z, in->X, in->Y);
+  double* bufA = nullptr; double* bufB = nullptr; double* d_h = nullptr; char* d_ch = nullptr; void* h = nullptr;
+  const size_t b_ch = chroma ? (size_t)3 * chroma_z * in->X * in->Y * (chroma_f64 ? 8 : 4) : 0;
+  if (sc.dalloc(&bufA, (size_t)np_ * 8) || sc.dalloc(&bufB, (size_t)np_ * 8) || sc.dalloc(&d_h, 1024) || sc.halloc(&h, 1024)) return -1;
+  if (chroma && sc.dalloc(&d_ch, b_ch)) return -1;
+  const int nt = spline_taps(static_cast<double*>(h), 128);
+  if (nt < 0) { set_error("spline tap table"); return -1; }
+  if (small_copy(d_h, h, (size_t)nt * 8, st)) return -1;
+  if (chroma) IA3_CUDA(cudaMemcpyAsync(d_ch, chroma, b_ch, cudaMemcpyHostToDevice, st));
+  const float d0 = drift ? drift[0] : 0.0f, d1 = drift ? drift[1] : 0.0f, d2 = drift ? drift[2] : 0.0f;
+  if (launch_warp((const uint16_t*)in->d_im, in->Z, in->X, in->Y, d_h, bufA, bufB, d_ch, chroma_f64, chroma_z, d0, d1, d2, (uint16_t*)out->d_im, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -1,0 +1,286 @@
+// Pre-processing kernels: the compute core of io_tools/load.py correct_fov_image, the step
+// that hands the seed / fit stages their stacks.  All whole-volume, HBM-bound passes on uint16 channel stacks.
+//
+//   k_hot_count      per (x, y) column: in how many planes is the voxel brighter than hot_th x the mean of its four
+//                    neighbours (corrections.py:496-499: np.roll, so borders wrap, and the y+1... neighbour is the
+//                    y-1 one taken twice, as the reference does)
+//   k_hot_fix        replaces the hot columns one after the other, in np.where order, by the float32 mean of their four
+//                    neighbours (:505-509); an already replaced neighbour contributes its float32 value, the final
+//                    store truncates to uint16 like .astype (one CTA: the list is tens of columns long)
+//   k_mix            bleed-through mixing sum_j im_j * profile[i, j] in float32, clip, truncate (io_tools/load.py:
+//                    347-367) fused with the illumination division (:369-381)
+//   k_spline_iir /   scipy.ndimage.spline_filter(np.pad(im, 12, 'edge'), 3, mode='nearest'): the cubic B-spline prefilter
+//   k_spline_fir_y   with pole z = sqrt 3 - 2 on the half-sample-symmetric extension of each padded line.  Along z and x
+//                    the two-pass recursion scipy runs, one thread per line; along y (contiguous) the equivalent
+//                    symmetric filter -6z/(1-z^2) z^|k| from shared memory (|z|^28 < 1e-16: 57 taps).  Both agree
+//                    with scipy's coefficients to ~1e-15 relative (checked in numpy before they were written)
+//   k_warp           map_coordinates(im, coords, order=3, mode='nearest') (:424-459) with coords = grid + chromatic
+//                    profile - drift formed exactly as numpy promotes them, 64-tap cubic interpolation on the
+//                    prefiltered volume, uint16 output rounded half up and saturated like ndimage's integer store
+#include <algorithm>
+#include <cmath>
+#include "ia3_device.h"
+#include "corr_kernels.h"
+
+namespace ia3 {
+
+__global__ void __launch_bounds__(256) k_hot_count(const uint16_t* __restrict__ im, int Z, int X, int Y, float hot_th, int* __restrict__ cnt) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)X * Y) return;
+  const int y = (int)(t % Y), x = (int)(t / Y);
+  const int xm = (x + X - 1) % X, xp = (x + 1) % X, ym = (y + Y - 1) % Y;
+  int c = 0;
+  for (int z = 0; z < Z; ++z) {
+    const uint16_t* pl = im + (long long)z * X * Y;
+    // np.roll(im,1,1)[x] = im[x-1]; roll(im,-1,1)[x] = im[x+1]; roll(im,1,2)[y] = im[y-1], taken twice (:496)
+    const float a = (float)pl[(long long)xm * Y + y], b = (float)pl[(long long)xp * Y + y], d = (float)pl[(long long)x * Y + ym];
+    const float conv = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, b), d), d), 4.0f);
+    if ((float)pl[(long long)x * Y + y] > __fmul_rn(hot_th, conv)) ++c;
+  }
+  cnt[t] = c;
+}
+
+__global__ void __launch_bounds__(256) k_hot_select(const int* __restrict__ cnt, long long n, double thr, int* __restrict__ out, int* __restrict__ count, int cap) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if ((double)cnt[t] > thr) { const int p = atomicAdd(count, 1); if (p < cap) out[p] = (int)t; }
+}
+
+// list: flat x * Y + y indices in ascending (np.where) order; vals: n x Z float32 scratch
+__global__ void __launch_bounds__(128) k_hot_fix(uint16_t* __restrict__ im, int Z, int X, int Y, const int* __restrict__ list, int n, float* __restrict__ vals) {
+  for (int i = 0; i < n; ++i) {
+    const int x = list[i] / Y, y = list[i] % Y;
+    const bool interior = x > 0 && y > 0 && x < X - 1 && y < Y - 1;
+    for (int z = threadIdx.x; z < Z; z += blockDim.x) {
+      float v;
+      if (interior) {
+        float nb[4];
+        const int nx[4] = {x + 1, x - 1, x, x}, ny[4] = {y, y, y + 1, y - 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int key = nx[k] * Y + ny[k];
+          float w = (float)im[((long long)z * X + nx[k]) * Y + ny[k]];
+          for (int j = 0; j < i; ++j) if (list[j] == key) w = vals[(long long)j * Z + z];      // already replaced: its float32 value
+          nb[k] = w;
+        }
+        v = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(nb[0], nb[1]), nb[2]), nb[3]), 4.0f);
+      } else {
+        v = (float)im[((long long)z * X + x) * Y + y];
+      }
+      vals[(long long)i * Z + z] = v;
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < n; ++i) {
+    const int x = list[i] / Y, y = list[i] % Y;
+    for (int z = threadIdx.x; z < Z; z += blockDim.x) im[((long long)z * X + x) * Y + y] = (uint16_t)(int)vals[(long long)i * Z + z];
+  }
+}
+
+__device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }      // no contraction into fma: numpy rounds each step
+__device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+
+// Tp = the profiles' dtype: uint16 * float32 stays float32 in numpy, uint16 * float64 is float64
+template <typename Tp>
+__global__ void __launch_bounds__(256) k_mix(const uint16_t* const* __restrict__ ins, int n_in, const Tp* __restrict__ bleed /* n_in x XY or null */,
+                                             const Tp* __restrict__ illum /* XY or null */, uint16_t* __restrict__ out, long long XY, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const long long pix = t % XY;
+    uint16_t u;
+    if (bleed) {
+      Tp acc = rn_mul((Tp)ins[0][t], bleed[pix]);
+      for (int j = 1; j < n_in; ++j) acc = rn_add(acc, rn_mul((Tp)ins[j][t], bleed[(long long)j * XY + pix]));
+      acc = acc > (Tp)65535 ? (Tp)65535 : acc;
+      acc = acc < (Tp)0 ? (Tp)0 : acc;
+      u = (uint16_t)(int)acc;
+    } else {
+      u = ins[0][t];
+    }
+    // the division runs on float32(im): float32 / float32 profile, or float64 when the profile is float64
+    if (illum) u = (uint16_t)(int)rn_div((Tp)(float)u, illum[pix]);
+    out[t] = u;
+  }
+}
+
+constexpr int NPAD = 12;        // scipy.ndimage._interpolation._prepad_for_spline_filter
+constexpr int KTAP = 28;
+
+__device__ __forceinline__ int refl(int i, int n) {     // d c b a | a b c d | d c b a
+  const int p = 2 * n;
+  int m = i % p;
+  if (m < 0) m += p;
+  return m < n ? m : p - 1 - m;
+}
+
+// Axis 0 / axis 1 of the prefilter as the two-pass recursion itself (what scipy runs): one thread per line, lines
+// side by side along y so every step of the recursion is a coalesced row of loads / stores.
+//   c+[0] = 6 (x[0] + z sum_k z^k x[k])  (half-sample-symmetric start, 28 terms),  c+[i] = 6 x[i] + z c+[i-1]
+//   c[n-1] = z / (z - 1) c+[n-1],  c[i] = z (c[i+1] - c+[i])
+// Tsrc = uint16: reads the image through the 'edge' padding (first pass); double: the padded volume, in place.
+template <typename Tsrc>
+__global__ void __launch_bounds__(128) k_spline_iir(const Tsrc* src, double* dst /* may be src */, int Z, int X, int Y, int axis) {
+  const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
+  const int L = axis == 0 ? PZ : PX, O = axis == 0 ? PX : PZ;          // line length, number of lines per y
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)O * PY) return;
+  const int y = (int)(t % PY), o = (int)(t / PY);
+  const long long stride = axis == 0 ? (long long)PX * PY : PY;
+  const long long base = axis == 0 ? (long long)o * PY + y : (long long)o * PX * PY + y;
+  const double zp = -0.26794919243112270647;                            // sqrt(3) - 2
+  auto in = [&](int i) -> double {
+    if constexpr (sizeof(Tsrc) == 2) {
+      const int zz = axis == 0 ? i : o, xx = axis == 0 ? o : i;
+      const int oz = min(max(zz - NPAD, 0), Z - 1), ox = min(max(xx - NPAD, 0), X - 1), oy = min(max(y - NPAD, 0), Y - 1);
+      return (double)src[((long long)oz * X + ox) * Y + oy];
+    } else {
+      return src[base + (long long)i * stride];
+    }
+  };
+  double s = 0.0, zk = 1.0;
+  for (int k = 0; k < KTAP; ++k) { s += zk * in(refl(k, L)); zk *= zp; }
+  double c = 6.0 * (in(0) + zp * s);
+  dst[base] = c;
+#pragma unroll 4
+  for (int i = 1; i < L; ++i) {
+    c = 6.0 * in(i) + zp * c;
+    dst[base + (long long)i * stride] = c;
+  }
+  c = zp / (zp - 1.0) * c;
+  dst[base + (long long)(L - 1) * stride] = c;
+#pragma unroll 4
+  for (int i = L - 2; i >= 0; --i) {
+    c = zp * (c - dst[base + (long long)i * stride]);
+    dst[base + (long long)i * stride] = c;
+  }
+}
+
+// Axis 2 (the contiguous one) as the equivalent symmetric filter -6z/(1-z^2) z^|k| out of shared memory: a block stages
+// a row segment plus 28 values either side (half-sample-symmetric beyond the row's ends)
+constexpr int SEG = 1024;
+__global__ void __launch_bounds__(256) k_spline_fir_y(const double* __restrict__ src, double* __restrict__ dst, int PY, const double* __restrict__ h) {
+  __shared__ double sm[SEG + 2 * KTAP];
+  __shared__ double hs[2 * KTAP + 1];
+  const long long row = blockIdx.x;
+  const int y0 = blockIdx.y * SEG;
+  const double* r = src + row * PY;
+  for (int j = threadIdx.x; j < SEG + 2 * KTAP; j += 256) sm[j] = r[refl(y0 - KTAP + j, PY)];
+  if (threadIdx.x < 2 * KTAP + 1) hs[threadIdx.x] = h[threadIdx.x];
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < SEG / 256; ++m) {
+    const int j = threadIdx.x + 256 * m;
+    if (y0 + j >= PY) break;
+    double acc = 0.0;
+#pragma unroll 19
+    for (int k = 0; k <= 2 * KTAP; ++k) acc += hs[k] * sm[j + k];
+    dst[row * PY + y0 + j] = acc;
+  }
+}
+
+__device__ __forceinline__ void cubic_w(double t, double* w) {       // ndimage's cubic B-spline weights at offset t in [0, 1)
+  const double y = t, z = 1.0 - t;
+  w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+  w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+  w[0] = z * z * z / 6.0;
+  w[3] = 1.0 - w[0] - w[1] - w[2];
+}
+
+template <typename Tc>
+__global__ void __launch_bounds__(256) k_warp(const double* __restrict__ coef, int Z, int X, int Y, const Tc* __restrict__ chroma /* 3 x CZ x X x Y or null */,
+                                              int CZ, float d0, float d1, float d2, uint16_t* __restrict__ out) {
+  const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
+  const long long n = (long long)Z * X * Y;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int y = (int)(t % Y), x = (int)((t / Y) % X), z = (int)(t / ((long long)X * Y));
+  // coords = int64 grid + float32 profile (-> float64) - float32 drift (-> float64)     io_tools/load.py:441-449
+  double c[3] = {(double)z, (double)x, (double)y};
+  if (chroma) {
+    const long long plane = (long long)CZ * X * Y, off = ((long long)(CZ == 1 ? 0 : z) * X + x) * Y + y;
+    c[0] = c[0] + (double)chroma[off]; c[1] = c[1] + (double)chroma[plane + off]; c[2] = c[2] + (double)chroma[2 * plane + off];
+  }
+  c[0] = c[0] - (double)d0; c[1] = c[1] - (double)d1; c[2] = c[2] - (double)d2;
+  const int dims[3] = {PZ, PX, PY};
+  int fl[3];
+  double w[3][4];
+  for (int a = 0; a < 3; ++a) {
+    double cc = c[a] + (double)NPAD;
+    cc = fmin(fmax(cc, 0.0), (double)(dims[a] - 1));          // mode='nearest' on the padded extent
+    const double f = floor(cc);
+    fl[a] = (int)f;
+    cubic_w(cc - f, w[a]);
+  }
+  double acc = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    const int iz = min(max(fl[0] - 1 + i, 0), PZ - 1);
+    for (int j = 0; j < 4; ++j) {
+      const int ix = min(max(fl[1] - 1 + j, 0), PX - 1);
+      const double* row = coef + ((long long)iz * PX + ix) * PY;
+      for (int k = 0; k < 4; ++k) {
+        const int iy = min(max(fl[2] - 1 + k, 0), PY - 1);
+        acc += row[iy] * w[0][i] * w[1][j] * w[2][k];
+      }
+    }
+  }
+  double r = acc > 0.0 ? acc + 0.5 : 0.0;                     // ndimage's store to an unsigned integer type
+  r = r > 65535.0 ? 65535.0 : r;
+  out[t] = (uint16_t)(unsigned)r;
+}
+
+int launch_hot_count(const uint16_t* im, int Z, int X, int Y, float hot_th, int* cnt, cudaStream_t st) {
+  const long long n = (long long)X * Y;
+  k_hot_count<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(im, Z, X, Y, hot_th, cnt);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+int launch_hot_select(const int* cnt, long long n, double thr, int* out, int* count, int cap, cudaStream_t st) {
+  IA3_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+  k_hot_select<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cnt, n, thr, out, count, cap);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, float* vals, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_hot_fix<<<1, 128, 0, st>>>(im, Z, X, Y, list, n, vals);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+template <typename Tp>
+int launch_mix(const uint16_t* const* d_ins, int n_in, const Tp* bleed, const Tp* illum, uint16_t* out, long long XY, long long n, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_mix<Tp><<<148 * 8, 256, 0, st>>>(d_ins, n_in, bleed, illum, out, XY, n);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+template int launch_mix<float>(const uint16_t* const*, int, const float*, const float*, uint16_t*, long long, long long, cudaStream_t);
+template int launch_mix<double>(const uint16_t* const*, int, const double*, const double*, uint16_t*, long long, long long, cudaStream_t);
+int spline_taps(double* h, int cap) {
+  if (cap < 2 * KTAP + 1) return -1;
+  const double z = std::sqrt(3.0) - 2.0, c0 = -6.0 * z / (1.0 - z * z);
+  for (int k = -KTAP; k <= KTAP; ++k) h[k + KTAP] = c0 * std::pow(z, std::abs(k));
+  return 2 * KTAP + 1;
+}
+long long warp_padded_voxels(int Z, int X, int Y) { return (long long)(Z + 2 * NPAD) * (X + 2 * NPAD) * (Y + 2 * NPAD); }
+int launch_warp(const uint16_t* im, int Z, int X, int Y, const double* d_h, double* bufA, double* bufB, const void* chroma, int chroma_f64, int CZ,
+                float d0, float d1, float d2, uint16_t* out, cudaStream_t st) {
+  const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
+  k_spline_iir<uint16_t><<<(unsigned)(((long long)PX * PY + 127) / 128), 128, 0, st>>>(im, bufA, Z, X, Y, 0);
+  IA3_LAUNCH_CHECK();
+  k_spline_iir<double><<<(unsigned)(((long long)PZ * PY + 127) / 128), 128, 0, st>>>(bufA, bufA, Z, X, Y, 1);
+  IA3_LAUNCH_CHECK();
+  k_spline_fir_y<<<dim3((unsigned)(PZ * PX), (unsigned)((PY + SEG - 1) / SEG)), 256, 0, st>>>(bufA, bufB, PY, d_h);
+  IA3_LAUNCH_CHECK();
+  bufA = bufB;
+  const long long n = (long long)Z * X * Y;
+  if (chroma_f64) k_warp<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bufA, Z, X, Y, (const double*)chroma, CZ, d0, d1, d2, out);
+  else k_warp<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bufA, Z, X, Y, (const float*)chroma, CZ, d0, d1, d2, out);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ia3

@@ -229,8 +229,85 @@ def main_extra():
     print("extra_r2.npz", os.path.getsize(os.path.join(OUT, "extra_r2.npz")), {k: np.shape(v) for k, v in out.items() if k != "meta"})
 
 
+def corr_case(seed=5, Z=8, X=40, Y=48, nbuf=2):
+    """a synthetic three-colour .dax movie with hot columns, its correction profiles and the frames array"""
+    rng = np.random.default_rng(seed)
+    chs = ['750', '647', '561']
+    ims = [synth((Z, X, Y), 10, 20 + i) for i in range(3)]
+    for i, im in enumerate(ims):
+        im[:, 10 + i, 12] = 30000                  # isolated hot columns
+        im[:, 20, 20 + i] = 9000                   # two adjacent ones, both detected (the y + 1 neighbour is not looked at):
+        im[:, 20, 21 + i] = 29000                  # the sequential fix of the second reads the replaced first
+        im[:, 0, 5] = 31000                        # on the border: detected (np.roll wraps) but never replaced
+    frames = np.zeros((2 * nbuf + Z * 3, X, Y), np.uint16)
+    for c in range(3):
+        s0 = nbuf + (c - nbuf) % 3
+        frames[s0:s0 + Z * 3:3] = ims[c]
+    illum = {ch: (1 + 0.2 * rng.random((X, Y))).astype(np.float32) for ch in chs}
+    bleed = (np.eye(3)[:, :, None, None] + 0.05 * rng.random((3, 3, X, Y))).astype(np.float32)
+    xx, yy = np.meshgrid(np.arange(X), np.arange(Y), indexing='ij')
+    chrom = {ch: np.stack([0.2 * np.ones((1, X, Y)), (0.5 * np.sin(xx / 9.))[None], (0.4 * np.cos(yy / 7.))[None]]).astype(np.float32)
+             if ch != '647' else None for ch in chs}
+    return chs, ims, frames, illum, bleed, chrom, nbuf
+
+
+def main_corr():
+    """tests/golden/corr_r2.npz: io_tools/load.py correct_fov_image, the UNMODIFIED reference function (lifted with
+    its helpers by ref_loader.load_corrections) run on a synthetic .dax movie; every case is also asserted equal to
+    oracle/correct_oracle.py, which pins that restatement."""
+    import tempfile
+    from oracle import correct_oracle
+    warnings.simplefilter("ignore")
+    ns = ref_loader.load_corrections()
+    chs, ims, frames, illum, bleed, chrom, nbuf = corr_case()
+    Z, X, Y = ims[0].shape
+    d = tempfile.mkdtemp()
+    fn = os.path.join(d, 'Conv_zscan_00.dax')
+    frames.tofile(fn)
+    with open(fn.replace('.dax', '.inf'), 'w') as fh:
+        fh.write(f"frame dimensions = {Y} x {X}\nnumber of frames = {frames.shape[0]}\n little endian\n")
+    kw = dict(single_im_size=[Z, X, Y], all_channels=chs, num_buffer_frames=nbuf, num_empty_frames=0, corr_channels=chs,
+              illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom, drift_channel='561')
+    off = dict(hot_pixel_corr=False, bleed_corr=False, illumination_corr=False, chromatic_corr=False)
+    drift = [0.4, -1.3, 2.2]
+    cases = {
+        "all_drift": (['750', '647'], drift, {}, True),
+        "all_nodrift": (['561'], None, {}, True),
+        "all_quiet": (['750', '647'], drift, {}, False),            # verbose=False: the reference does not warp
+        "hot_only": (['750', '647', '561'], None, {**off, 'hot_pixel_corr': True}, True),
+        "bleed_only": (['750', '647'], None, {**off, 'bleed_corr': True}, True),
+        "illum_only": (['750', '561'], None, {**off, 'illumination_corr': True}, True),
+        "chrom_only": (['750', '561'], None, {**off, 'chromatic_corr': True}, True),
+        "drift_only": (['647'], [-2.6, 3.3, -0.7], off, True),
+        "drift_big": (['647'], [11.0, -30.5, 60.25], off, True),    # far beyond the padding: mode='nearest' clamps
+    }
+    out = dict(frames=frames, bleed=bleed, meta=np.array(repr(dict(numpy=np.__version__, scipy=scipy.__version__))))
+    for ch in chs:
+        out[f"illum_{ch}"] = illum[ch]
+        if chrom[ch] is not None:
+            out[f"chrom_{ch}"] = chrom[ch]
+    names = []
+    for tag, (sel, dr, flags, verbose) in cases.items():
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            got, = ns.correct_fov_image(fn, sel, drift=dr, verbose=verbose, **{**kw, **flags})
+        mine = correct_oracle.correct_stacks(ims, chs, sel, chs, drift=dr, illumination_profile=illum, bleed_profile=bleed,
+                                             chromatic_profile=chrom, verbose=verbose, **flags)
+        assert all(np.array_equal(a, b) for a, b in zip(got, mine)), tag
+        for ch, a in zip(sel, got):
+            assert a.dtype == np.uint16
+            out[f"{tag}__{ch}"] = a
+        names.append(f"{tag}|{','.join(sel)}|{repr(dr)}|{repr(flags)}|{int(verbose)}")
+        print(tag, "reference == oracle on", sel)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "corr_r2.npz"), **out)
+    print("corr_r2.npz", os.path.getsize(os.path.join(OUT, "corr_r2.npz")))
+
+
 if __name__ == "__main__":
-    if "extra" in sys.argv[1:]:
+    if "corr" in sys.argv[1:]:
+        main_corr()
+    elif "extra" in sys.argv[1:]:
         main_extra()
     else:
         main()

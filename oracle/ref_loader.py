@@ -172,3 +172,34 @@ def _lift_visual(v3, sigma_zxy):
     code = compile(ast.Module(body=nodes, type_ignores=[]), "<reference visual_tools.py (lifted)>", "exec")
     exec(code, env)
     return types.SimpleNamespace(**{k: env[k] for k in wanted if k in env})
+
+
+def load_corrections():
+    """The reference's pre-processing step: io_tools/load.py correct_fov_image (:166-521) with the helpers it calls
+    (get_num_frame :17-45, split_im_by_channels :524-550, load_correction_profile :553-640), corrections.py
+    Remove_Hot_Pixels (:490-510) and the .dax reader (visual_tools.py:906-1089), lifted by AST because neither
+    package imports here.  -> namespace with .correct_fov_image, .Remove_Hot_Pixels, .split_im_by_channels"""
+    if "corr" in _cache:
+        return _cache["corr"]
+    load()
+    from scipy.ndimage import map_coordinates, shift
+    import scipy
+    import time as _time
+    vt_env = dict(np=np, os=os, sys=sys, _correction_folder="")
+    _lift_nodes("visual_tools.py", {"Reader", "DaxReader"}, vt_env)
+    vt = sys.modules[_PKG + ".visual_tools"]
+    vt.DaxReader = vt_env["DaxReader"]
+    cor_env = dict(np=np, os=os)
+    _lift_nodes("corrections.py", {"Remove_Hot_Pixels"}, cor_env)
+    corrections = types.SimpleNamespace(Remove_Hot_Pixels=cor_env["Remove_Hot_Pixels"])
+    load_m = sys.modules[_PKG + ".io_tools.load"]
+    env = load_m.__dict__
+    env.update(np=np, os=os, sys=sys, time=_time, scipy=scipy, map_coordinates=map_coordinates, shift=shift, corrections=corrections,
+               _image_size=[30, 2048, 2048], _allowed_colors=["750", "647", "561", "488", "405"], _corr_channels=["750", "647", "561"],
+               _correction_folder="", _num_buffer_frames=10, _num_empty_frames=0, __package__=_PKG + ".io_tools",
+               __name__=_PKG + ".io_tools.load")
+    _lift_nodes("io_tools/load.py", {"get_num_frame", "correct_fov_image", "split_im_by_channels", "load_correction_profile"}, env)
+    ns = types.SimpleNamespace(correct_fov_image=env["correct_fov_image"], Remove_Hot_Pixels=cor_env["Remove_Hot_Pixels"],
+                               split_im_by_channels=env["split_im_by_channels"], load_correction_profile=env["load_correction_profile"])
+    _cache["corr"] = ns
+    return ns

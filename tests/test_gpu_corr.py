@@ -1,0 +1,125 @@
+"""GPU parity of correct_fov_image (io_tools/load.py mirror over ia3_corr_*) with the unmodified reference's outputs
+(tests/golden/corr_r2.npz) and with the oracle on fresh seeded inputs; size-independent properties at full size."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_corr_host import parse_case, profiles, write_movie
+
+pytestmark = pytest.mark.gpu
+
+# the spline coefficients are floating point: ours and scipy's agree to ~1e-11 of a count, so the rounded uint16
+# output may differ by one count where a value lies that close to a half-integer -- nowhere in practice
+WARP_MAX_DIFF = 1
+WARP_MAX_FRAC = 1e-5
+
+
+def same_warp(a, b, what):
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    assert d.max() <= WARP_MAX_DIFF and (d > 0).mean() <= WARP_MAX_FRAC, f"{what}: max diff {d.max()}, {(d > 0).sum()} voxels differ"
+
+
+@pytest.fixture(scope="module")
+def corr():
+    return np.load(os.path.join(GOLDEN, "corr_r2.npz"))
+
+
+def test_correct_fov_image_matches_reference_fixture(lib, corr, tmp_path):
+    from imageanalysis3_b200.io_tools import load
+    chs, illum, bleed, chrom = profiles(corr)
+    fn = write_movie(tmp_path, corr)
+    kw = dict(single_im_size=[8, 40, 48], all_channels=chs, num_buffer_frames=2, num_empty_frames=0, corr_channels=chs,
+              illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom, drift_channel='561')
+    n_exact = n_total = 0
+    for line in corr["cases"]:
+        tag, sel, drift, flags, verbose = parse_case(str(line))
+        got, = load.correct_fov_image(fn, sel, drift=drift, verbose=verbose, **{**kw, **flags})
+        warped = verbose and (drift is not None or flags.get('chromatic_corr', True))
+        for ch, a in zip(sel, got):
+            want = corr[f"{tag}__{ch}"]
+            assert a.dtype == np.uint16 and a.shape == want.shape
+            if warped:
+                same_warp(a, want, f"{tag} {ch}")
+            else:
+                assert np.array_equal(a, want), (tag, ch)          # integer work: bit-exact
+            n_exact += int(np.array_equal(a, want))
+            n_total += 1
+    assert n_exact == n_total, f"{n_total - n_exact} warped stacks differ from the reference by one count somewhere"
+    # return_drift and resident outputs
+    (st,), d, flag = load.correct_fov_image(fn, ['647'], drift=[0.4, -1.3, 2.2], return_drift=True, return_stacks=True, verbose=False, force_warp=True, **kw)
+    assert flag == 0 and np.array_equal(d, np.array([0.4, -1.3, 2.2], dtype=np.float32))
+    assert np.array_equal(st.fetch(), corr["all_drift__647"])
+
+
+@pytest.mark.parametrize("shape,seed", [((7, 33, 130), 1), ((12, 96, 64), 2)])
+def test_each_step_matches_oracle_on_fresh_inputs(lib, shape, seed):
+    from imageanalysis3_b200.io_tools import load
+    from imageanalysis3_b200.synth import synth
+    from oracle import correct_oracle
+    rng = np.random.default_rng(seed)
+    Z, X, Y = shape
+    chs = ['750', '647', '561']
+    ims = [synth(shape, 12, 40 + seed * 3 + i) for i in range(3)]
+    for i, im in enumerate(ims):
+        for _ in range(6):
+            x, y = rng.integers(0, X), rng.integers(0, Y)
+            im[:, x, y] = 15000
+            if rng.random() < 0.5:
+                im[:, x, min(y + 1, Y - 1)] = 50000          # also detected; its fix reads the replaced (x, y)
+    for dt in (np.float32, np.float64):
+        illum = {ch: (0.7 + 0.6 * rng.random((X, Y))).astype(dt) for ch in chs}
+        bleed = (np.eye(3)[:, :, None, None] * 1.3 + 0.1 * rng.standard_normal((3, 3, X, Y))).astype(dt)   # reaches both clip ends
+        chrom = {ch: (rng.standard_normal((3, 1, X, Y)) * 0.8).astype(np.float32) if ch != '647' else None for ch in chs}
+        for sel, drift in ((['750', '561'], None), (['647', '561'], [0.25, -3.5, 1.75])):
+            want = correct_oracle.correct_stacks(ims, chs, sel, chs, drift=drift, illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom)
+            got = load.correct_image_stacks(ims, chs, sel, chs, drift=drift, illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom)
+            for ch, a, b in zip(sel, got, want):
+                same_warp(a, b, f"{shape} {dt.__name__} {ch}")
+            # without the warp everything is integer work
+            want = correct_oracle.correct_stacks(ims, chs, sel, chs, illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom, warp_image=False)
+            got = load.correct_image_stacks(ims, chs, sel, chs, illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom, warp=False)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    # a per-plane chromatic profile (3, Z, X, Y)
+    chrom_z = {ch: (rng.standard_normal((3, Z, X, Y)) * 0.5).astype(np.float32) if ch != '647' else None for ch in chs}
+    off = dict(hot_pixel_corr=False, bleed_corr=False, illumination_corr=False)
+    want = correct_oracle.correct_stacks(ims, chs, ['750'], chs, chromatic_profile=chrom_z, **off)
+    got = load.correct_image_stacks(ims, chs, ['750'], chs, chromatic_profile=chrom_z, **off)
+    same_warp(got[0], want[0], "per-plane chromatic profile")
+
+
+def test_full_size_properties(lib):
+    """at the reference's stack size (30 x 2048 x 2048): an integer drift is an exact shift with edge replication,
+    identity profiles leave the stack unchanged, and a stack without hot columns is untouched"""
+    rng = np.random.default_rng(3)
+    shape = (30, 2048, 2048)
+    im = rng.integers(100, 3000, size=shape, dtype=np.uint16)
+    st = lib.Stack(im)
+    assert st.remove_hot_pixels() == 0 and np.array_equal(st.fetch(), im)
+    out = lib.Stack.mix([st], illum=np.ones(shape[1:], dtype=np.float32)).fetch()
+    assert np.array_equal(out, im)
+    eye = np.zeros((2,) + shape[1:], dtype=np.float32)
+    eye[0] = 1
+    assert np.array_equal(lib.Stack.mix([st, st], bleed=eye).fetch(), im)
+    dz, dx, dy = 2, -3, 5
+    got = st.warp(drift=[dz, dx, dy]).fetch()
+    zi = np.clip(np.arange(shape[0]) - dz, 0, shape[0] - 1)
+    xi = np.clip(np.arange(shape[1]) - dx, 0, shape[1] - 1)
+    yi = np.clip(np.arange(shape[2]) - dy, 0, shape[2] - 1)
+    assert np.array_equal(got, im[zi][:, xi][:, :, yi])
+    # hot columns at full size: count and replacement against the oracle's rule on the touched columns only
+    im2 = im.copy()
+    cols = [(5, 7), (1000, 1000), (1000, 1001), (2046, 2046), (0, 9)]
+    for x, y in cols:
+        im2[:, x, y] = 65535
+    im2[:, 1000, 1000] = 20000                  # (1000, 1001) is still detected: only the y - 1 neighbour counts, twice
+    st2 = lib.Stack(im2)
+    n = st2.remove_hot_pixels()
+    got = st2.fetch()
+    from oracle import correct_oracle
+    crop = im2[:, 990:1012, 990:1012]
+    want = correct_oracle.remove_hot_pixels(crop.astype(np.float32))
+    assert n == len(cols)
+    assert np.array_equal(got[:, 992:1010, 992:1010], want[:, 2:-2, 2:-2].astype(np.uint16))
+    assert np.array_equal(got[:, 0, 9], im2[:, 0, 9])                        # border column: found, never replaced
