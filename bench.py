@@ -81,14 +81,46 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
+    """SM clock and throttle reasons of this rank's GPU DURING the timed region (the quantities of the profiling
+    recipe's nvidia-smi clocks line), read through NVML inside the process every 50 ms.  Spawning nvidia-smi from
+    every rank at the start of the timed region (fork of a process with GBs of pinned memory + an 8-GPU enumeration
+    per instance) cost ~0.2 s of the timed region on an 8-GPU box; the fallback below is only used without pynvml."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, pci_bus_id=None):
+        self.index, self.rows, self.proc, self.nv, self.h = index, [], None, None, None
+        self.sm, self.mx, self.bits, self._stop = [], [], 0, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id) if pci_bus_id else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self._sample()                                  # first call loads whatever NVML loads lazily
+            self.sm, self.mx, self.bits = [], [], 0
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.bits |= int(get(self.h))
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self._stop.wait(0.05)
 
     def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -101,6 +133,16 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+            nv = self.nv
+            masks = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": [k for k, m in masks.items() if self.bits & m], "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -110,7 +152,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def _dist_setup():
@@ -237,6 +279,16 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
     SHAPE, KW = cfg["shape"], dict(cfg["kw"], verbose=False)
     os.environ.setdefault("IA3_DEVICE", str(local))
+    if world > 1 and os.environ.get("IA3_BENCH_PIN", "1") != "0":
+        # one rank = one GPU = its own share of the box's cores: the ranks' host threads stop migrating over each other
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            share = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, cpus[local * share:(local + 1) * share] or cpus)
+        except (AttributeError, OSError):
+            pass
+    if os.environ.get("IA3_SWITCH_INTERVAL"):
+        sys.setswitchinterval(float(os.environ["IA3_SWITCH_INTERVAL"]))
     from imageanalysis3_b200 import _lib
     _lib.init(local)          # before torch touches the device: the library asks for blocking-sync waits
     import torch
@@ -291,9 +343,14 @@ def run_ours(args):
 
     # ---- value: HBM-resident -------------------------------------------------------------------
     # warm-up fills the library's allocation pools for D stacks in flight (a cudaMalloc inside the timed region stalls every stream)
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        bus = None
+    sampler = ClockSampler(local, bus)                      # NVML is initialised here, outside the timed region
     run_steps(step_resident, 0, max(args.warmup, D))
     barrier()
-    sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
     _lib.timer_start()

@@ -96,6 +96,21 @@ static void release_event(cudaEvent_t e) {
   std::lock_guard<std::mutex> lk(g_mu);
   g_event_pool.push_back(e);
 }
+static std::vector<cudaEvent_t> g_bs_event_pool;  // blocking-sync events: a waiting host thread sleeps
+static int acquire_event_bs(cudaEvent_t* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_bs_event_pool.empty()) { *out = g_bs_event_pool.back(); g_bs_event_pool.pop_back(); return 0; }
+  }
+  IA3_CUDA(cudaEventCreateWithFlags(out, cudaEventBlockingSync | cudaEventDisableTiming));
+  return 0;
+}
+static void release_event_bs(cudaEvent_t e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_bs_event_pool.push_back(e);
+}
+
 static std::multimap<size_t, void*> g_host_free;
 static std::unordered_map<void*, size_t> g_host_sizes;
 static int host_alloc(void** p, size_t bytes) {
@@ -550,7 +565,8 @@ static int stack_common(ia3_stack* s, int dtype, int Z, int X, int Y) {
   s->dtype = dtype; s->Z = Z; s->X = X; s->Y = Y;
   s->nvox = (size_t)Z * X * Y;
   if (acquire_stream(&s->stream)) return -1;
-  for (auto& e : s->ev) if (acquire_event(&e)) return -1;
+  for (int i = 0; i < 5; ++i) if (acquire_event(&s->ev[i])) return -1;        // timing events of the seed stage
+  if (acquire_event_bs(&s->ev[5])) return -1;                                   // end of the upload: waited on without spinning
   if (host_alloc(&s->h_mail, 4096)) return -1;
   return 0;
 }
@@ -593,7 +609,8 @@ int ia3_stack_destroy(ia3_stack* s) {
   dev_free(s->fg); dev_free(s->bg); dev_free(s->scratch);
   dev_free(s->bits); dev_free(s->counts); dev_free(s->offsets);
   dev_free(s->cand_zxy); dev_free(s->cand_h);
-  for (auto& e : s->ev) release_event(e);
+  for (int i = 0; i < 5; ++i) release_event(s->ev[i]);
+  release_event_bs(s->ev[5]);
   release_stream(s->stream);
   host_free(s->h_mail);
   delete s;
@@ -861,21 +878,6 @@ struct ia3_fit {
 };
 constexpr int kTiePrefetch = 16384;               // ties copied with the count (one wait instead of two)
 constexpr size_t kPinBytes = 1024 + 2 * sizeof(int) * kTiePrefetch;
-
-static std::vector<cudaEvent_t> g_bs_event_pool;  // blocking-sync events: a waiting host thread sleeps
-static int acquire_event_bs(cudaEvent_t* out) {
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_bs_event_pool.empty()) { *out = g_bs_event_pool.back(); g_bs_event_pool.pop_back(); return 0; }
-  }
-  IA3_CUDA(cudaEventCreateWithFlags(out, cudaEventBlockingSync | cudaEventDisableTiming));
-  return 0;
-}
-static void release_event_bs(cudaEvent_t e) {
-  if (!e) return;
-  std::lock_guard<std::mutex> lk(g_mu);
-  g_bs_event_pool.push_back(e);
-}
 
 static int build_neighbours(ia3_fit* f) {
   cudaStream_t st = f->st;
