@@ -210,7 +210,7 @@ def _neighbor_boxes(coords, crop_size, shape):
     return out
 
 
-def _image_backgrounds(im, stack, boxes, dtype='uint16', bin_size=10, make_plot=False, max_iter=10):
+def _image_backgrounds(im, stack, boxes, dtype='uint16', bin_size=10, make_plot=False, max_iter=10, _resident=False):
     """find_image_background (io_tools/load.py:642-686) for every box of ``im``.  uint16 stacks that are
     resident on the device are histogrammed there (one CTA per box); anything else (float images, other
     ``dtype`` arguments) keeps the reference's own numpy/scipy expressions."""
@@ -229,6 +229,8 @@ def _image_backgrounds(im, stack, boxes, dtype='uint16', bin_size=10, make_plot=
             out = stack.box_background(safe, first, last, int(bin_size), int(max_iter))
             out[empty] = np.nan
             return out
+    if _resident:
+        raise NotImplementedError("these background_args need the image on the host: pass the numpy image, not a resident stack")
     return np.array([_find_image_background(im[b[0]:b[1], b[2]:b[3], b[4]:b[5]], dtype=dtype, bin_size=bin_size, max_iter=max_iter)
                      for b in boxes])
 
@@ -294,6 +296,16 @@ def _fit_fov_image(im, channel, seeds=None,
     if verbose:
         print(f"-- start fitting spots in channel:{channel}, ", end='')
         t0 = time.time()
+    resident = isinstance(im, _lib.Stack)
+    if resident:
+        # a stack that is already in HBM (e.g. from io_tools.load.correct_fov_image(..., return_stacks=True)): `im`
+        # below only carries shape and dtype, its values are never read
+        if im.dtype != np.uint16 or len(im.shape) != 3:
+            raise NotImplementedError("resident input: uint16 (Z, X, Y) stacks")
+        if 'sel_center' in seeding_kwargs:
+            raise NotImplementedError("sel_center crops the image on the host: pass the numpy image, not a resident stack")
+        _stack = im
+        im = np.broadcast_to(np.zeros((), dtype=np.uint16), _stack.shape)
     stack = _stack
     own_stack = _stack is None
     if stack is None and isinstance(im, np.ndarray) and im.ndim == 3 and im.dtype.kind in "uibf" and im.dtype.itemsize >= (4 if im.dtype.kind == "f" else 1):
@@ -340,12 +352,12 @@ def _fit_fov_image(im, channel, seeds=None,
         inside = (_spots[:, 1:4] > np.zeros(3)).all(1) * (_spots[:, 1:4] < np.array(np.shape(im))).all(1)
         _spots = _spots[np.where(inside)[0]]
     if normalize_background and not normalize_local:
-        back = _image_backgrounds(im, stack, np.array([[0, im.shape[0], 0, im.shape[1], 0, im.shape[2]]]), **background_args)[0]
+        back = _image_backgrounds(im, stack, np.array([[0, im.shape[0], 0, im.shape[1], 0, im.shape[2]]]), _resident=resident, **background_args)[0]
         if verbose:
             print(f"normalize total background:{back:.2f}, ", end='')
         _spots[:, 0] = _spots[:, 0] / back
     elif normalize_local:
-        backs = _image_backgrounds(im, stack, _neighbor_boxes(_spots[:, 1:4], fit_radius * 2, np.shape(im)), **background_args)
+        backs = _image_backgrounds(im, stack, _neighbor_boxes(_spots[:, 1:4], fit_radius * 2, np.shape(im)), _resident=resident, **background_args)
         if verbose:
             print(f"normalize local background for each spot, ", end='')
         _spots[:, 0] = _spots[:, 0] / np.array(backs)

@@ -123,3 +123,24 @@ def test_full_size_properties(lib):
     assert n == len(cols)
     assert np.array_equal(got[:, 992:1010, 992:1010], want[:, 2:-2, 2:-2].astype(np.uint16))
     assert np.array_equal(got[:, 0, 9], im2[:, 0, 9])                        # border column: found, never replaced
+
+
+def test_corrected_stacks_feed_fit_fov_image_without_leaving_the_device(lib, corr, tmp_path):
+    """correct_fov_image(return_stacks=True) -> fit_fov_image(stack, ...) equals the route through numpy arrays"""
+    from imageanalysis3_b200.io_tools import load
+    from imageanalysis3_b200.spot_tools.fitting import fit_fov_image
+    chs, illum, bleed, chrom = profiles(corr)
+    fn = write_movie(tmp_path, corr)
+    kw = dict(single_im_size=[8, 40, 48], all_channels=chs, num_buffer_frames=2, corr_channels=chs, illumination_profile=illum,
+              bleed_profile=bleed, chromatic_profile=chrom, drift_channel='561', drift=[0.4, -1.3, 2.2], verbose=False, force_warp=True)
+    (arrays,) = load.correct_fov_image(fn, ['750', '647'], **kw)
+    (stacks,) = load.correct_fov_image(fn, ['750', '647'], return_stacks=True, **kw)
+    fkw = dict(th_seed=50., max_num_seeds=20, verbose=False)
+    for ch, a, st in zip(['750', '647'], arrays, stacks):
+        want = fit_fov_image(a, ch, **fkw)
+        got = fit_fov_image(st, ch, **fkw)
+        assert len(want) > 0 and np.array_equal(got, want)
+        assert np.array_equal(fit_fov_image(st, ch, normalize_local=True, **fkw), fit_fov_image(a, ch, normalize_local=True, **fkw))
+        assert np.array_equal(st.fetch(), a)                      # the caller's stack keeps its image
+        with pytest.raises(NotImplementedError):
+            fit_fov_image(st, ch, seeding_kwargs=dict(sel_center=[4, 20, 20]), **fkw)
