@@ -840,6 +840,7 @@ static const int g_team_cap_long = std::max(1, env_int("IA3_FIT_TEAM_CAP_LONG", 
 static const int g_memo_on = env_int("IA3_FIT_MEMO", 1) != 0;
 static const int g_spec_on = env_int("IA3_FIT_SPEC", 1) != 0;
 static const int g_chunk = std::max(1, env_int("IA3_FIT_CHUNK", 4));
+static const int g_merge_small = std::max(0, env_int("IA3_FIT_MERGE", 74));   // <= this many tasks in a round: all of them run as team tasks
 // CTAs per launch: the first two rounds of a run hold one task per seed, later ones a few % of that
 static const int g_grid_bulk = std::max(1, env_int("IA3_FIT_GRID", 148 * 16));
 static const int g_grid_bulk_late = std::max(1, env_int("IA3_FIT_GRID_LATE", 148 * 3));
@@ -993,6 +994,7 @@ int ia3_fit_create(ia3_stack* s, const double* centers_zxy, int64_t n, const ia3
   for (int i = 0; i < 3; ++i) d.init_w[i] = cfg->init_w[i];
   d.delta_first = 1.0; d.delta_repeat = 2.5; d.th2 = 0.01; d.max_sweeps = 11;
   d.cap_bulk = g_cap_bulk; d.team_after = g_team_after; d.cap_team_short = g_team_cap; d.cap_team_long = g_team_cap_long;
+  d.merge_small = g_merge_small;
   d.memo_on = g_memo_on;
 
   // inputs go through one pinned arena (no pageable copies); it is next written after a synchronisation

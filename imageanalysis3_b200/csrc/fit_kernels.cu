@@ -447,12 +447,22 @@ __global__ void __launch_bounds__(256) k_sched(FitDev d, int round, int phases, 
       const int al = *(volatile int*)&c->alive[pr];
       const int nb = *(volatile int*)&c->n_bulk[pr];
       c->cap_team_now = (nb == 0) ? d.cap_team_long : d.cap_team_short;
+      // A short work list leaves the GPU to this stack's critical path: the team kernel and the one-warp kernel
+      // of a round run one after the other, and a team evaluates twice as fast.  With few tasks in all, the one-warp
+      // ones join the team list (results do not depend on who runs a task) and the one-warp kernel finds nothing.
+      const int nt = *(volatile int*)&c->n_team[pr];
+      if (nb > 0 && nb + nt <= d.merge_small) {
+        for (int q = 0; q < nb; ++q) team[nt + q] = *(volatile unsigned*)&bulk[q];
+        c->n_team[pr] = nt + nb;
+        c->n_bulk[pr] = 0;
+        __threadfence();
+      }
       if (!al) { c->done = 1; *(volatile int*)d.h_done = 1; __threadfence_system(); }
       else {
         const int slot = c->st_rounds & 511;
         unsigned long long ns;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
-        c->trace_work[slot] = ((unsigned)min(nb, 65535) << 16) | (unsigned)min(*(volatile int*)&c->n_team[pr], 65535);
+        c->trace_work[slot] = ((unsigned)min(*(volatile int*)&c->n_bulk[pr], 65535) << 16) | (unsigned)min(*(volatile int*)&c->n_team[pr], 65535);
         c->trace_ns[slot] = ns;
         c->st_rounds += 1;
       }

@@ -112,6 +112,7 @@ struct FitDev {
   LMLive* live;                       // 2 n parked-run slots: seed (F, R), n + seed (S)
   unsigned* lists; int list_cap;      // bulk[2], team[2], park[2], list_cap entries each
   int cap_bulk, cap_team_short, cap_team_long, team_after;
+  int merge_small;            // a round whose one-warp + team work lists together hold <= this many tasks runs them all as team tasks
   int memo_on;
 };
 

@@ -375,6 +375,8 @@ def test_engine_schedule_does_not_change_a_bit(lib, tmp_path):
     cfgs = {"plain": dict(IA3_FIT_CAP="0", IA3_FIT_MEMO="0", IA3_FIT_SPEC="0"),
             "busy": dict(IA3_FIT_CAP="3", IA3_FIT_TEAM_AFTER="9", IA3_FIT_TEAM_CAP="5", IA3_FIT_TEAM_CAP_LONG="7", IA3_FIT_MEMO="1",
                          IA3_FIT_SPEC="1", IA3_FIT_CHUNK="3"),
+            "merged": dict(IA3_FIT_MERGE="100000", IA3_FIT_CAP="3", IA3_FIT_TEAM_CAP="4"),   # every task of every round runs on a team
+            "merge_small": dict(IA3_FIT_MERGE="64"),
             "default": {}}
     res = {}
     for tag, env in cfgs.items():
@@ -384,7 +386,7 @@ def test_engine_schedule_does_not_change_a_bit(lib, tmp_path):
     assert res["plain"]["v4_nfev"].max() > 50                       # the image does contain long runs
     assert res["plain"]["v4_stats"][:3].sum() == 0
     assert (res["busy"]["v4_stats"] > 0).all(), res["busy"]["v4_stats"]     # every mechanism was exercised
-    for tag in ("busy", "default"):
+    for tag in ("busy", "merged", "merge_small", "default"):
         for key in res["plain"].files:
             if key.endswith("_stats"):
                 continue
