@@ -209,21 +209,17 @@ def run_reference(args):
     times, spots = [], []
     full = None
     with ctx.Pool(procs) as pool:
-        # ONE worker also runs the workload's full-size stack once (C1 / C2 only: minutes beyond that), to pin the
-        # extrapolation from crops: its spots/s on one core is reported next to the crops' per-core rate
-        full_job = None
-        if args.full_check and args.config in ("C1", "C2"):
-            full_job = pool.apply_async(_cpu_worker, ((cfg["seed"], cfg["shape"], cfg["n"], cfg["h"], cfg["kw"]),))
         for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
             res = pool.map(_cpu_worker, [(1000 + it * procs + i, crop, n_crop, cfg["h"], cfg["kw"]) for i in range(procs)], chunksize=1)
-            dt = time.perf_counter() - t0
             if it >= args.warmup:
-                times.append(dt)
+                times.append(max(r[1] for r in res))     # the step lasts as long as its slowest worker's fit_fov_image (image synthesis not counted)
                 spots.append(sum(r[0] for r in res))
-        if full_job is not None:
+        # AFTER the timed steps (a busy worker would halve the pool's rate), ONE worker runs the workload's full-size stack
+        # once (C1 / C2 only: minutes beyond that) to pin the extrapolation from crops: its spots/s on one otherwise idle
+        # core is reported next to the crops' per-core rate with every core busy
+        if args.full_check and args.config in ("C1", "C2"):
             try:
-                n_full, t_full = full_job.get(timeout=240)
+                n_full, t_full = pool.apply_async(_cpu_worker, ((cfg["seed"], cfg["shape"], cfg["n"], cfg["h"], cfg["kw"]),)).get(timeout=300)
                 full = {"spots": n_full, "seconds": t_full, "spots_per_s_one_core": n_full / t_full}
             except Exception as exc:      # noqa: BLE001
                 full = {"unfinished": type(exc).__name__}
@@ -237,7 +233,7 @@ def run_reference(args):
         "stacks_per_s": vox / float(np.prod(cfg["shape"])) / T,
         "config": {"workload": cfg["text"],
                    "sample": f"reference CPU path timed on {crop[0]}x{crop[1]}x{crop[2]} crops of that workload (same spot density), "
-                             f"one crop per worker per step; per-core rate of the crops {value / procs:.1f} spots/s",
+                             f"one crop per worker per step, a step = its slowest worker; per-core rate with all {procs} cores busy {value / procs:.1f} spots/s",
                    "full_stack_check": full},
         "cpu_baseline": {"value": value, "unit": "spots/s", "cores": procs, "kind": "port",
                          "sample": f"{procs} process(es) x one {crop[0]}x{crop[1]}x{crop[2]} crop of the {args.config} stack per step "
