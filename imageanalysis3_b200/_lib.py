@@ -56,7 +56,7 @@ EXPORTS = [
     "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count", "ia3_debug_stats",
     "ia3_timer_start", "ia3_timer_stop",
     "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
-    "ia3_stack_alloc", "ia3_stack_fetch", "ia3_corr_hot_pixels", "ia3_corr_mix", "ia3_corr_warp",
+    "ia3_stack_alloc", "ia3_stack_fetch", "ia3_corr_hot_pixels", "ia3_corr_mix", "ia3_corr_warp", "ia3_device_upload", "ia3_device_free",
     "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_seed_gather_volume", "ia3_box_background",
     "ia3_seed_v2", "ia3_fft_gaussian", "ia3_seed_logratio", "ia3_stack_histogram",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
@@ -99,6 +99,8 @@ def load():
     lib.ia3_stack_trim.argtypes = [vp, i32]
     lib.ia3_stack_alloc.argtypes = [i32, i32, i32, i32, P(vp)]
     lib.ia3_stack_fetch.argtypes = [vp, vp]
+    lib.ia3_device_upload.argtypes = [vp, C.c_size_t, P(vp)]
+    lib.ia3_device_free.argtypes = [vp]
     lib.ia3_corr_hot_pixels.argtypes = [vp, dbl, dbl, P(i64)]
     lib.ia3_corr_mix.argtypes = [P(vp), i32, vp, vp, i32, vp]
     lib.ia3_corr_warp.argtypes = [vp, vp, vp, i32, i32, vp]
@@ -165,6 +167,37 @@ def launch_count():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceArray:
+    """A constant array (a correction profile) uploaded once and kept in device memory; rows of it are addressed
+    by byte offset (``ptr(i)``)."""
+
+    def __init__(self, a):
+        a = np.ascontiguousarray(a)
+        self.shape, self.dtype, self.nbytes = a.shape, a.dtype, a.nbytes
+        self._d = C.c_void_p()
+        _check(load().ia3_device_upload(_ptr(a), a.nbytes, C.byref(self._d)))
+        _count("h2d", a.nbytes)
+        self._fin = weakref.finalize(self, load().ia3_device_free, self._d)
+
+    def ptr(self, row=None):
+        if row is None:
+            return C.c_void_p(self._d.value)
+        return C.c_void_p(self._d.value + int(row) * (self.nbytes // self.shape[0]))
+
+    def close(self):
+        self._fin()
+
+
+def _profile_arg(a, row=None):
+    """(pointer, dtype, shape of the addressed part, host bytes copied by the call) of a numpy array or DeviceArray"""
+    if a is None:
+        return None, None, None, 0
+    if isinstance(a, DeviceArray):
+        return a.ptr(row), a.dtype, (a.shape if row is None else a.shape[1:]), 0
+    a = np.ascontiguousarray(a if row is None else a[row])
+    return _ptr(a), a.dtype, a.shape, a.nbytes
 
 
 class Stack:
@@ -280,39 +313,47 @@ class Stack:
         return int(n.value)
 
     @staticmethod
-    def mix(ins, bleed=None, illum=None, out=None):
-        """out = illumination(bleed-through(ins)); bleed (len(ins), X, Y), illum (X, Y), both of one floating dtype"""
+    def mix(ins, bleed=None, illum=None, out=None, bleed_row=None):
+        """out = illumination(bleed-through(ins)); bleed (len(ins), X, Y) -- or row ``bleed_row`` of an (n, n, X, Y) array --,
+        illum (X, Y); numpy arrays or DeviceArrays, all of one floating dtype"""
         ins = list(ins)
         out = Stack(shape=ins[0].shape, dtype=np.uint16) if out is None else out
-        dts = {np.asarray(a).dtype for a in (bleed, illum) if a is not None}
+        keep = []
+        pb, dtb, shb, nb = _profile_arg(bleed, bleed_row)
+        pi, dti, shi, ni = _profile_arg(illum)
+        dts = {np.dtype(d) for d in (dtb, dti) if d is not None}
         if len(dts) > 1 or (dts and next(iter(dts)) not in (np.dtype(np.float32), np.dtype(np.float64))):
             raise TypeError("bleed-through and illumination profiles of one call are both float32 or both float64")
         f64 = bool(dts) and next(iter(dts)) == np.dtype(np.float64)
-        bleed = None if bleed is None else np.ascontiguousarray(bleed)
-        illum = None if illum is None else np.ascontiguousarray(illum)
-        if bleed is not None and bleed.shape != (len(ins),) + tuple(ins[0].shape[1:]):
-            raise ValueError(f"bleed-through rows of shape {bleed.shape} do not match {len(ins)} stacks of {ins[0].shape}")
-        if illum is not None and illum.shape != tuple(ins[0].shape[1:]):
-            raise ValueError(f"illumination profile of shape {illum.shape} does not match stacks of {ins[0].shape}")
+        if shb is not None and tuple(shb) != (len(ins),) + tuple(ins[0].shape[1:]):
+            raise ValueError(f"bleed-through rows of shape {tuple(shb)} do not match {len(ins)} stacks of {ins[0].shape}")
+        if shi is not None and tuple(shi) != tuple(ins[0].shape[1:]):
+            raise ValueError(f"illumination profile of shape {tuple(shi)} does not match stacks of {ins[0].shape}")
         arr = (C.c_void_p * len(ins))(*[s._h for s in ins])
-        _check(load().ia3_corr_mix(arr, len(ins), _ptr(bleed), _ptr(illum), int(f64), out._h))
-        _count("h2d", (0 if bleed is None else bleed.nbytes) + (0 if illum is None else illum.nbytes))
+        _check(load().ia3_corr_mix(arr, len(ins), pb, pi, int(f64), out._h))
+        _count("h2d", nb + ni)
+        del keep
         return out
 
     def warp(self, drift=None, chroma=None, out=None):
-        """map_coordinates(im, grid + chroma - drift, order 3, mode 'nearest') -> a new uint16 stack"""
+        """map_coordinates(im, grid + chroma - drift, order 3, mode 'nearest') -> a new uint16 stack; chroma: numpy
+        array or DeviceArray of shape (3, 1 or Z, X, Y)"""
         out = Stack(shape=self.shape, dtype=np.uint16) if out is None else out
         d = None if drift is None else np.ascontiguousarray(drift, dtype=np.float32)
-        cz = 0
+        cz, f64, pc, nc = 0, 0, None, 0
         if chroma is not None:
-            chroma = np.ascontiguousarray(chroma)
+            if not isinstance(chroma, DeviceArray):
+                chroma = np.ascontiguousarray(chroma)
+                if chroma.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+                    chroma = chroma.astype(np.float64)                       # what numpy promotes int64 + profile to
+            if len(chroma.shape) != 4 or chroma.shape[0] != 3 or tuple(chroma.shape[2:]) != tuple(self.shape[1:]) or chroma.shape[1] not in (1, self.shape[0]):
+                raise ValueError(f"chromatic profile of shape {tuple(chroma.shape)} does not match a stack of {self.shape}")
             if chroma.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
-                chroma = chroma.astype(np.float64)                           # what numpy promotes int64 + profile to
-            if chroma.ndim != 4 or chroma.shape[0] != 3 or tuple(chroma.shape[2:]) != tuple(self.shape[1:]):
-                raise ValueError(f"chromatic profile of shape {chroma.shape} does not match a stack of {self.shape}")
-            cz = chroma.shape[1]
-        _check(load().ia3_corr_warp(self._h, _ptr(d), _ptr(chroma), int(chroma is not None and chroma.dtype == np.float64), int(cz), out._h))
-        _count("h2d", 0 if chroma is None else chroma.nbytes)
+                raise TypeError("chromatic profile: float32 or float64")
+            cz, f64 = chroma.shape[1], int(chroma.dtype == np.float64)
+            pc, _, _, nc = _profile_arg(chroma)
+        _check(load().ia3_corr_warp(self._h, _ptr(d), pc, f64, int(cz), out._h))
+        _count("h2d", nc)
         return out
 
     def histogram(self):

@@ -521,14 +521,16 @@ static int download_image(const void* d_src, void* dst, size_t bytes, cudaStream
   return 0;
 }
 
-static int upload_image(ia3_stack* s, const void* im, size_t bytes) {
+// host -> device copy of `bytes` on the shared upload stream; `ev` (blocking sync) is recorded behind the last DMA and
+// waited for.  Pinned sources go to the copy engine directly, pageable ones through the staging workers.
+static int upload_bytes(void* d_dst, const void* src, size_t bytes, cudaEvent_t ev, cudaStream_t then_stream) {
   cudaStream_t us;
   if (upload_stream(&us)) return -1;
   cudaError_t e = cudaSuccess;
-  if (is_pinned(im)) {
+  if (is_pinned(src)) {
     std::lock_guard<std::mutex> lk(g_upload_mu);
-    e = cudaMemcpyAsync(s->d_im, im, bytes, cudaMemcpyHostToDevice, us);
-    if (e == cudaSuccess) e = cudaEventRecord(s->ev[5], us);
+    e = cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, us);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, us);
   } else {
     IA3_STAT("  upload: pinned staging");
     if (start_stage_workers()) return -1;
@@ -539,7 +541,7 @@ static int upload_image(ia3_stack* s, const void* im, size_t bytes) {
       std::lock_guard<std::mutex> lk(g_sq_mu);
       for (int j = 0; j < njobs; ++j) {
         const size_t off = (size_t)j * kStageJob;
-        g_sq.push_back(StageJob{static_cast<const char*>(im) + off, static_cast<char*>(s->d_im) + off, std::min(kStageJob, bytes - off), &pending, &err});
+        g_sq.push_back(StageJob{static_cast<const char*>(src) + off, static_cast<char*>(d_dst) + off, std::min(kStageJob, bytes - off), &pending, &err});
       }
     }
     g_sq_cv.notify_all();
@@ -547,14 +549,22 @@ static int upload_image(ia3_stack* s, const void* im, size_t bytes) {
       std::unique_lock<std::mutex> lk(g_sq_mu);
       g_sq_done.wait(lk, [&] { return pending.load() == 0; });
     }
-    if (err.load()) { set_error("image upload failed in the staging workers"); return -1; }
+    if (err.load()) { set_error("upload failed in the staging workers"); return -1; }
     std::lock_guard<std::mutex> lk(g_upload_mu);
-    e = cudaEventRecord(s->ev[5], us);                          // behind every chunk's DMA
+    e = cudaEventRecord(ev, us);                                // behind every chunk's DMA
   }
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(s->stream, s->ev[5], 0);
-  if (e == cudaSuccess) e = cudaEventSynchronize(s->ev[5]);
-  if (e != cudaSuccess) { set_error(std::string("image upload failed: ") + cudaGetErrorString(e)); return -1; }
+  if (e == cudaSuccess && then_stream) e = cudaStreamWaitEvent(then_stream, ev, 0);
+  if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+  if (e != cudaSuccess) { set_error(std::string("upload failed: ") + cudaGetErrorString(e)); return -1; }
   return 0;
+}
+
+static int upload_image(ia3_stack* s, const void* im, size_t bytes) { return upload_bytes(s->d_im, im, bytes, s->ev[5], s->stream); }
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice;
 }
 
 extern "C" {
@@ -1719,6 +1729,28 @@ int ia3_stack_alloc(int dtype, int Z, int X, int Y, ia3_stack** out) {
   return 0;
 }
 
+int ia3_device_upload(const void* host, size_t bytes, void** dev) {
+  if (ensure_device()) return -1;
+  if (!host || !dev || bytes == 0) { set_error("null argument"); return -1; }
+  void* d = nullptr;
+  if (dev_alloc(&d, bytes)) return -1;
+  cudaEvent_t ev = nullptr;
+  if (acquire_event_bs(&ev)) { dev_free(d); return -1; }
+  const int rc = upload_bytes(d, host, bytes, ev, nullptr);
+  release_event_bs(ev);
+  if (rc) { dev_free(d); return -1; }
+  *dev = d;
+  return 0;
+}
+
+int ia3_device_free(void* dev) {
+  if (!dev) return 0;
+  if (g_device >= 0) cudaSetDevice(g_device);
+  cudaDeviceSynchronize();                      // nothing in flight may still read it
+  dev_free(dev);
+  return 0;
+}
+
 int ia3_stack_fetch(ia3_stack* s, void* out) {
   if (ensure_device()) return -1;
   if (!s || !out) { set_error("null argument"); return -1; }
@@ -1777,20 +1809,24 @@ int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void*
   Scoped sc;
   const size_t es = profile_f64 ? 8 : 4, nxy = (size_t)out->X * out->Y;
   const size_t b_bleed = bleed ? (size_t)n_in * nxy * es : 0, b_illum = illum ? nxy * es : 0;
-  char* d_prof = nullptr; const uint16_t** d_ptrs = nullptr; void* h = nullptr;
-  if (sc.dalloc(&d_prof, b_bleed + b_illum + 256) || sc.dalloc(&d_ptrs, 256) || sc.halloc(&h, 256)) return -1;
-  // the profiles are per-dataset constants: a caller that corrects many fields of view keeps them pinned, the copy
-  // below then runs at link speed; pageable arrays go through the driver's staging
-  if (bleed) IA3_CUDA(cudaMemcpyAsync(d_prof, bleed, b_bleed, cudaMemcpyHostToDevice, st));
-  if (illum) IA3_CUDA(cudaMemcpyAsync(d_prof + b_bleed, illum, b_illum, cudaMemcpyHostToDevice, st));
+  char* d_bleed = nullptr; char* d_illum = nullptr; const uint16_t** d_ptrs = nullptr; void* h = nullptr;
+  if (sc.dalloc(&d_ptrs, 256) || sc.halloc(&h, 256)) return -1;
+  // the profiles are per-dataset constants: a caller that corrects many fields of view uploads them once
+  // (ia3_device_upload) and passes the device pointers; host arrays are copied here, every call
+  if (bleed) {
+    if (is_device_ptr(bleed)) d_bleed = const_cast<char*>(static_cast<const char*>(bleed));
+    else { if (sc.dalloc(&d_bleed, b_bleed)) return -1; IA3_CUDA(cudaMemcpyAsync(d_bleed, bleed, b_bleed, cudaMemcpyHostToDevice, st)); }
+  }
+  if (illum) {
+    if (is_device_ptr(illum)) d_illum = const_cast<char*>(static_cast<const char*>(illum));
+    else { if (sc.dalloc(&d_illum, b_illum)) return -1; IA3_CUDA(cudaMemcpyAsync(d_illum, illum, b_illum, cudaMemcpyHostToDevice, st)); }
+  }
   const uint16_t** hp = static_cast<const uint16_t**>(h);
   for (int j = 0; j < n_in; ++j) hp[j] = (const uint16_t*)ins[j]->d_im;
   if (small_copy(d_ptrs, hp, (size_t)n_in * sizeof(void*), st)) return -1;
   int rc;
-  if (profile_f64) rc = launch_mix<double>(d_ptrs, n_in, bleed ? (const double*)d_prof : nullptr, illum ? (const double*)(d_prof + b_bleed) : nullptr,
-                                           (uint16_t*)out->d_im, (long long)nxy, (long long)out->nvox, st);
-  else rc = launch_mix<float>(d_ptrs, n_in, bleed ? (const float*)d_prof : nullptr, illum ? (const float*)(d_prof + b_bleed) : nullptr,
-                              (uint16_t*)out->d_im, (long long)nxy, (long long)out->nvox, st);
+  if (profile_f64) rc = launch_mix<double>(d_ptrs, n_in, (const double*)d_bleed, (const double*)d_illum, (uint16_t*)out->d_im, (long long)nxy, (long long)out->nvox, st);
+  else rc = launch_mix<float>(d_ptrs, n_in, (const float*)d_bleed, (const float*)d_illum, (uint16_t*)out->d_im, (long long)nxy, (long long)out->nvox, st);
   if (rc) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   return 0;
@@ -1806,16 +1842,19 @@ int ia3_corr_warp(ia3_stack* in, const float* drift, const void* chroma, int chr
   cudaStream_t st = out->stream;
   Scoped sc;
   const long long np_ = warp_padded_voxels(in->Z, in->X, in->Y);
-  double* bufA = nullptr; double* bufB = nullptr; double* d_h = nullptr; char* d_ch = nullptr; void* h = nullptr;
+  double* buf = nullptr; char* d_ch = nullptr;
   const size_t b_ch = chroma ? (size_t)3 * chroma_z * in->X * in->Y * (chroma_f64 ? 8 : 4) : 0;
-  if (sc.dalloc(&bufA, (size_t)np_ * 8) || sc.dalloc(&bufB, (size_t)np_ * 8) || sc.dalloc(&d_h, 1024) || sc.halloc(&h, 1024)) return -1;
-  if (chroma && sc.dalloc(&d_ch, b_ch)) return -1;
-  const int nt = spline_taps(static_cast<double*>(h), 128);
-  if (nt < 0) { set_error("spline tap table"); return -1; }
-  if (small_copy(d_h, h, (size_t)nt * 8, st)) return -1;
-  if (chroma) IA3_CUDA(cudaMemcpyAsync(d_ch, chroma, b_ch, cudaMemcpyHostToDevice, st));
+  if (sc.dalloc(&buf, (size_t)np_ * 8)) return -1;
+  if (chroma) {
+    // a profile that already lives in device memory (ia3_device_upload) is used where it is
+    if (is_device_ptr(chroma)) d_ch = const_cast<char*>(static_cast<const char*>(chroma));
+    else {
+      if (sc.dalloc(&d_ch, b_ch)) return -1;
+      IA3_CUDA(cudaMemcpyAsync(d_ch, chroma, b_ch, cudaMemcpyHostToDevice, st));
+    }
+  }
   const float d0 = drift ? drift[0] : 0.0f, d1 = drift ? drift[1] : 0.0f, d2 = drift ? drift[2] : 0.0f;
-  if (launch_warp((const uint16_t*)in->d_im, in->Z, in->X, in->Y, d_h, bufA, bufB, d_ch, chroma_f64, chroma_z, d0, d1, d2, (uint16_t*)out->d_im, st)) return -1;
+  if (launch_warp((const uint16_t*)in->d_im, in->Z, in->X, in->Y, buf, d_ch, chroma_f64, chroma_z, d0, d1, d2, (uint16_t*)out->d_im, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

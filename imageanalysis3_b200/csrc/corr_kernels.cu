@@ -10,10 +10,11 @@
 //   k_mix            bleed-through mixing sum_j im_j * profile[i, j] in float32, clip, truncate (io_tools/load.py:
 //                    347-367) fused with the illumination division (:369-381)
 //   k_spline_iir /   scipy.ndimage.spline_filter(np.pad(im, 12, 'edge'), 3, mode='nearest'): the cubic B-spline prefilter
-//   k_spline_fir_y   with pole z = sqrt 3 - 2 on the half-sample-symmetric extension of each padded line.  Along z and x
-//                    the two-pass recursion scipy runs, one thread per line; along y (contiguous) the equivalent
-//                    symmetric filter -6z/(1-z^2) z^|k| from shared memory (|z|^28 < 1e-16: 57 taps).  Both agree
-//                    with scipy's coefficients to ~1e-15 relative (checked in numpy before they were written)
+//   k_spline_iir_y   with pole z = sqrt 3 - 2 on the half-sample-symmetric extension of each padded line -- the two-pass
+//                    recursion scipy runs, one thread per line, in place on one float64 padded volume; the causal start
+//                    is the 28-term sum (|z|^28 < 1e-16).  Along z and x the lines lie side by side in y (every step is a
+//                    coalesced row); along y the rows go through transposing shared-memory tiles.  Agrees with scipy's
+//                    coefficients to ~1e-15 relative (checked in numpy before it was written)
 //   k_warp           map_coordinates(im, coords, order=3, mode='nearest') (:424-459) with coords = grid + chromatic
 //                    profile - drift formed exactly as numpy promotes them, 64-tap cubic interpolation on the
 //                    prefiltered volume, uint16 output rounded half up and saturated like ndimage's integer store
@@ -145,40 +146,81 @@ __global__ void __launch_bounds__(128) k_spline_iir(const Tsrc* src, double* dst
   for (int k = 0; k < KTAP; ++k) { s += zk * in(refl(k, L)); zk *= zp; }
   double c = 6.0 * (in(0) + zp * s);
   dst[base] = c;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = 1; i < L; ++i) {
     c = 6.0 * in(i) + zp * c;
     dst[base + (long long)i * stride] = c;
   }
   c = zp / (zp - 1.0) * c;
   dst[base + (long long)(L - 1) * stride] = c;
-#pragma unroll 4
+#pragma unroll 8
   for (int i = L - 2; i >= 0; --i) {
     c = zp * (c - dst[base + (long long)i * stride]);
     dst[base + (long long)i * stride] = c;
   }
 }
 
-// Axis 2 (the contiguous one) as the equivalent symmetric filter -6z/(1-z^2) z^|k| out of shared memory: a block stages
-// a row segment plus 28 values either side (half-sample-symmetric beyond the row's ends)
-constexpr int SEG = 1024;
-__global__ void __launch_bounds__(256) k_spline_fir_y(const double* __restrict__ src, double* __restrict__ dst, int PY, const double* __restrict__ h) {
-  __shared__ double sm[SEG + 2 * KTAP];
-  __shared__ double hs[2 * KTAP + 1];
-  const long long row = blockIdx.x;
-  const int y0 = blockIdx.y * SEG;
-  const double* r = src + row * PY;
-  for (int j = threadIdx.x; j < SEG + 2 * KTAP; j += 256) sm[j] = r[refl(y0 - KTAP + j, PY)];
-  if (threadIdx.x < 2 * KTAP + 1) hs[threadIdx.x] = h[threadIdx.x];
-  __syncthreads();
-#pragma unroll
-  for (int m = 0; m < SEG / 256; ++m) {
-    const int j = threadIdx.x + 256 * m;
-    if (y0 + j >= PY) break;
-    double acc = 0.0;
-#pragma unroll 19
-    for (int k = 0; k <= 2 * KTAP; ++k) acc += hs[k] * sm[j + k];
-    dst[row * PY + y0 + j] = acc;
+// Axis 2 (the contiguous one): the same recursion, one thread per row, fed through shared memory so that global memory
+// is still read and written in coalesced rows: a block owns 128 rows and walks them in chunks of 32 columns (forward for
+// the causal pass, backward for the anticausal one); a chunk is loaded row-wise by the warps, each thread runs its row's 32
+// recursion steps in the tile (odd pitch: no bank conflicts), and the chunk is written back row-wise.  In place.
+constexpr int YR = 128, YC = 32;
+__global__ void __launch_bounds__(YR) k_spline_iir_y(double* buf, long long n_rows, int L) {
+  __shared__ double tile[YR][YC + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long r0 = (long long)blockIdx.x * YR;
+  const long long mine = r0 + tid;
+  const bool ok = mine < n_rows;
+  const double zp = -0.26794919243112270647;
+  double c = 0.0;
+  if (ok) {
+    const double* r = buf + mine * L;
+    double sum = 0.0, zk = 1.0;
+    for (int k = 0; k < KTAP; ++k) { sum += zk * r[refl(k, L)]; zk *= zp; }
+    c = 6.0 * sum;                                  // c+[0] = 6 x[0] + z (6 sum)
+  }
+  const int nch = (L + YC - 1) / YC;
+  auto load = [&](int y0) {
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long row = r0 + warp * 32 + rr;
+      if (row < n_rows && y0 + lane < L) tile[warp * 32 + rr][lane] = buf[row * L + y0 + lane];
+    }
+  };
+  auto store = [&](int y0) {
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long row = r0 + warp * 32 + rr;
+      if (row < n_rows && y0 + lane < L) buf[row * L + y0 + lane] = tile[warp * 32 + rr][lane];
+    }
+  };
+  for (int ch = 0; ch < nch; ++ch) {
+    const int y0 = ch * YC, nk = min(YC, L - y0);
+    load(y0);
+    __syncthreads();
+    if (ok) {
+#pragma unroll 8
+      for (int k = 0; k < nk; ++k) { c = 6.0 * tile[tid][k] + zp * c; tile[tid][k] = c; }
+    }
+    __syncthreads();
+    store(y0);
+    __syncthreads();
+  }
+  c = zp / (zp - 1.0) * c;                           // c[L-1] from c+[L-1]
+  for (int ch = nch - 1; ch >= 0; --ch) {
+    const int y0 = ch * YC, nk = min(YC, L - y0);
+    load(y0);
+    __syncthreads();
+    if (ok) {
+#pragma unroll 8
+      for (int k = nk - 1; k >= 0; --k) {
+        if (y0 + k != L - 1) c = zp * (c - tile[tid][k]);
+        tile[tid][k] = c;
+      }
+    }
+    __syncthreads();
+    store(y0);
+    __syncthreads();
   }
 }
 
@@ -190,46 +232,56 @@ __device__ __forceinline__ void cubic_w(double t, double* w) {       // ndimage'
   w[3] = 1.0 - w[0] - w[1] - w[2];
 }
 
+// A thread owns one (x, y) column and walks it along z: three of the four coefficient planes an output needs were touched
+// by the previous output of the same block, so they come from L1 / L2 instead of HBM (the padded volume is 1.85 GB; four
+// planes of it exceed the L2).  A block covers 8 x 32 columns.
 template <typename Tc>
 __global__ void __launch_bounds__(256) k_warp(const double* __restrict__ coef, int Z, int X, int Y, const Tc* __restrict__ chroma /* 3 x CZ x X x Y or null */,
                                               int CZ, float d0, float d1, float d2, uint16_t* __restrict__ out) {
   const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
-  const long long n = (long long)Z * X * Y;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const int y = (int)(t % Y), x = (int)((t / Y) % X), z = (int)(t / ((long long)X * Y));
-  // coords = int64 grid + float32 profile (-> float64) - float32 drift (-> float64)     io_tools/load.py:441-449
-  double c[3] = {(double)z, (double)x, (double)y};
-  if (chroma) {
-    const long long plane = (long long)CZ * X * Y, off = ((long long)(CZ == 1 ? 0 : z) * X + x) * Y + y;
-    c[0] = c[0] + (double)chroma[off]; c[1] = c[1] + (double)chroma[plane + off]; c[2] = c[2] + (double)chroma[2 * plane + off];
-  }
-  c[0] = c[0] - (double)d0; c[1] = c[1] - (double)d1; c[2] = c[2] - (double)d2;
+  const int y = blockIdx.x * 32 + (threadIdx.x & 31), x = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= X || y >= Y) return;
   const int dims[3] = {PZ, PX, PY};
-  int fl[3];
-  double w[3][4];
-  for (int a = 0; a < 3; ++a) {
-    double cc = c[a] + (double)NPAD;
-    cc = fmin(fmax(cc, 0.0), (double)(dims[a] - 1));          // mode='nearest' on the padded extent
-    const double f = floor(cc);
-    fl[a] = (int)f;
-    cubic_w(cc - f, w[a]);
-  }
-  double acc = 0.0;
-  for (int i = 0; i < 4; ++i) {
-    const int iz = min(max(fl[0] - 1 + i, 0), PZ - 1);
-    for (int j = 0; j < 4; ++j) {
-      const int ix = min(max(fl[1] - 1 + j, 0), PX - 1);
-      const double* row = coef + ((long long)iz * PX + ix) * PY;
-      for (int k = 0; k < 4; ++k) {
-        const int iy = min(max(fl[2] - 1 + k, 0), PY - 1);
-        acc += row[iy] * w[0][i] * w[1][j] * w[2][k];
-      }
+  const double drift[3] = {(double)d0, (double)d1, (double)d2};
+  const long long plane = (long long)CZ * X * Y;
+  for (int z = 0; z < Z; ++z) {
+    // coords = int64 grid + profile (-> float64) - float32 drift (-> float64)     io_tools/load.py:441-449
+    double c[3] = {(double)z, (double)x, (double)y};
+    if (chroma) {
+      const long long off = ((long long)(CZ == 1 ? 0 : z) * X + x) * Y + y;
+      c[0] = c[0] + (double)chroma[off]; c[1] = c[1] + (double)chroma[plane + off]; c[2] = c[2] + (double)chroma[2 * plane + off];
     }
+    int idx[3][4];
+    double w[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double cc = (c[a] - drift[a]) + (double)NPAD;
+      cc = fmin(fmax(cc, 0.0), (double)(dims[a] - 1));          // mode='nearest' on the padded extent
+      const double f = floor(cc);
+      const int fl = (int)f;
+      cubic_w(cc - f, w[a]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) idx[a][i] = min(max(fl - 1 + i, 0), dims[a] - 1);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double pi = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double* row = coef + ((long long)idx[0][i] * PX + idx[1][j]) * PY;
+        double sj = row[idx[2][0]] * w[2][0];
+        sj = fma(row[idx[2][1]], w[2][1], sj);
+        sj = fma(row[idx[2][2]], w[2][2], sj);
+        sj = fma(row[idx[2][3]], w[2][3], sj);
+        pi = fma(sj, w[1][j], pi);
+      }
+      acc = fma(pi, w[0][i], acc);
+    }
+    double r = acc > 0.0 ? acc + 0.5 : 0.0;                     // ndimage's store to an unsigned integer type
+    r = r > 65535.0 ? 65535.0 : r;
+    out[((long long)z * X + x) * Y + y] = (uint16_t)(unsigned)r;
   }
-  double r = acc > 0.0 ? acc + 0.5 : 0.0;                     // ndimage's store to an unsigned integer type
-  r = r > 65535.0 ? 65535.0 : r;
-  out[t] = (uint16_t)(unsigned)r;
 }
 
 int launch_hot_count(const uint16_t* im, int Z, int X, int Y, float hot_th, int* cnt, cudaStream_t st) {
@@ -259,26 +311,20 @@ int launch_mix(const uint16_t* const* d_ins, int n_in, const Tp* bleed, const Tp
 }
 template int launch_mix<float>(const uint16_t* const*, int, const float*, const float*, uint16_t*, long long, long long, cudaStream_t);
 template int launch_mix<double>(const uint16_t* const*, int, const double*, const double*, uint16_t*, long long, long long, cudaStream_t);
-int spline_taps(double* h, int cap) {
-  if (cap < 2 * KTAP + 1) return -1;
-  const double z = std::sqrt(3.0) - 2.0, c0 = -6.0 * z / (1.0 - z * z);
-  for (int k = -KTAP; k <= KTAP; ++k) h[k + KTAP] = c0 * std::pow(z, std::abs(k));
-  return 2 * KTAP + 1;
-}
 long long warp_padded_voxels(int Z, int X, int Y) { return (long long)(Z + 2 * NPAD) * (X + 2 * NPAD) * (Y + 2 * NPAD); }
-int launch_warp(const uint16_t* im, int Z, int X, int Y, const double* d_h, double* bufA, double* bufB, const void* chroma, int chroma_f64, int CZ,
+int launch_warp(const uint16_t* im, int Z, int X, int Y, double* buf, const void* chroma, int chroma_f64, int CZ,
                 float d0, float d1, float d2, uint16_t* out, cudaStream_t st) {
   const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
-  k_spline_iir<uint16_t><<<(unsigned)(((long long)PX * PY + 127) / 128), 128, 0, st>>>(im, bufA, Z, X, Y, 0);
+  k_spline_iir<uint16_t><<<(unsigned)(((long long)PX * PY + 127) / 128), 128, 0, st>>>(im, buf, Z, X, Y, 0);
   IA3_LAUNCH_CHECK();
-  k_spline_iir<double><<<(unsigned)(((long long)PZ * PY + 127) / 128), 128, 0, st>>>(bufA, bufA, Z, X, Y, 1);
+  k_spline_iir<double><<<(unsigned)(((long long)PZ * PY + 127) / 128), 128, 0, st>>>(buf, buf, Z, X, Y, 1);
   IA3_LAUNCH_CHECK();
-  k_spline_fir_y<<<dim3((unsigned)(PZ * PX), (unsigned)((PY + SEG - 1) / SEG)), 256, 0, st>>>(bufA, bufB, PY, d_h);
+  const long long n_rows = (long long)PZ * PX;
+  k_spline_iir_y<<<(unsigned)((n_rows + YR - 1) / YR), YR, 0, st>>>(buf, n_rows, PY);
   IA3_LAUNCH_CHECK();
-  bufA = bufB;
-  const long long n = (long long)Z * X * Y;
-  if (chroma_f64) k_warp<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bufA, Z, X, Y, (const double*)chroma, CZ, d0, d1, d2, out);
-  else k_warp<float><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bufA, Z, X, Y, (const float*)chroma, CZ, d0, d1, d2, out);
+  const dim3 grid((unsigned)((Y + 31) / 32), (unsigned)((X + 7) / 8));
+  if (chroma_f64) k_warp<double><<<grid, 256, 0, st>>>(buf, Z, X, Y, (const double*)chroma, CZ, d0, d1, d2, out);
+  else k_warp<float><<<grid, 256, 0, st>>>(buf, Z, X, Y, (const float*)chroma, CZ, d0, d1, d2, out);
   IA3_LAUNCH_CHECK();
   return 0;
 }

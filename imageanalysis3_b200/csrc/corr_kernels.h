@@ -10,8 +10,7 @@ int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, fl
 // Tp = float or double: the dtype the profile arrays were saved in decides numpy's arithmetic type
 template <typename Tp>
 int launch_mix(const uint16_t* const* d_ins, int n_in, const Tp* bleed, const Tp* illum, uint16_t* out, long long XY, long long n, cudaStream_t st);
-int spline_taps(double* h, int cap);
 long long warp_padded_voxels(int Z, int X, int Y);
-int launch_warp(const uint16_t* im, int Z, int X, int Y, const double* d_h, double* bufA, double* bufB, const void* chroma, int chroma_f64, int CZ,
+int launch_warp(const uint16_t* im, int Z, int X, int Y, double* buf, const void* chroma, int chroma_f64, int CZ,
                 float d0, float d1, float d2, uint16_t* out, cudaStream_t st);
 }  // namespace ia3

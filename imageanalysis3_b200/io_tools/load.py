@@ -128,10 +128,44 @@ def load_correction_profile(corr_type, corr_channels=_corr_channels, correction_
 
 
 def _float_profile(a, what):
+    if isinstance(a, _lib.DeviceArray):
+        return a
     a = np.asarray(a)
     if a.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
         raise NotImplementedError(f"{what} of dtype {a.dtype}: the device path takes float32 or float64 profiles")
     return a
+
+
+# Correction profiles are per-dataset constants (a chromatic profile is 3 x Z x X x Y float64 = 3 GB at the reference's
+# stack size): a profile array that comes back on a later call -- the same numpy object, as when a caller loads the
+# profiles once and corrects many fields of view -- is uploaded once.  Entries die with their arrays.
+_RESIDENT = {}
+_RESIDENT_MAX_BYTES = int(os.environ.get("IA3_PROFILE_CACHE_BYTES", str(24 << 30)))
+
+
+def resident_profile(a):
+    """the DeviceArray holding numpy array ``a`` (uploaded on first use, reused while ``a`` is alive and unchanged in
+    identity); arrays that are not C-contiguous, or a cache that is full, fall back to per-call copies"""
+    if a is None or isinstance(a, _lib.DeviceArray):
+        return a
+    if not isinstance(a, np.ndarray) or not a.flags.c_contiguous or a.base is not None and not isinstance(a.base, np.ndarray):
+        return a
+    key = id(a)
+    mark = float(a.ravel()[::max(1, a.size // 4096)].sum(dtype=np.float64))      # an array edited in place is uploaded again
+    hit = _RESIDENT.get(key)
+    if hit is not None and hit[0]() is a and hit[2] == mark:
+        return hit[1]
+    _RESIDENT.pop(key, None)
+    if sum(v[1].nbytes for v in _RESIDENT.values()) + a.nbytes > _RESIDENT_MAX_BYTES:
+        return a
+    import weakref
+    try:
+        ref = weakref.ref(a, lambda _r, k=key: _RESIDENT.pop(k, None))
+    except TypeError:
+        return a
+    dev = _lib.DeviceArray(a)
+    _RESIDENT[key] = (ref, dev, mark)
+    return dev
 
 
 def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=None,
@@ -158,17 +192,18 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
     overlap = [ch for ch in corr_channels if ch in sel_channels]
     illum = {}
     if illumination_corr:
-        illum = {ch: _float_profile(illumination_profile[ch], "illumination profile") for ch in load_channels}
+        illum = {ch: resident_profile(_float_profile(illumination_profile[ch], "illumination profile")) for ch in load_channels}
     done = set()
     if overlap and bleed_corr:
         bleed_profile = _float_profile(bleed_profile, "bleed-through profile")
-        if bleed_profile.ndim != 4:
+        if len(bleed_profile.shape) != 4:
             raise NotImplementedError("per-plane (n, n, Z, X, Y) bleed-through profiles are not supported on the device")
+        bleed_dev = resident_profile(bleed_profile)
         bld = [stacks[load_channels.index(ch)] for ch in corr_channels]
         mixed = []
         for i, ch in enumerate(corr_channels):
             fuse = ch in illum and illum[ch].dtype == bleed_profile.dtype
-            mixed.append(_lib.Stack.mix(bld, bleed=bleed_profile[i], illum=illum[ch] if fuse else None))
+            mixed.append(_lib.Stack.mix(bld, bleed=bleed_dev, bleed_row=i, illum=illum[ch] if fuse else None))
             if fuse:
                 done.add(ch)
         for s, ch in zip(mixed, corr_channels):
@@ -183,7 +218,7 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
         for ch in sel_channels:
             with_chroma = chromatic_corr and ch in chroma_channels
             if with_chroma or drift.any():
-                pf = chromatic_profile[ch] if with_chroma else None
+                pf = resident_profile(chromatic_profile[ch]) if with_chroma else None
                 k = load_channels.index(ch)
                 stacks[k] = stacks[k].warp(drift=drift if drift.any() else None, chroma=pf)
     out = [stacks[load_channels.index(ch)] for ch in sel_channels]

@@ -66,6 +66,10 @@ int ia3_stack_histogram(ia3_stack* s, uint64_t* counts);
  * (DaxReader, io_tools/load.py:290-300) and the profile loading stay on the host side of this boundary. */
 /* An owned, uninitialised stack: the destination of ia3_corr_mix / ia3_corr_warp. */
 int ia3_stack_alloc(int dtype, int Z, int X, int Y, ia3_stack** out);
+/* Per-dataset constants (correction profiles) kept in device memory across calls: ia3_corr_mix / ia3_corr_warp take either
+ * host pointers (copied on every call) or pointers returned here.  Pageable sources are staged like stacks. */
+int ia3_device_upload(const void* host, size_t bytes, void** dev);
+int ia3_device_free(void* dev);
 /* Copy a resident stack's image to the host (Z*X*Y elements of its dtype). */
 int ia3_stack_fetch(ia3_stack* s, void* out);
 /* corrections.py:490-510 Remove_Hot_Pixels(im.astype(float32), dtype=uint16, hot_pix_th, hot_th), in place: columns
@@ -75,11 +79,13 @@ int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t*
 /* out = illumination(bleed-through(ins)) (io_tools/load.py:347-381): with ``bleed`` (host, n_in x X x Y: row i of the
  * (n, n, X, Y) profile) out = clip(sum_j ins[j] * bleed[j]) truncated to uint16, else out = ins[0]; with ``illum``
  * (host, X x Y) that result is divided by it and truncated again.  profile_f64: the profiles are float64 (numpy then
- * computes in float64) instead of float32.  Bleed-through mixing cannot run in place. */
+ * computes in float64) instead of float32.  bleed / illum: host or ia3_device_upload pointers.  Bleed-through mixing cannot
+ * run in place. */
 int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void* illum, int profile_f64, ia3_stack* out);
 /* out = scipy.ndimage.map_coordinates(in, grid + chroma - drift, order 3, mode 'nearest') rounded to uint16
- * (io_tools/load.py:424-459).  drift: 3 float32 (z, x, y) or null; chroma: host float32 (or float64 with chroma_f64) array
- * (3, chroma_z, X, Y) with chroma_z = 1 or Z, or null.  Floating-point path: the spline coefficients agree with scipy's recursion to ~1e-11
+ * (io_tools/load.py:424-459).  drift: 3 float32 (z, x, y) or null; chroma: float32 (or float64 with chroma_f64) array
+ * (3, chroma_z, X, Y) with chroma_z = 1 or Z (what correction_tools/chromatic.py:282-289 saves), host or ia3_device_upload
+ * pointer, or null.  Floating-point path: the spline coefficients agree with scipy's recursion to ~1e-11
  * of a count, so the rounded uint16 output is equal except where a value falls within that of a half-integer. */
 int ia3_corr_warp(ia3_stack* in, const float* drift, const void* chroma, int chroma_f64, int chroma_z, ia3_stack* out);
 

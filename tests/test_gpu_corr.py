@@ -87,6 +87,17 @@ def test_each_step_matches_oracle_on_fresh_inputs(lib, shape, seed):
     want = correct_oracle.correct_stacks(ims, chs, ['750'], chs, chromatic_profile=chrom_z, **off)
     got = load.correct_image_stacks(ims, chs, ['750'], chs, chromatic_profile=chrom_z, **off)
     same_warp(got[0], want[0], "per-plane chromatic profile")
+    # what correction_tools/chromatic.py saves: float64, one plane per z; uploaded once, reused by the second call
+    chrom_64 = {ch: None if v is None else v.astype(np.float64) for ch, v in chrom_z.items()}
+    want = correct_oracle.correct_stacks(ims, chs, ['561'], chs, drift=[-0.5, 0.25, 3.0], chromatic_profile=chrom_64, **off)
+    for _ in range(2):
+        got = load.correct_image_stacks(ims, chs, ['561'], chs, drift=[-0.5, 0.25, 3.0], chromatic_profile=chrom_64, **off)
+        same_warp(got[0], want[0], "float64 per-plane chromatic profile")
+    assert any(ref() is chrom_64['561'] for ref, _, _ in load._RESIDENT.values())
+    chrom_64['561'][1] += 0.75                                       # edited in place: must not be served from the device copy
+    want = correct_oracle.correct_stacks(ims, chs, ['561'], chs, chromatic_profile=chrom_64, **off)
+    got = load.correct_image_stacks(ims, chs, ['561'], chs, chromatic_profile=chrom_64, **off)
+    same_warp(got[0], want[0], "edited chromatic profile")
 
 
 def test_full_size_properties(lib):

@@ -19,7 +19,8 @@ def main():
         im[:, 100, 200] = 60000
     illum = {ch: (0.7 + 0.6 * rng.random(shape[1:])).astype(np.float32) for ch in chs}
     bleed = (np.eye(3)[:, :, None, None] + 0.05 * rng.random((3, 3) + shape[1:])).astype(np.float32)
-    chrom = {ch: (rng.standard_normal((3, 1) + shape[1:]) * 0.5).astype(np.float32) if ch != '647' else None for ch in chs}
+    # what correction_tools/chromatic.py saves: float64, one plane per z (3 GB per channel at this size)
+    chrom = {ch: (rng.standard_normal((3,) + shape) * 0.5) if ch != '647' else None for ch in chs}
     drift = [0.4, -1.3, 2.2]
     _lib.init()
     for rep in range(3):
@@ -29,9 +30,9 @@ def main():
         for s in stacks:
             s.remove_hot_pixels()
         t2 = time.perf_counter()
-        mixed = [_lib.Stack.mix(stacks, bleed=bleed[i], illum=illum[ch]) for i, ch in enumerate(chs)]
+        mixed = [_lib.Stack.mix(stacks, bleed=load.resident_profile(bleed), bleed_row=i, illum=load.resident_profile(illum[ch])) for i, ch in enumerate(chs)]
         t3 = time.perf_counter()
-        warped = [s.warp(drift=drift, chroma=chrom[ch]) for s, ch in zip(mixed, chs)]
+        warped = [s.warp(drift=drift, chroma=load.resident_profile(chrom[ch])) for s, ch in zip(mixed, chs)]
         t4 = time.perf_counter()
         outs = [s.fetch() for s in warped]
         t5 = time.perf_counter()
