@@ -365,14 +365,14 @@ def test_engine_schedule_does_not_change_a_bit(lib, tmp_path):
     """The fit engine may suspend a run after any number of evaluations, continue it with one warp or
     with a team of warps, skip a re-fit whose inputs are those of the seed's previous visit (memo) and
     start the first repeat visit of isolated seeds speculatively: none of that may change a single bit.
-    Reference configuration: no suspension, no memo, no speculation (every visit runs lmder from
-    scratch on one warp).  Aggressive configuration: suspend every 3 evaluations, team continuation after
+    Reference configuration: no suspension, no memo, no speculation, no merging of short rounds (every visit
+    runs lmder from scratch on one warp).  Aggressive configuration: suspend every 3 evaluations, team continuation after
     9, memo and speculation on."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cfgs = {"plain": dict(IA3_FIT_CAP="0", IA3_FIT_MEMO="0", IA3_FIT_SPEC="0"),
+    cfgs = {"plain": dict(IA3_FIT_CAP="0", IA3_FIT_MEMO="0", IA3_FIT_SPEC="0", IA3_FIT_MERGE="0"),
             "busy": dict(IA3_FIT_CAP="3", IA3_FIT_TEAM_AFTER="9", IA3_FIT_TEAM_CAP="5", IA3_FIT_TEAM_CAP_LONG="7", IA3_FIT_MEMO="1",
                          IA3_FIT_SPEC="1", IA3_FIT_CHUNK="3"),
             "merged": dict(IA3_FIT_MERGE="100000", IA3_FIT_CAP="3", IA3_FIT_TEAM_CAP="4"),   # every task of every round runs on a team
