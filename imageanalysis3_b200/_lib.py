@@ -339,7 +339,8 @@ class Stack:
         """map_coordinates(im, grid + chroma - drift, order 3, mode 'nearest') -> a new uint16 stack; chroma: numpy
         array or DeviceArray of shape (3, 1 or Z, X, Y)"""
         out = Stack(shape=self.shape, dtype=np.uint16) if out is None else out
-        d = None if drift is None else np.ascontiguousarray(drift, dtype=np.float32)
+        # float32 drifts (what correct_fov_image makes of a given drift) widen exactly; align_image's float64 result passes through
+        d = None if drift is None else np.ascontiguousarray(np.asarray(drift), dtype=np.float64)
         cz, f64, pc, nc = 0, 0, None, 0
         if chroma is not None:
             if not isinstance(chroma, DeviceArray):

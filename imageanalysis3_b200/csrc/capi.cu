@@ -1832,7 +1832,7 @@ int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void*
   return 0;
 }
 
-int ia3_corr_warp(ia3_stack* in, const float* drift, const void* chroma, int chroma_f64, int chroma_z, ia3_stack* out) {
+int ia3_corr_warp(ia3_stack* in, const double* drift, const void* chroma, int chroma_f64, int chroma_z, ia3_stack* out) {
   IA3_STAT("ia3_corr_warp");
   if (ensure_device()) return -1;
   if (corr_check(in, "ia3_corr_warp") || corr_check(out, "ia3_corr_warp")) return -1;
@@ -1853,7 +1853,7 @@ int ia3_corr_warp(ia3_stack* in, const float* drift, const void* chroma, int chr
       IA3_CUDA(cudaMemcpyAsync(d_ch, chroma, b_ch, cudaMemcpyHostToDevice, st));
     }
   }
-  const float d0 = drift ? drift[0] : 0.0f, d1 = drift ? drift[1] : 0.0f, d2 = drift ? drift[2] : 0.0f;
+  const double d0 = drift ? drift[0] : 0.0, d1 = drift ? drift[1] : 0.0, d2 = drift ? drift[2] : 0.0;
   if (launch_warp((const uint16_t*)in->d_im, in->Z, in->X, in->Y, buf, d_ch, chroma_f64, chroma_z, d0, d1, d2, (uint16_t*)out->d_im, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   return 0;

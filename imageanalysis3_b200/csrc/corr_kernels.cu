@@ -237,15 +237,15 @@ __device__ __forceinline__ void cubic_w(double t, double* w) {       // ndimage'
 // planes of it exceed the L2).  A block covers 8 x 32 columns.
 template <typename Tc>
 __global__ void __launch_bounds__(256) k_warp(const double* __restrict__ coef, int Z, int X, int Y, const Tc* __restrict__ chroma /* 3 x CZ x X x Y or null */,
-                                              int CZ, float d0, float d1, float d2, uint16_t* __restrict__ out) {
+                                              int CZ, double d0, double d1, double d2, uint16_t* __restrict__ out) {
   const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
   const int y = blockIdx.x * 32 + (threadIdx.x & 31), x = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (x >= X || y >= Y) return;
   const int dims[3] = {PZ, PX, PY};
-  const double drift[3] = {(double)d0, (double)d1, (double)d2};
+  const double drift[3] = {d0, d1, d2};
   const long long plane = (long long)CZ * X * Y;
   for (int z = 0; z < Z; ++z) {
-    // coords = int64 grid + profile (-> float64) - float32 drift (-> float64)     io_tools/load.py:441-449
+    // coords = int64 grid + profile (-> float64) - drift (float32 or float64, -> float64)     io_tools/load.py:441-449
     double c[3] = {(double)z, (double)x, (double)y};
     if (chroma) {
       const long long off = ((long long)(CZ == 1 ? 0 : z) * X + x) * Y + y;
@@ -313,7 +313,7 @@ template int launch_mix<float>(const uint16_t* const*, int, const float*, const 
 template int launch_mix<double>(const uint16_t* const*, int, const double*, const double*, uint16_t*, long long, long long, cudaStream_t);
 long long warp_padded_voxels(int Z, int X, int Y) { return (long long)(Z + 2 * NPAD) * (X + 2 * NPAD) * (Y + 2 * NPAD); }
 int launch_warp(const uint16_t* im, int Z, int X, int Y, double* buf, const void* chroma, int chroma_f64, int CZ,
-                float d0, float d1, float d2, uint16_t* out, cudaStream_t st) {
+                double d0, double d1, double d2, uint16_t* out, cudaStream_t st) {
   const int PZ = Z + 2 * NPAD, PX = X + 2 * NPAD, PY = Y + 2 * NPAD;
   k_spline_iir<uint16_t><<<(unsigned)(((long long)PX * PY + 127) / 128), 128, 0, st>>>(im, buf, Z, X, Y, 0);
   IA3_LAUNCH_CHECK();

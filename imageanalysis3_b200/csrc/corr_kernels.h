@@ -12,5 +12,5 @@ template <typename Tp>
 int launch_mix(const uint16_t* const* d_ins, int n_in, const Tp* bleed, const Tp* illum, uint16_t* out, long long XY, long long n, cudaStream_t st);
 long long warp_padded_voxels(int Z, int X, int Y);
 int launch_warp(const uint16_t* im, int Z, int X, int Y, double* buf, const void* chroma, int chroma_f64, int CZ,
-                float d0, float d1, float d2, uint16_t* out, cudaStream_t st);
+                double d0, double d1, double d2, uint16_t* out, cudaStream_t st);
 }  // namespace ia3

@@ -7,8 +7,8 @@ correction runs on the resident uint16 stacks through libia3b200 (ia3_corr_*); t
 to spot_tools.fitting.fit_fov_image without leaving the device (``return_stacks=True``).
 
 Same signature, argument meaning and error behaviour as the reference.  Branches of the reference that leave this
-path raise NotImplementedError instead of computing something else: calculate_drift (correction_tools/alignment.py
-align_image -- phase correlation via skimage, not built), warp_image=False (returns spot-coordinate functions from
+path raise NotImplementedError instead of computing something else: calculate_drift with use_autocorr=True (correction_tools/
+alignment.py align_image's phase correlation via skimage; its bead-fitting mode, use_autocorr=False, is built), warp_image=False (returns spot-coordinate functions from
 correction_tools/chromatic.py), z_shift_corr, gaussian_highpass, normalization and a non-uint16 output_dtype.
 
 One reference behaviour is kept on purpose because results must be the same: the warp code in the reference sits
@@ -173,11 +173,12 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
                          illumination_corr=True, illumination_profile=None,
                          bleed_corr=True, bleed_profile=None,
                          chromatic_ref_channel='647', chromatic_corr=True, chromatic_profile=None,
-                         warp=True, return_stacks=False):
+                         warp=True, return_stacks=False, drift_from=None):
     """The compute core of correct_fov_image on in-memory channel stacks (reference io_tools/load.py:318-459).
 
     ims: one (Z, X, Y) uint16 array (or resident _lib.Stack) per channel of load_channels -> the corrected stacks of
-    sel_channels, as numpy arrays or, with return_stacks, as resident stacks."""
+    sel_channels, as numpy arrays or, with return_stacks, as resident stacks.  ``drift_from``: called with {channel: stack}
+    after the illumination step (where the reference estimates the drift, :383-419); its return value replaces ``drift``."""
     stacks = []
     for im in ims:
         if isinstance(im, _lib.Stack):
@@ -212,7 +213,10 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
         if ch not in done:
             s = stacks[load_channels.index(ch)]
             _lib.Stack.mix([s], illum=pf, out=s)
-    drift = np.zeros(3, dtype=np.float32) if drift is None else np.array(drift, dtype=np.float32)
+    if drift_from is not None:
+        drift = drift_from({ch: stacks[load_channels.index(ch)] for ch in load_channels})
+    # (the reference warps with whatever align_image returned -- float64 -- and with float32 for a given drift)
+    drift = np.zeros(3, dtype=np.float32) if drift is None else (np.asarray(drift) if drift_from is not None else np.array(drift, dtype=np.float32))
     chroma_channels = [ch for ch in corr_channels if ch in sel_channels and ch != chromatic_ref_channel]
     if warp:
         for ch in sel_channels:
@@ -263,8 +267,11 @@ def correct_fov_image(dax_filename, sel_channels,
     if str(drift_channel) not in all_channels:
         raise ValueError(f"Wrong input of drift_channel:{drift_channel}, should be among {all_channels}")
     # branches of the reference that leave the device path (see the module docstring)
-    if calculate_drift:
-        raise NotImplementedError("calculate_drift=True needs correction_tools.alignment.align_image, which this framework does not build; pass drift=")
+    if calculate_drift and use_autocorr:
+        raise NotImplementedError("calculate_drift=True with use_autocorr=True needs skimage's phase_cross_correlation (correction_tools."
+                                  "alignment.align_image), not built; use_autocorr=False (bead fitting on the device) or pass drift=")
+    if calculate_drift and str(drift_channel) not in load_channels:
+        load_channels.append(str(drift_channel))
     if not warp_image:
         raise NotImplementedError("warp_image=False returns spot-coordinate functions (correction_tools.chromatic), not built")
     if z_shift_corr or gaussian_highpass or normalization:
@@ -311,8 +318,24 @@ def correct_fov_image(dax_filename, sel_channels,
     del raw
     if verbose:
         print(f"-- loaded image from file:{dax_filename} in {time.time() - t0:.3f}s")
+    found = {"drift": drift.copy(), "flag": 0}
+    drift_from = None
+    if calculate_drift:
+        def drift_from(stacks):
+            # io_tools/load.py:383-419: the bead channel after hot-pixel / bleed-through / illumination against the reference file
+            from ..correction_tools.alignment import align_image
+            args = dict(drift_args)
+            args.update(all_channels=all_channels, ref_all_channels=all_channels, drift_channel=drift_channel)
+            found["drift"], found["flag"] = align_image(
+                stacks[str(drift_channel)].fetch(), ref_filename, use_autocorr=use_autocorr,
+                correction_args={'single_im_size': single_im_size, 'num_buffer_frames': num_buffer_frames,
+                                 'num_empty_frames': num_empty_frames, 'correction_folder': correction_folder},
+                verbose=verbose, **args)
+            if verbose:
+                print(f"--- finish drift: {np.around(found['drift'], 2)}")
+            return found["drift"]
     t0 = time.time()
-    out = correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=drift,
+    out = correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=drift, drift_from=drift_from,
                                hot_pixel_corr=hot_pixel_corr, hot_pixel_th=hot_pixel_th,
                                illumination_corr=illumination_corr, illumination_profile=illumination_profile,
                                bleed_corr=bleed_corr, bleed_profile=bleed_profile,
@@ -323,5 +346,5 @@ def correct_fov_image(dax_filename, sel_channels,
         print(f"-- finish correction in {time.time() - t_total:.3f}s")
     ret = [out]
     if return_drift:
-        ret.extend([drift.copy(), 0])
+        ret.extend([found["drift"], found["flag"]])
     return tuple(ret)

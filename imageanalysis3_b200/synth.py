@@ -47,6 +47,20 @@ def synth(shape, n, seed, bg=300.0, h_range=(600.0, 4000.0), sigma=SIGMA_ZXY, ma
     return im
 
 
+def bead_pair(shape, n, drift, seed, bg=300.0, h_range=(1500.0, 4000.0), sigma=SIGMA_ZXY, margin=6, read_noise=3.0):
+    """(reference image, drifted image, centres): the same ``n`` beads, in the second image displaced by ``drift`` (z, x, y),
+    independent noise -- the input of correction_tools.alignment.align_image"""
+    centers, heights, rng = planted_spots(shape, n, seed, h_range, margin)
+    out = []
+    for shift in (np.zeros(3), np.asarray(drift, dtype=float)):
+        signal = np.full(tuple(shape), bg, dtype=np.float32)
+        _add_spots(signal, centers + shift, heights, sigma)
+        noisy = rng.poisson(signal).astype(np.float32)
+        noisy += rng.normal(0.0, read_noise, size=signal.shape).astype(np.float32)
+        out.append(np.clip(np.rint(noisy), 0, 65535).astype(np.uint16))
+    return out[0], out[1], centers
+
+
 def synth_torch(shape, n, seed, device, bg=300.0, h_range=(600.0, 4000.0), sigma=SIGMA_ZXY,
                 margin=8, read_noise=3.0):
     """Bench-scale generator on a torch device (returns a uint16 torch tensor on ``device``).

@@ -83,11 +83,11 @@ int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t*
  * run in place. */
 int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void* illum, int profile_f64, ia3_stack* out);
 /* out = scipy.ndimage.map_coordinates(in, grid + chroma - drift, order 3, mode 'nearest') rounded to uint16
- * (io_tools/load.py:424-459).  drift: 3 float32 (z, x, y) or null; chroma: float32 (or float64 with chroma_f64) array
+ * (io_tools/load.py:424-459).  drift: 3 doubles (z, x, y) -- the reference's float32 drift widened, or align_image's float64 result -- or null; chroma: float32 (or float64 with chroma_f64) array
  * (3, chroma_z, X, Y) with chroma_z = 1 or Z (what correction_tools/chromatic.py:282-289 saves), host or ia3_device_upload
  * pointer, or null.  Floating-point path: the spline coefficients agree with scipy's recursion to ~1e-11
  * of a count, so the rounded uint16 output is equal except where a value falls within that of a half-integer. */
-int ia3_corr_warp(ia3_stack* in, const float* drift, const void* chroma, int chroma_f64, int chroma_z, ia3_stack* out);
+int ia3_corr_warp(ia3_stack* in, const double* drift, const void* chroma, int chroma_f64, int chroma_z, ia3_stack* out);
 
 /* ---- seed stage ------------------------------------------------------------------------ */
 typedef struct {

@@ -304,8 +304,97 @@ def main_corr():
     print("corr_r2.npz", os.path.getsize(os.path.join(OUT, "corr_r2.npz")))
 
 
+ALIGN_CASE = dict(shape=(16, 256, 256), n=300, drift=(0.35, 2.4, -1.7), seed=41)
+
+
+def write_dax(path, channels_ims, nbuf):
+    """interleaved movie of the given channel stacks (in all_channels order) with nbuf buffer frames at both ends"""
+    ncol, (Z, X, Y) = len(channels_ims), channels_ims[0].shape
+    frames = np.zeros((2 * nbuf + Z * ncol, X, Y), np.uint16)
+    for c, im in enumerate(channels_ims):
+        s0 = nbuf + (c - nbuf) % ncol
+        frames[s0:s0 + Z * ncol:ncol] = im
+    frames.tofile(path)
+    with open(path.replace('.dax', '.inf'), 'w') as fh:
+        fh.write(f"frame dimensions = {Y} x {X}\nnumber of frames = {frames.shape[0]}\n little endian\n")
+
+
+def align_files(folder, ref, src, other_ref, other_src, nbuf=2):
+    """two .dax movies (channels '647' = a signal image, '488' = beads) and an illumination profile folder"""
+    X, Y = ref.shape[1:]
+    write_dax(os.path.join(folder, 'ref.dax'), [other_ref, ref], nbuf)
+    write_dax(os.path.join(folder, 'src.dax'), [other_src, src], nbuf)
+    xx, yy = np.meshgrid(np.arange(X), np.arange(Y), indexing='ij')
+    for ch, amp in (('647', 0.15), ('488', 0.1)):
+        pf = (1.0 + amp * np.cos((xx - X / 2) / X) * np.cos((yy - Y / 2) / Y)).astype(np.float32)
+        np.save(os.path.join(folder, f'illumination_correction_{ch}_{X}x{Y}.npy'), pf)
+    return os.path.join(folder, 'src.dax'), os.path.join(folder, 'ref.dax')
+
+
+def main_align():
+    """tests/golden/align_r2.npz: correction_tools/alignment.py align_image in its bead-fitting mode (use_autocorr=False; the
+    phase-correlation mode needs scikit-image, absent here), the UNMODIFIED reference functions lifted by
+    ref_loader.load_alignment, on a synthetic bead pair (imageanalysis3_b200.synth.bead_pair: images are regenerated in the
+    tests from the stored parameters, a checksum guards the generator), and correct_fov_image(calculate_drift=True) on two
+    .dax movies built from it."""
+    import contextlib, io, tempfile
+    from imageanalysis3_b200.synth import bead_pair
+    warnings.simplefilter("ignore")
+    ns = ref_loader.load_alignment()
+    cor = ref_loader.load_corrections()
+    c = ALIGN_CASE
+    ref, src, centers = bead_pair(c["shape"], c["n"], c["drift"], c["seed"])
+    out = dict(shape=np.array(c["shape"]), n=c["n"], drift_planted=np.array(c["drift"]), seed=c["seed"],
+               checksum=np.array([int(ref.astype(np.uint64).sum()), int(src.astype(np.uint64).sum()), int((ref.astype(np.int64) * 3 + src).std() * 1e6)]),
+               meta=np.array(repr(dict(numpy=np.__version__, scipy=scipy.__version__))))
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        out["crops"] = ns.generate_drift_crops(list(c["shape"]))
+        d0, f0 = ns.align_image(src, ref, use_autocorr=False, correction_args=dict(single_im_size=list(c["shape"])), verbose=False)
+        d1, f1 = ns.align_image(src, ref, use_autocorr=False, drift_diff_th=1e-4, correction_args=dict(single_im_size=list(c["shape"])), verbose=False)
+        d2, f2 = ns.align_image(src, ref, use_autocorr=False, crop_list=out["crops"][[5, 2, 7]], min_good_drifts=2, match_distance_th=1.5,
+                                fitting_args=dict(max_num_seeds=12), correction_args=dict(single_im_size=list(c["shape"])), verbose=False)
+    out.update(drift_default=d0, flag_default=f0, drift_suboptimal=d1, flag_suboptimal=f1, drift_custom=d2, flag_custom=f2)
+    print("planted", c["drift"], "reference finds", -d0, f0, "| sub-optimal path", -d1, f1, "| custom", -d2, f2)
+    assert f0 == 0 and f1 == 1 and np.abs(d0 + np.array(c["drift"])).max() < 0.05
+    # one crop's pairing, step by step (inputs of the host functions)
+    s = tuple(slice(*r) for r in out["crops"][0])
+    with contextlib.redirect_stdout(sink):
+        sp_src = ns_fit_centers(src[s])
+        sp_ref = ns_fit_centers(ref[s])
+        rough = ns.fft3d_from2d(src[s], ref[s], gb=0, max_disp=np.max(src[s].shape) / 2)
+        dft, p_t, p_r = ns.find_paired_centers(sp_src, sp_ref, rough, cutoff=2., return_paired_cts=True)
+        dft2, k_t, k_r = ns.check_paired_centers(p_t, p_r, outlier_sigma=1.5, return_paired_cts=True)
+    out.update(crop0_src_cts=sp_src, crop0_ref_cts=sp_ref, crop0_rough=rough, crop0_drift_paired=dft, crop0_paired_tar=p_t, crop0_paired_ref=p_r,
+               crop0_drift_checked=dft2, crop0_kept_tar=k_t, crop0_kept_ref=k_r)
+    # through files: correct_fov_image(calculate_drift=True) of a two-colour movie
+    other_ref = synth(c["shape"], 40, 77)
+    other_src = synth(c["shape"], 40, 78)
+    folder = tempfile.mkdtemp()
+    src_dax, ref_dax = align_files(folder, ref, src, other_ref, other_src)
+    with contextlib.redirect_stdout(sink):
+        ims, drift, flag = cor.correct_fov_image(src_dax, ['647'], single_im_size=list(c["shape"]), all_channels=['647', '488'], num_buffer_frames=2,
+                                                 num_empty_frames=0, calculate_drift=True, drift_channel='488', ref_filename=ref_dax, use_autocorr=False,
+                                                 corr_channels=['647'], correction_folder=folder, bleed_corr=False, chromatic_corr=False,
+                                                 return_drift=True, verbose=True)
+    out.update(file_drift=drift, file_flag=flag, file_im_647_slab=ims[0][4:12, 64:192, 64:192], file_im_647_sum=int(ims[0].astype(np.uint64).sum()),
+               file_other_seeds=np.array([77, 78]))
+    print("through files: drift", drift, flag, "corrected image", ims[0].shape, ims[0].dtype)
+    np.savez_compressed(os.path.join(OUT, "align_r2.npz"), **out)
+    print("align_r2.npz", os.path.getsize(os.path.join(OUT, "align_r2.npz")))
+
+
+def ns_fit_centers(im):
+    ns = ref_loader.load()
+    al = ref_loader.load_alignment()
+    spots = ns.fitting.fit_fov_image(im, '488', verbose=False, **al.defaults[1])
+    return ns.fitting.select_sparse_centers(spots[:, 1:4], 2.)
+
+
 if __name__ == "__main__":
-    if "corr" in sys.argv[1:]:
+    if "align" in sys.argv[1:]:
+        main_align()
+    elif "corr" in sys.argv[1:]:
         main_corr()
     elif "extra" in sys.argv[1:]:
         main_extra()

@@ -203,3 +203,64 @@ def load_corrections():
                                split_im_by_channels=env["split_im_by_channels"], load_correction_profile=env["load_correction_profile"])
     _cache["corr"] = ns
     return ns
+
+
+def _lift_assigns(relpath, names, env):
+    """module-level ``name = literal`` statements of the reference file, evaluated in env"""
+    with open(os.path.join(REF_ROOT, relpath), "r", encoding="utf-8", errors="replace") as fh:
+        tree = ast.parse(fh.read())
+    nodes = [n for n in tree.body if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name)
+             and n.targets[0].id in names]
+    exec(compile(ast.Module(body=nodes, type_ignores=[]), f"<reference {relpath} (lifted assignments)>", "exec"), env)
+    return env
+
+
+def load_alignment():
+    """The reference's drift estimation: correction_tools/alignment.py align_image (:527-696), align_beads (:139-217),
+    generate_drift_crops (:87-136) with alignment_tools.py fft3d_from2d / fftalign_2d (:286-353) and spot_tools/matching.py
+    find_paired_centers / check_paired_centers (:148-287), lifted by AST.  skimage is not installed here, so
+    ``phase_cross_correlation`` is a stub that raises: only the bead-fitting mode (use_autocorr=False) can run.
+    -> namespace with .align_image, .align_beads, .generate_drift_crops, .fft3d_from2d, .find_paired_centers, .check_paired_centers"""
+    if "align" in _cache:
+        return _cache["align"]
+    load()
+    load_corrections()
+    import time as _time
+    root = sys.modules[_PKG]
+    if "skimage" not in sys.modules:
+        try:
+            import skimage.registration  # noqa: F401
+        except Exception:
+            sk, reg = types.ModuleType("skimage"), types.ModuleType("skimage.registration")
+
+            def phase_cross_correlation(*a, **k):
+                raise RuntimeError("skimage is not installed: the phase-correlation mode of align_image cannot run here")
+            reg.phase_cross_correlation = phase_cross_correlation
+            sk.registration = reg
+            sys.modules.update({"skimage": sk, "skimage.registration": reg})
+    at = types.ModuleType(_PKG + ".alignment_tools")
+    at.__dict__.update(np=np, os=os, sys=sys)
+    _lift_nodes("alignment_tools.py", {"fft3d_from2d", "fftalign_2d", "blurnorm2d", "translation_align_pts"}, at.__dict__)
+    sys.modules[_PKG + ".alignment_tools"] = at
+    root.alignment_tools = at
+    mt = types.ModuleType(_PKG + ".spot_tools.matching")
+    mt.__dict__.update(np=np, os=os, sys=sys)
+    _lift_nodes("spot_tools/matching.py", {"find_paired_centers", "check_paired_centers"}, mt.__dict__)
+    sys.modules[_PKG + ".spot_tools.matching"] = mt
+    sys.modules[_PKG + ".spot_tools"].matching = mt
+    ct = types.ModuleType(_PKG + ".correction_tools")
+    ct.__path__ = []
+    al = types.ModuleType(_PKG + ".correction_tools.alignment")
+    al.__dict__.update(np=np, os=os, time=_time, _allowed_colors=root._allowed_colors, _image_size=root._image_size, _num_buffer_frames=10,
+                       _num_empty_frames=0, _image_dtype="uint16", _correction_folder="", __package__=_PKG + ".correction_tools",
+                       __name__=_PKG + ".correction_tools.alignment")
+    _lift_assigns("correction_tools/alignment.py", {"_default_align_corr_args", "_default_align_fitting_args"}, al.__dict__)
+    _lift_nodes("correction_tools/alignment.py", {"_find_boundary", "generate_drift_crops", "align_beads", "align_image"}, al.__dict__)
+    ct.alignment = al
+    sys.modules.update({_PKG + ".correction_tools": ct, _PKG + ".correction_tools.alignment": al})
+    root.correction_tools = ct
+    ns = types.SimpleNamespace(align_image=al.align_image, align_beads=al.align_beads, generate_drift_crops=al.generate_drift_crops,
+                               fft3d_from2d=at.fft3d_from2d, fftalign_2d=at.fftalign_2d, find_paired_centers=mt.find_paired_centers,
+                               check_paired_centers=mt.check_paired_centers, defaults=(al._default_align_corr_args, al._default_align_fitting_args))
+    _cache["align"] = ns
+    return ns
