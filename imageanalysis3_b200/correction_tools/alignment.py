@@ -102,6 +102,7 @@ def align_image(src_im, ref_im, crop_list=None, use_autocorr=True, precision_fol
     """(drift, flag) of ``src_im`` against ``ref_im`` (arrays or .dax files), reference correction_tools/alignment.py:
     527-696: crops are processed in order until ``min_good_drifts`` of their drifts lie within ``drift_diff_th`` of the
     running mean (flag 0); otherwise the mean of the closest pair of drifts and the one nearest to both (flag 1)"""
+    from ..sharding import map_stacks
     from ..spot_tools.fitting import fit_fov_image, select_sparse_centers
     corr_args = dict(_default_align_corr_args)
     corr_args.update(correction_args)
@@ -132,9 +133,10 @@ def align_image(src_im, ref_im, crop_list=None, use_autocorr=True, precision_fol
         t0 = time.time()
         sel = tuple(slice(*np.array(c, dtype=int)) for c in crop)
         sim, rim = np.ascontiguousarray(src[sel]), np.ascontiguousarray(ref[sel])
-        src_cts = select_sparse_centers(fit_fov_image(sim, channel, verbose=detailed_verbose, **fit_args)[:, 1:4], match_distance_th)
-        ref_cts = select_sparse_centers(fit_fov_image(rim, channel, verbose=detailed_verbose, **fit_args)[:, 1:4], match_distance_th,
-                                        verbose=detailed_verbose)
+        # the two fits of a crop are independent: both in flight at once (each is latency-bound on its own)
+        spots = map_stacks(lambda im: fit_fov_image(im, channel, verbose=detailed_verbose, **fit_args), [sim, rim], inflight=2)
+        src_cts = select_sparse_centers(spots[0][:, 1:4], match_distance_th)
+        ref_cts = select_sparse_centers(spots[1][:, 1:4], match_distance_th, verbose=detailed_verbose)
         dft, _, _ = align_beads(src_cts, ref_cts, sim, rim, use_fft=True, match_distance_th=match_distance_th,
                                 return_paired_cts=True, verbose=detailed_verbose)
         drifts.append(dft * -1)                       # bead centres move opposite to the cross-correlation convention
