@@ -1789,7 +1789,7 @@ int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t*
   std::sort(hl, hl + n);                                     // np.where order: the fix is sequential and in place
   if (small_copy(d_list, hl, (size_t)n * 4, st)) return -1;
   if (sc.dalloc(&d_vals, (size_t)n * s->Z * 4)) return -1;
-  if (launch_hot_fix((uint16_t*)s->d_im, s->Z, s->X, s->Y, d_list, n, d_vals, st)) return -1;
+  if (launch_hot_fix((uint16_t*)s->d_im, s->Z, s->X, s->Y, d_list, n, d_cnt /* the counts are no longer needed */, d_vals, st)) return -1;
   IA3_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

@@ -6,7 +6,8 @@
 //                    y-1 one taken twice, as the reference does)
 //   k_hot_fix        replaces the hot columns one after the other, in np.where order, by the float32 mean of their four
 //                    neighbours (:505-509); an already replaced neighbour contributes its float32 value, the final
-//                    store truncates to uint16 like .astype (one CTA: the list is tens of columns long)
+//                    store truncates to uint16 like .astype (one CTA walks the list; a column's position in it is looked
+//                    up in an X x Y table, so even thousands of hot columns cost microseconds each)
 //   k_mix            bleed-through mixing sum_j im_j * profile[i, j] in float32, clip, truncate (io_tools/load.py:
 //                    347-367) fused with the illumination division (:369-381)
 //   k_spline_iir /   scipy.ndimage.spline_filter(np.pad(im, 12, 'edge'), 3, mode='nearest'): the cubic B-spline prefilter
@@ -47,8 +48,15 @@ __global__ void __launch_bounds__(256) k_hot_select(const int* __restrict__ cnt,
   if ((double)cnt[t] > thr) { const int p = atomicAdd(count, 1); if (p < cap) out[p] = (int)t; }
 }
 
-// list: flat x * Y + y indices in ascending (np.where) order; vals: n x Z float32 scratch
-__global__ void __launch_bounds__(128) k_hot_fix(uint16_t* __restrict__ im, int Z, int X, int Y, const int* __restrict__ list, int n, float* __restrict__ vals) {
+// slot[x * Y + y] = position of the column in the sorted list of hot columns, -1 elsewhere
+__global__ void __launch_bounds__(256) k_hot_slots(const int* __restrict__ list, int n, int* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) slot[list[i]] = i;
+}
+
+// list: flat x * Y + y indices in ascending (np.where) order; vals: n x Z float32 scratch; slot: see k_hot_slots
+__global__ void __launch_bounds__(128) k_hot_fix(uint16_t* __restrict__ im, int Z, int X, int Y, const int* __restrict__ list, int n,
+                                                 const int* __restrict__ slot, float* __restrict__ vals) {
   for (int i = 0; i < n; ++i) {
     const int x = list[i] / Y, y = list[i] % Y;
     const bool interior = x > 0 && y > 0 && x < X - 1 && y < Y - 1;
@@ -59,10 +67,9 @@ __global__ void __launch_bounds__(128) k_hot_fix(uint16_t* __restrict__ im, int 
         const int nx[4] = {x + 1, x - 1, x, x}, ny[4] = {y, y, y + 1, y - 1};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int key = nx[k] * Y + ny[k];
-          float w = (float)im[((long long)z * X + nx[k]) * Y + ny[k]];
-          for (int j = 0; j < i; ++j) if (list[j] == key) w = vals[(long long)j * Z + z];      // already replaced: its float32 value
-          nb[k] = w;
+          const int j = slot[nx[k] * Y + ny[k]];
+          // a neighbour that was replaced earlier in the sequence contributes its float32 value
+          nb[k] = (j >= 0 && j < i) ? vals[(long long)j * Z + z] : (float)im[((long long)z * X + nx[k]) * Y + ny[k]];
         }
         v = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(nb[0], nb[1]), nb[2]), nb[3]), 4.0f);
       } else {
@@ -296,9 +303,12 @@ int launch_hot_select(const int* cnt, long long n, double thr, int* out, int* co
   IA3_LAUNCH_CHECK();
   return 0;
 }
-int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, float* vals, cudaStream_t st) {
+int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, int* slot, float* vals, cudaStream_t st) {
   if (n == 0) return 0;
-  k_hot_fix<<<1, 128, 0, st>>>(im, Z, X, Y, list, n, vals);
+  IA3_CUDA(cudaMemsetAsync(slot, 0xff, (size_t)X * Y * sizeof(int), st));
+  k_hot_slots<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(list, n, slot);
+  IA3_LAUNCH_CHECK();
+  k_hot_fix<<<1, 128, 0, st>>>(im, Z, X, Y, list, n, slot, vals);
   IA3_LAUNCH_CHECK();
   return 0;
 }

@@ -6,7 +6,7 @@
 namespace ia3 {
 int launch_hot_count(const uint16_t* im, int Z, int X, int Y, float hot_th, int* cnt, cudaStream_t st);
 int launch_hot_select(const int* cnt, long long n, double thr, int* out, int* count, int cap, cudaStream_t st);
-int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, float* vals, cudaStream_t st);
+int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, int* slot /* X*Y ints, scratch */, float* vals, cudaStream_t st);
 // Tp = float or double: the dtype the profile arrays were saved in decides numpy's arithmetic type
 template <typename Tp>
 int launch_mix(const uint16_t* const* d_ins, int n_in, const Tp* bleed, const Tp* illum, uint16_t* out, long long XY, long long n, cudaStream_t st);

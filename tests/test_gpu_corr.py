@@ -155,3 +155,22 @@ def test_corrected_stacks_feed_fit_fov_image_without_leaving_the_device(lib, cor
         assert np.array_equal(st.fetch(), a)                      # the caller's stack keeps its image
         with pytest.raises(NotImplementedError):
             fit_fov_image(st, ch, seeding_kwargs=dict(sel_center=[4, 20, 20]), **fkw)
+
+
+def test_thousands_of_hot_columns(lib):
+    """a camera with many hot columns (or a low hot_th): the sequential replacement still follows np.where order"""
+    from oracle import correct_oracle
+    rng = np.random.default_rng(9)
+    Z, X, Y = 6, 240, 250
+    im = rng.integers(200, 400, size=(Z, X, Y), dtype=np.uint16)
+    xs, ys = rng.integers(0, X, 3000), rng.integers(0, Y - 1, 3000)
+    im[:, xs, ys] = 15000
+    half = rng.random(3000) < 0.5
+    im[:, xs[half], ys[half] + 1] = 60000            # runs of adjacent hot columns: later fixes read earlier ones
+    want = correct_oracle.remove_hot_pixels(im.astype(np.float32))
+    st = lib.Stack(im)
+    n = st.remove_hot_pixels()
+    f = im.astype(np.float32)
+    conv = (np.roll(f, 1, 1) + np.roll(f, -1, 1) + np.roll(f, 1, 2) + np.roll(f, 1, 2)) / 4
+    assert n == int((np.sum(f > 4 * conv, 0) > 0.5 * Z).sum()) and n > 2500
+    assert np.array_equal(st.fetch(), want.astype(np.uint16))
