@@ -7,9 +7,10 @@ correction runs on the resident uint16 stacks through libia3b200 (ia3_corr_*); t
 to spot_tools.fitting.fit_fov_image without leaving the device (``return_stacks=True``).
 
 Same signature, argument meaning and error behaviour as the reference.  Branches of the reference that leave this
-path raise NotImplementedError instead of computing something else: calculate_drift with use_autocorr=True (correction_tools/
-alignment.py align_image's phase correlation via skimage; its bead-fitting mode, use_autocorr=False, is built), warp_image=False (returns spot-coordinate functions from
-correction_tools/chromatic.py), z_shift_corr, gaussian_highpass, normalization and a non-uint16 output_dtype.
+path raise NotImplementedError instead of computing something else: calculate_drift with use_autocorr=True (the phase
+correlation of correction_tools/alignment.py align_image needs skimage; its bead-fitting mode, use_autocorr=False, is built),
+z_shift_corr, gaussian_highpass, normalization and a non-uint16 output_dtype.  ``warp_image=False`` returns, like the
+reference, the unwarped images plus one spot-coordinate function per channel (correction_tools/chromatic.py).
 
 One reference behaviour is kept on purpose because results must be the same: the warp code in the reference sits
 inside its ``if verbose:`` block (io_tools/load.py:436-459), so images are only warped when ``verbose`` is true.
@@ -272,8 +273,6 @@ def correct_fov_image(dax_filename, sel_channels,
                                   "alignment.align_image), not built; use_autocorr=False (bead fitting on the device) or pass drift=")
     if calculate_drift and str(drift_channel) not in load_channels:
         load_channels.append(str(drift_channel))
-    if not warp_image:
-        raise NotImplementedError("warp_image=False returns spot-coordinate functions (correction_tools.chromatic), not built")
     if z_shift_corr or gaussian_highpass or normalization:
         raise NotImplementedError("z_shift_corr / gaussian_highpass / normalization are not built on the device path")
     if np.dtype(output_dtype) != np.dtype(np.uint16):
@@ -301,7 +300,7 @@ def correct_fov_image(dax_filename, sel_channels,
                 raise IndexError(f"Wrong input shape for bleed_profile: {bleed_profile.shape}, should be {(n, n, single_im_size[-2], single_im_size[-1])}")
     if chromatic_corr and overlap:
         if chromatic_profile is None:
-            chromatic_profile = load_correction_profile('chromatic', corr_channels=corr_channels, correction_folder=correction_folder,
+            chromatic_profile = load_correction_profile('chromatic' if warp_image else 'chromatic_constants', corr_channels=corr_channels, correction_folder=correction_folder,
                                                         all_channels=all_channels, ref_channel=chromatic_ref_channel,
                                                         im_size=single_im_size, verbose=verbose)
         else:
@@ -340,11 +339,25 @@ def correct_fov_image(dax_filename, sel_channels,
                                illumination_corr=illumination_corr, illumination_profile=illumination_profile,
                                bleed_corr=bleed_corr, bleed_profile=bleed_profile,
                                chromatic_ref_channel=chromatic_ref_channel, chromatic_corr=chromatic_corr,
-                               chromatic_profile=chromatic_profile, warp=bool(verbose or force_warp), return_stacks=return_stacks)
+                               chromatic_profile=chromatic_profile, warp=bool(warp_image and (verbose or force_warp)), return_stacks=return_stacks)
+    warp_functions = None
+    if not warp_image:
+        # io_tools/load.py:461-485: the images stay where they are, the spots are moved instead
+        from ..correction_tools.chromatic import generate_chromatic_function
+        chroma_channels = [ch for ch in corr_channels if ch in sel_channels and ch != chromatic_ref_channel]
+        final_drift = np.asarray(found["drift"])
+        warp_functions = []
+        for ch in sel_channels:
+            if (chromatic_corr and ch in chroma_channels) or final_drift.any():
+                warp_functions.append(generate_chromatic_function(chromatic_profile[ch] if (chromatic_corr and ch in chroma_channels) else None, final_drift))
+            else:
+                warp_functions.append(lambda _spots: _spots)
     if verbose:
         print(f"-- corrected channels {sel_channels} on the device in {time.time() - t0:.3f}s")
         print(f"-- finish correction in {time.time() - t_total:.3f}s")
     ret = [out]
+    if not warp_image:
+        ret.append(warp_functions)
     if return_drift:
         ret.extend([found["drift"], found["flag"]])
     return tuple(ret)

@@ -259,6 +259,7 @@ def main_corr():
     from oracle import correct_oracle
     warnings.simplefilter("ignore")
     ns = ref_loader.load_corrections()
+    ref_loader.load_chromatic()
     chs, ims, frames, illum, bleed, chrom, nbuf = corr_case()
     Z, X, Y = ims[0].shape
     d = tempfile.mkdtemp()
@@ -300,6 +301,26 @@ def main_corr():
         names.append(f"{tag}|{','.join(sel)}|{repr(dr)}|{repr(flags)}|{int(verbose)}")
         print(tag, "reference == oracle on", sel)
     out["cases"] = np.array(names)
+    # warp_image=False: unwarped images + one spot-coordinate function per channel (correction_tools/chromatic.py:41-114)
+    consts = {'750': dict(constants=[np.array([0.2, 1e-3, -2e-3, 5e-4]), np.array([-0.1, 2e-3, 1e-3, 0., 1e-5, 0., 0., 2e-5, 0., -1e-5]), np.array([0.3])],
+                          fitting_orders=np.array([1, 2, 0]), ref_center=np.array([4., 20., 24.])),
+              '647': None, '561': dict(constants=[np.array([0.]), np.array([0.05]), np.array([-0.02, 1e-3, 0., 0.])],
+                                       fitting_orders=np.array([0, 0, 1]), ref_center=np.array([4., 20., 24.]))}
+    pts = np.random.default_rng(3).uniform([0, 0, 0], [Z, X, Y], size=(40, 3))
+    table = np.concatenate([np.full((40, 1), 900.), pts, np.ones((40, 7))], axis=1).astype(np.float32)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ims_nw, funcs = ns.correct_fov_image(fn, ['750', '647', '561'], drift=drift, warp_image=False, verbose=True,
+                                             **{**kw, 'chromatic_profile': consts})
+        ims_nw0, funcs0 = ns.correct_fov_image(fn, ['647'], drift=None, warp_image=False, verbose=True, **{**kw, 'chromatic_profile': consts})
+    out["nowarp_pts"], out["nowarp_table"] = pts, table
+    for ch, im, f in zip(['750', '647', '561'], ims_nw, funcs):
+        assert np.array_equal(im, out[f"all_quiet__{ch}"]) if f"all_quiet__{ch}" in out else True
+        out[f"nowarp_pts__{ch}"], out[f"nowarp_table__{ch}"] = f(pts), f(table)
+    out["nowarp_identity"] = funcs0[0](pts)
+    assert np.array_equal(out["nowarp_identity"], pts)
+    out["nowarp_consts"] = np.array(repr({k: (None if v is None else {a: np.asarray(b).tolist() if a != 'constants' else [c.tolist() for c in b] for a, b in v.items()})
+                                          for k, v in consts.items()}))
     np.savez_compressed(os.path.join(OUT, "corr_r2.npz"), **out)
     print("corr_r2.npz", os.path.getsize(os.path.join(OUT, "corr_r2.npz")))
 

@@ -248,8 +248,7 @@ def load_alignment():
     _lift_nodes("spot_tools/matching.py", {"find_paired_centers", "check_paired_centers"}, mt.__dict__)
     sys.modules[_PKG + ".spot_tools.matching"] = mt
     sys.modules[_PKG + ".spot_tools"].matching = mt
-    ct = types.ModuleType(_PKG + ".correction_tools")
-    ct.__path__ = []
+    ct = _correction_tools_pkg()
     al = types.ModuleType(_PKG + ".correction_tools.alignment")
     al.__dict__.update(np=np, os=os, time=_time, _allowed_colors=root._allowed_colors, _image_size=root._image_size, _num_buffer_frames=10,
                        _num_empty_frames=0, _image_dtype="uint16", _correction_folder="", __package__=_PKG + ".correction_tools",
@@ -257,10 +256,37 @@ def load_alignment():
     _lift_assigns("correction_tools/alignment.py", {"_default_align_corr_args", "_default_align_fitting_args"}, al.__dict__)
     _lift_nodes("correction_tools/alignment.py", {"_find_boundary", "generate_drift_crops", "align_beads", "align_image"}, al.__dict__)
     ct.alignment = al
-    sys.modules.update({_PKG + ".correction_tools": ct, _PKG + ".correction_tools.alignment": al})
-    root.correction_tools = ct
+    sys.modules[_PKG + ".correction_tools.alignment"] = al
     ns = types.SimpleNamespace(align_image=al.align_image, align_beads=al.align_beads, generate_drift_crops=al.generate_drift_crops,
                                fft3d_from2d=at.fft3d_from2d, fftalign_2d=at.fftalign_2d, find_paired_centers=mt.find_paired_centers,
                                check_paired_centers=mt.check_paired_centers, defaults=(al._default_align_corr_args, al._default_align_fitting_args))
     _cache["align"] = ns
+    return ns
+
+
+def _correction_tools_pkg():
+    name = _PKG + ".correction_tools"
+    if name not in sys.modules:
+        ct = types.ModuleType(name)
+        ct.__path__ = []
+        sys.modules[name] = ct
+        sys.modules[_PKG].correction_tools = ct
+    return sys.modules[name]
+
+
+def load_chromatic():
+    """correction_tools/chromatic.py generate_chromatic_function (:41-114) and generate_polynomial_data (:415-438), lifted:
+    what the reference's correct_fov_image(warp_image=False) imports.  -> namespace with both functions"""
+    if "chrom" in _cache:
+        return _cache["chrom"]
+    load()
+    import pickle
+    ct = _correction_tools_pkg()
+    ch = types.ModuleType(_PKG + ".correction_tools.chromatic")
+    ch.__dict__.update(np=np, os=os, pickle=pickle)
+    _lift_nodes("correction_tools/chromatic.py", {"generate_chromatic_function", "generate_polynomial_data"}, ch.__dict__)
+    ct.chromatic = ch
+    sys.modules[_PKG + ".correction_tools.chromatic"] = ch
+    ns = types.SimpleNamespace(generate_chromatic_function=ch.generate_chromatic_function, generate_polynomial_data=ch.generate_polynomial_data)
+    _cache["chrom"] = ns
     return ns

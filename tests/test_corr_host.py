@@ -104,8 +104,36 @@ def test_argument_errors_follow_the_reference(corr, tmp_path):
         load.correct_fov_image(fn, ['750'], **{**kw, 'bleed_profile': bleed[:2, :2]})
     with pytest.raises(KeyError):
         load.correct_fov_image(fn, ['750'], **{**kw, 'chromatic_profile': {'647': None}})
-    for flag in ('calculate_drift', 'z_shift_corr', 'gaussian_highpass', 'normalization'):
+    for flag in ('calculate_drift', 'z_shift_corr', 'gaussian_highpass', 'normalization'):      # calculate_drift: with the default use_autocorr=True
         with pytest.raises(NotImplementedError):
             load.correct_fov_image(fn, ['750'], **{**kw, flag: True})
-    with pytest.raises(NotImplementedError):
-        load.correct_fov_image(fn, ['750'], **{**kw, 'warp_image': False})
+
+
+def nowarp_consts(g):
+    raw = ast.literal_eval(str(g["nowarp_consts"]))
+    return {ch: None if v is None else dict(constants=[np.array(c) for c in v['constants']], fitting_orders=np.array(v['fitting_orders']),
+                                            ref_center=np.array(v['ref_center'])) for ch, v in raw.items()}
+
+
+def test_chromatic_coordinate_functions_match_reference(corr, tmp_path):
+    """generate_chromatic_function (correction_tools/chromatic.py:41-114): what correct_fov_image(warp_image=False) hands back"""
+    import pickle
+    from imageanalysis3_b200.correction_tools import chromatic
+    consts = nowarp_consts(corr)
+    drift = np.array([0.4, -1.3, 2.2], dtype=np.float32)
+    pts, table = corr["nowarp_pts"], corr["nowarp_table"]
+    for ch in ('750', '647', '561'):
+        f = chromatic.generate_chromatic_function(consts[ch], drift)
+        assert np.array_equal(f(pts), corr[f"nowarp_pts__{ch}"]) and np.array_equal(f(table), corr[f"nowarp_table__{ch}"]), ch
+        assert f(table).dtype == corr[f"nowarp_table__{ch}"].dtype
+    with open(tmp_path / "c.pkl", "wb") as fh:
+        pickle.dump(consts['750'], fh)
+    assert np.array_equal(chromatic.generate_chromatic_function(str(tmp_path / "c.pkl"), drift)(pts), corr["nowarp_pts__750"])
+    ident = chromatic.generate_chromatic_function(None, None)
+    assert ident(pts) is pts and len(chromatic.generate_chromatic_function(consts['750'])([])) == 0
+    with pytest.raises(TypeError):
+        chromatic.generate_chromatic_function(3)
+    with pytest.raises(ValueError):
+        chromatic.generate_chromatic_function(consts['750'])(np.zeros((4, 5)))
+    X = chromatic.generate_polynomial_data(np.array([[1., 2., 3.], [2., 0., -1.]]), 2)
+    assert X.shape == (2, 10) and np.array_equal(X[0], [1, 1, 2, 3, 1, 2, 3, 4, 6, 9])

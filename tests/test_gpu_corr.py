@@ -174,3 +174,20 @@ def test_thousands_of_hot_columns(lib):
     conv = (np.roll(f, 1, 1) + np.roll(f, -1, 1) + np.roll(f, 1, 2) + np.roll(f, 1, 2)) / 4
     assert n == int((np.sum(f > 4 * conv, 0) > 0.5 * Z).sum()) and n > 2500
     assert np.array_equal(st.fetch(), want.astype(np.uint16))
+
+
+def test_warp_image_false_returns_images_and_coordinate_functions(lib, corr, tmp_path):
+    from imageanalysis3_b200.io_tools import load
+    from test_corr_host import nowarp_consts
+    chs, illum, bleed, chrom = profiles(corr)
+    fn = write_movie(tmp_path, corr)
+    kw = dict(single_im_size=[8, 40, 48], all_channels=chs, num_buffer_frames=2, num_empty_frames=0, corr_channels=chs,
+              illumination_profile=illum, bleed_profile=bleed, chromatic_profile=nowarp_consts(corr), drift_channel='561')
+    ims, funcs, drift, flag = load.correct_fov_image(fn, ['750', '647', '561'], drift=[0.4, -1.3, 2.2], warp_image=False, return_drift=True, verbose=True, **kw)
+    assert flag == 0 and drift.dtype == np.float32 and len(funcs) == 3
+    for ch, im, f in zip(['750', '647', '561'], ims, funcs):
+        if f"all_quiet__{ch}" in corr.files:
+            assert np.array_equal(im, corr[f"all_quiet__{ch}"])            # corrected, not warped
+        assert np.array_equal(f(corr["nowarp_pts"]), corr[f"nowarp_pts__{ch}"]) and np.array_equal(f(corr["nowarp_table"]), corr[f"nowarp_table__{ch}"])
+    (ims0, funcs0) = load.correct_fov_image(fn, ['647'], drift=None, warp_image=False, verbose=False, **kw)
+    assert funcs0[0](corr["nowarp_pts"]) is corr["nowarp_pts"] or np.array_equal(funcs0[0](corr["nowarp_pts"]), corr["nowarp_identity"])
