@@ -279,8 +279,9 @@ def run_ours(args):
         # one rank = one GPU = its own share of the box's cores: the ranks' host threads stop migrating over each other
         try:
             cpus = sorted(os.sched_getaffinity(0))
-            share = max(1, len(cpus) // world)
-            os.sched_setaffinity(0, cpus[local * share:(local + 1) * share] or cpus)
+            share = len(cpus) // world
+            if share >= 4:                                   # with fewer cores per rank the ranks are better off sharing all of them
+                os.sched_setaffinity(0, cpus[local * share:(local + 1) * share])
         except (AttributeError, OSError):
             pass
     if os.environ.get("IA3_SWITCH_INTERVAL"):
