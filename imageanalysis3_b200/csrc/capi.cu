@@ -1794,6 +1794,47 @@ int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t*
   return 0;
 }
 
+// median of N values given as a 65536-bin histogram, as np.median returns it for a float32 array of integers: the middle
+// element, or the float32 mean of the two middle elements
+static float median_from_counts(const unsigned long long* c, unsigned long long N) {
+  const unsigned long long k_lo = (N - 1) / 2, k_hi = N / 2;
+  unsigned long long run = 0;
+  int v_lo = -1, v_hi = -1;
+  for (int v = 0; v < 65536 && v_hi < 0; ++v) {
+    run += c[v];
+    if (v_lo < 0 && run > k_lo) v_lo = v;
+    if (run > k_hi) v_hi = v;
+  }
+  return ((float)v_lo + (float)v_hi) / 2.0f;
+}
+
+int ia3_corr_zshift(ia3_stack* s) {
+  IA3_STAT("ia3_corr_zshift");
+  if (ensure_device()) return -1;
+  if (corr_check(s, "ia3_corr_zshift")) return -1;
+  cudaStream_t st = s->stream;
+  Scoped sc;
+  const size_t hb = 65536 * sizeof(unsigned long long), nxy = (size_t)s->X * s->Y;
+  unsigned long long* d_h = nullptr; float* d_med = nullptr; void* h = nullptr;
+  if (sc.dalloc(&d_h, hb * s->Z) || sc.dalloc(&d_med, sizeof(float) * s->Z + 256) || sc.halloc(&h, hb * s->Z + sizeof(float) * s->Z + 256)) return -1;
+  for (int z = 0; z < s->Z; ++z)
+    if (launch_hist_u16((const uint16_t*)s->d_im + (size_t)z * nxy, (long long)nxy, d_h + (size_t)z * 65536, st)) return -1;
+  if (small_copy(h, d_h, hb * s->Z, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long* hc = static_cast<const unsigned long long*>(h);
+  float* med = reinterpret_cast<float*>(static_cast<char*>(h) + hb * s->Z);
+  std::vector<unsigned long long> all(65536, 0);
+  for (int z = 0; z < s->Z; ++z) {
+    med[z] = median_from_counts(hc + (size_t)z * 65536, nxy);
+    for (int v = 0; v < 65536; ++v) all[v] += hc[(size_t)z * 65536 + v];
+  }
+  const float med_all = median_from_counts(all.data(), (unsigned long long)s->nvox);
+  if (small_copy(d_med, med, sizeof(float) * s->Z, st)) return -1;
+  if (launch_zshift((uint16_t*)s->d_im, (long long)nxy, (long long)s->nvox, d_med, med_all, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void* illum, int profile_f64, ia3_stack* out) {
   IA3_STAT("ia3_corr_mix");
   if (ensure_device()) return -1;

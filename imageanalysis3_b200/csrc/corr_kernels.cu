@@ -8,6 +8,8 @@
 //                    neighbours (:505-509); an already replaced neighbour contributes its float32 value, the final
 //                    store truncates to uint16 like .astype (one CTA walks the list; a column's position in it is looked
 //                    up in an X x Y table, so even thousands of hot columns cost microseconds each)
+//   k_zshift         corrections.py:479-487 Z_Shift_Correction: planes scaled to the stack's median; the medians are read off
+//                    per-plane device histograms on the host (exact order statistics)
 //   k_mix            bleed-through mixing sum_j im_j * profile[i, j] in float32, clip, truncate (io_tools/load.py:
 //                    347-367) fused with the illumination division (:369-381)
 //   k_spline_iir /   scipy.ndimage.spline_filter(np.pad(im, 12, 'edge'), 3, mode='nearest'): the cubic B-spline prefilter
@@ -113,6 +115,14 @@ __global__ void __launch_bounds__(256) k_mix(const uint16_t* const* __restrict__
     if (illum) u = (uint16_t)(int)rn_div((Tp)(float)u, illum[pix]);
     out[t] = u;
   }
+}
+
+// corrections.py:479-487 Z_Shift_Correction: every plane scaled to the whole stack's median, float32 arithmetic in numpy's
+// order (im / median_z, then * median_all), truncated to uint16 like .astype
+__global__ void __launch_bounds__(256) k_zshift(uint16_t* __restrict__ im, long long XY, long long n, const float* __restrict__ med_z, float med_all) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+    im[t] = (uint16_t)(int)__fmul_rn(__fdiv_rn((float)im[t], med_z[t / XY]), med_all);
 }
 
 constexpr int NPAD = 12;        // scipy.ndimage._interpolation._prepad_for_spline_filter
@@ -291,6 +301,12 @@ __global__ void __launch_bounds__(256) k_warp(const double* __restrict__ coef, i
   }
 }
 
+int launch_zshift(uint16_t* im, long long XY, long long n, const float* d_med_z, float med_all, cudaStream_t st) {
+  if (n == 0) return 0;
+  k_zshift<<<148 * 8, 256, 0, st>>>(im, XY, n, d_med_z, med_all);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
 int launch_hot_count(const uint16_t* im, int Z, int X, int Y, float hot_th, int* cnt, cudaStream_t st) {
   const long long n = (long long)X * Y;
   k_hot_count<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(im, Z, X, Y, hot_th, cnt);

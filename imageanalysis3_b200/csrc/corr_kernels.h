@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 namespace ia3 {
+int launch_zshift(uint16_t* im, long long XY, long long n, const float* d_med_z, float med_all, cudaStream_t st);
 int launch_hot_count(const uint16_t* im, int Z, int X, int Y, float hot_th, int* cnt, cudaStream_t st);
 int launch_hot_select(const int* cnt, long long n, double thr, int* out, int* count, int cap, cudaStream_t st);
 int launch_hot_fix(uint16_t* im, int Z, int X, int Y, const int* list, int n, int* slot /* X*Y ints, scratch */, float* vals, cudaStream_t st);

@@ -9,7 +9,7 @@ to spot_tools.fitting.fit_fov_image without leaving the device (``return_stacks=
 Same signature, argument meaning and error behaviour as the reference.  Branches of the reference that leave this
 path raise NotImplementedError instead of computing something else: calculate_drift with use_autocorr=True (the phase
 correlation of correction_tools/alignment.py align_image needs skimage; its bead-fitting mode, use_autocorr=False, is built),
-z_shift_corr, gaussian_highpass, normalization and a non-uint16 output_dtype.  ``warp_image=False`` returns, like the
+gaussian_highpass, normalization and a non-uint16 output_dtype.  ``warp_image=False`` returns, like the
 reference, the unwarped images plus one spot-coordinate function per channel (correction_tools/chromatic.py).
 
 One reference behaviour is kept on purpose because results must be the same: the warp code in the reference sits
@@ -170,7 +170,7 @@ def resident_profile(a):
 
 
 def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=None,
-                         hot_pixel_corr=True, hot_pixel_th=4,
+                         hot_pixel_corr=True, hot_pixel_th=4, z_shift_corr=False,
                          illumination_corr=True, illumination_profile=None,
                          bleed_corr=True, bleed_profile=None,
                          chromatic_ref_channel='647', chromatic_corr=True, chromatic_profile=None,
@@ -191,6 +191,9 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
     if hot_pixel_corr:
         for s in stacks:
             s.remove_hot_pixels(hot_th=hot_pixel_th)
+    if z_shift_corr:
+        for s in stacks:
+            s.z_shift_correct()
     overlap = [ch for ch in corr_channels if ch in sel_channels]
     illum = {}
     if illumination_corr:
@@ -273,8 +276,8 @@ def correct_fov_image(dax_filename, sel_channels,
                                   "alignment.align_image), not built; use_autocorr=False (bead fitting on the device) or pass drift=")
     if calculate_drift and str(drift_channel) not in load_channels:
         load_channels.append(str(drift_channel))
-    if z_shift_corr or gaussian_highpass or normalization:
-        raise NotImplementedError("z_shift_corr / gaussian_highpass / normalization are not built on the device path")
+    if gaussian_highpass or normalization:
+        raise NotImplementedError("gaussian_highpass / normalization are not built on the device path")
     if np.dtype(output_dtype) != np.dtype(np.uint16):
         raise NotImplementedError("the device corrections produce uint16 stacks (the reference's default output_dtype)")
     if illumination_corr:
@@ -335,7 +338,7 @@ def correct_fov_image(dax_filename, sel_channels,
             return found["drift"]
     t0 = time.time()
     out = correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=drift, drift_from=drift_from,
-                               hot_pixel_corr=hot_pixel_corr, hot_pixel_th=hot_pixel_th,
+                               hot_pixel_corr=hot_pixel_corr, hot_pixel_th=hot_pixel_th, z_shift_corr=z_shift_corr,
                                illumination_corr=illumination_corr, illumination_profile=illumination_profile,
                                bleed_corr=bleed_corr, bleed_profile=bleed_profile,
                                chromatic_ref_channel=chromatic_ref_channel, chromatic_corr=chromatic_corr,

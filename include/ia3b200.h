@@ -76,6 +76,9 @@ int ia3_stack_fetch(ia3_stack* s, void* out);
  * brighter than hot_th x the mean of their np.roll neighbours in more than hot_pix_th x Z planes are replaced, in
  * np.where order, by the float32 mean of their four neighbours.  *n_hot = number of such columns. */
 int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t* n_hot);
+/* corrections.py:479-487 Z_Shift_Correction(im.astype(float32), dtype=uint16), in place: every plane divided by its median and multiplied
+ * by the stack's median (float32, numpy's order), truncated to uint16.  io_tools/load.py:336-345. */
+int ia3_corr_zshift(ia3_stack* s);
 /* out = illumination(bleed-through(ins)) (io_tools/load.py:347-381): with ``bleed`` (host, n_in x X x Y: row i of the
  * (n, n, X, Y) profile) out = clip(sum_j ins[j] * bleed[j]) truncated to uint16, else out = ins[0]; with ``illum``
  * (host, X x Y) that result is divided by it and truncated again.  profile_f64: the profiles are float64 (numpy then

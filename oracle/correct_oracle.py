@@ -2,6 +2,7 @@
 
 Not part of the product.  Restates, on in-memory channel stacks (file reading stays with the caller),
   hot-pixel removal        corrections.py:490-510 Remove_Hot_Pixels (called at io_tools/load.py:323-334)
+  z-shift correction       corrections.py:479-487 Z_Shift_Correction (io_tools/load.py:336-345)
   bleed-through mixing     io_tools/load.py:347-367
   illumination division    io_tools/load.py:369-381
   drift + chromatic warp   io_tools/load.py:424-459 (scipy.ndimage.map_coordinates, cubic, mode='nearest')
@@ -28,7 +29,12 @@ def remove_hot_pixels(im, dtype=np.uint16, hot_pix_th=0.50, hot_th=4):
     return nim.astype(dtype)
 
 
-def correct_stacks(ims, load_channels, sel_channels, corr_channels, drift=None, hot_pixel_corr=True, hot_pixel_th=4,
+def z_shift_correction(im, dtype=np.uint16):
+    """im float32 (Z, X, Y): every plane divided by its median and multiplied by the stack's median (corrections.py:479-487)"""
+    return (im / np.median(im, axis=(1, 2))[:, np.newaxis, np.newaxis] * np.median(im)).astype(dtype)
+
+
+def correct_stacks(ims, load_channels, sel_channels, corr_channels, drift=None, hot_pixel_corr=True, hot_pixel_th=4, z_shift_corr=False,
                    illumination_corr=True, illumination_profile=None, bleed_corr=True, bleed_profile=None,
                    chromatic_ref_channel='647', chromatic_corr=True, chromatic_profile=None, warp_image=True,
                    output_dtype=np.uint16, verbose=True):
@@ -39,6 +45,8 @@ def correct_stacks(ims, load_channels, sel_channels, corr_channels, drift=None, 
     ims = [np.array(im) for im in ims]
     if hot_pixel_corr:
         ims = [remove_hot_pixels(im.astype(np.float32), dtype=output_dtype, hot_th=hot_pixel_th) for im in ims]
+    if z_shift_corr:
+        ims = [z_shift_correction(im.astype(np.float32), dtype=output_dtype) for im in ims]
     overlap = [ch for ch in corr_channels if ch in sel_channels]
     if len(overlap) > 0 and bleed_corr:
         bld = [ims[load_channels.index(ch)] for ch in corr_channels]

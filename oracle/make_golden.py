@@ -234,6 +234,8 @@ def corr_case(seed=5, Z=8, X=40, Y=48, nbuf=2):
     rng = np.random.default_rng(seed)
     chs = ['750', '647', '561']
     ims = [synth((Z, X, Y), 10, 20 + i) for i in range(3)]
+    gain = 1.0 + 0.05 * np.arange(Z)[:, None, None]                        # planes of different brightness: Z_Shift_Correction has work to do
+    ims = [np.clip(im * gain, 0, 65535).astype(np.uint16) for im in ims]
     for i, im in enumerate(ims):
         im[:, 10 + i, 12] = 30000                  # isolated hot columns
         im[:, 20, 20 + i] = 9000                   # two adjacent ones, both detected (the y + 1 neighbour is not looked at):
@@ -281,6 +283,8 @@ def main_corr():
         "chrom_only": (['750', '561'], None, {**off, 'chromatic_corr': True}, True),
         "drift_only": (['647'], [-2.6, 3.3, -0.7], off, True),
         "drift_big": (['647'], [11.0, -30.5, 60.25], off, True),    # far beyond the padding: mode='nearest' clamps
+        "zshift_only": (['750', '561'], None, {**off, 'z_shift_corr': True}, True),
+        "zshift_all": (['750', '647'], drift, {'z_shift_corr': True}, True),
     }
     out = dict(frames=frames, bleed=bleed, meta=np.array(repr(dict(numpy=np.__version__, scipy=scipy.__version__))))
     for ch in chs:

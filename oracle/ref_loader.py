@@ -190,8 +190,8 @@ def load_corrections():
     vt = sys.modules[_PKG + ".visual_tools"]
     vt.DaxReader = vt_env["DaxReader"]
     cor_env = dict(np=np, os=os)
-    _lift_nodes("corrections.py", {"Remove_Hot_Pixels"}, cor_env)
-    corrections = types.SimpleNamespace(Remove_Hot_Pixels=cor_env["Remove_Hot_Pixels"])
+    _lift_nodes("corrections.py", {"Remove_Hot_Pixels", "Z_Shift_Correction"}, cor_env)
+    corrections = types.SimpleNamespace(Remove_Hot_Pixels=cor_env["Remove_Hot_Pixels"], Z_Shift_Correction=cor_env["Z_Shift_Correction"])
     load_m = sys.modules[_PKG + ".io_tools.load"]
     env = load_m.__dict__
     env.update(np=np, os=os, sys=sys, time=_time, scipy=scipy, map_coordinates=map_coordinates, shift=shift, corrections=corrections,

@@ -81,6 +81,17 @@ def test_each_step_matches_oracle_on_fresh_inputs(lib, shape, seed):
             want = correct_oracle.correct_stacks(ims, chs, sel, chs, illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom, warp_image=False)
             got = load.correct_image_stacks(ims, chs, sel, chs, illumination_profile=illum, bleed_profile=bleed, chromatic_profile=chrom, warp=False)
             assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    # z-shift correction: planes of different brightness scaled to the stack's median (exact medians from device histograms)
+    dim = [np.clip(im * (0.6 + 0.05 * np.arange(Z))[:, None, None], 0, 65535).astype(np.uint16) for im in ims]
+    st = lib.Stack(dim[0])
+    st.z_shift_correct()
+    assert np.array_equal(st.fetch(), correct_oracle.z_shift_correction(dim[0].astype(np.float32)))
+    want = correct_oracle.correct_stacks(dim, chs, ['750', '561'], chs, drift=[0.5, 0.5, -0.5], z_shift_corr=True, illumination_profile=illum,
+                                         bleed_profile=bleed, chromatic_profile=chrom)
+    got = load.correct_image_stacks(dim, chs, ['750', '561'], chs, drift=[0.5, 0.5, -0.5], z_shift_corr=True, illumination_profile=illum,
+                                    bleed_profile=bleed, chromatic_profile=chrom)
+    for ch, a, b in zip(['750', '561'], got, want):
+        same_warp(a, b, f"z-shift + everything else, {ch}")
     # a per-plane chromatic profile (3, Z, X, Y)
     chrom_z = {ch: (rng.standard_normal((3, Z, X, Y)) * 0.5).astype(np.float32) if ch != '647' else None for ch in chs}
     off = dict(hot_pixel_corr=False, bleed_corr=False, illumination_corr=False)
