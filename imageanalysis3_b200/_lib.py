@@ -56,7 +56,7 @@ EXPORTS = [
     "ia3_init", "ia3_last_error", "ia3_version", "ia3_device_sm_count", "ia3_launch_count", "ia3_debug_stats",
     "ia3_timer_start", "ia3_timer_stop",
     "ia3_stack_create", "ia3_stack_wrap_device", "ia3_stack_destroy", "ia3_stack_trim",
-    "ia3_stack_alloc", "ia3_stack_fetch", "ia3_corr_hot_pixels", "ia3_corr_zshift", "ia3_corr_mix", "ia3_corr_warp", "ia3_device_upload", "ia3_device_free",
+    "ia3_stack_alloc", "ia3_stack_fetch", "ia3_corr_hot_pixels", "ia3_corr_zshift", "ia3_corr_highpass", "ia3_corr_mix", "ia3_corr_warp", "ia3_device_upload", "ia3_device_free",
     "ia3_seed_run", "ia3_seed_fetch", "ia3_seed_fetch_volume", "ia3_seed_gather_volume", "ia3_box_background",
     "ia3_seed_v2", "ia3_fft_gaussian", "ia3_seed_logratio", "ia3_stack_histogram",
     "ia3_fit_create", "ia3_fit_destroy", "ia3_fit_first_prepare", "ia3_fit_first_ties",
@@ -103,6 +103,7 @@ def load():
     lib.ia3_device_free.argtypes = [vp]
     lib.ia3_corr_hot_pixels.argtypes = [vp, dbl, dbl, P(i64)]
     lib.ia3_corr_zshift.argtypes = [vp]
+    lib.ia3_corr_highpass.argtypes = [vp, vp, i32]
     lib.ia3_corr_mix.argtypes = [P(vp), i32, vp, vp, i32, vp]
     lib.ia3_corr_warp.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.ia3_seed_run.argtypes = [vp, P(SeedCfg), P(i64), P(SeedTiming)]
@@ -316,6 +317,15 @@ class Stack:
     def z_shift_correct(self):
         """corrections.Z_Shift_Correction in place: planes scaled to the stack's median"""
         _check(load().ia3_corr_zshift(self._h))
+
+    def gaussian_highpass(self, sigma=5, truncate=2):
+        """correction_tools.filter.gaussian_high_pass_filter in place"""
+        sd = float(sigma)
+        r = int(truncate * sd + 0.5)                               # scipy.ndimage._filters.gaussian_filter1d
+        x = np.arange(-r, r + 1)
+        phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+        w = np.ascontiguousarray((phi / phi.sum())[r:])
+        _check(load().ia3_corr_highpass(self._h, _ptr(w), r))
 
     @staticmethod
     def mix(ins, bleed=None, illum=None, out=None, bleed_row=None):

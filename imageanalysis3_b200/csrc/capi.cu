@@ -1835,6 +1835,22 @@ int ia3_corr_zshift(ia3_stack* s) {
   return 0;
 }
 
+int ia3_corr_highpass(ia3_stack* s, const double* w_half, int r) {
+  IA3_STAT("ia3_corr_highpass");
+  if (ensure_device()) return -1;
+  if (corr_check(s, "ia3_corr_highpass")) return -1;
+  if (!w_half || r < 0 || r > 255) { set_error("bad Gaussian kernel"); return -1; }
+  cudaStream_t st = s->stream;
+  Scoped sc;
+  uint16_t* a = nullptr; uint16_t* b = nullptr; double* d_w = nullptr; void* h = nullptr;
+  if (sc.dalloc(&a, s->nvox * 2) || sc.dalloc(&b, s->nvox * 2) || sc.dalloc(&d_w, 4096) || sc.halloc(&h, 4096)) return -1;
+  memcpy(h, w_half, sizeof(double) * (size_t)(r + 1));
+  if (small_copy(d_w, h, sizeof(double) * (size_t)(r + 1), st)) return -1;
+  if (launch_highpass((uint16_t*)s->d_im, a, b, s->Z, s->X, s->Y, d_w, r, st)) return -1;
+  IA3_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int ia3_corr_mix(ia3_stack* const* ins, int n_in, const void* bleed, const void* illum, int profile_f64, ia3_stack* out) {
   IA3_STAT("ia3_corr_mix");
   if (ensure_device()) return -1;

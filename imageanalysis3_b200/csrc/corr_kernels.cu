@@ -10,6 +10,8 @@
 //                    up in an X x Y table, so even thousands of hot columns cost microseconds each)
 //   k_zshift         corrections.py:479-487 Z_Shift_Correction: planes scaled to the stack's median; the medians are read off
 //                    per-plane device histograms on the host (exact order statistics)
+//   k_gauss_nearest  correction_tools/filter.py:14-19 gaussian_high_pass_filter: exact uint16 Gaussian with mode='nearest', then
+//   / k_highpass     im - lowpass clipped at 0
 //   k_mix            bleed-through mixing sum_j im_j * profile[i, j] in float32, clip, truncate (io_tools/load.py:
 //                    347-367) fused with the illumination division (:369-381)
 //   k_spline_iir /   scipy.ndimage.spline_filter(np.pad(im, 12, 'edge'), 3, mode='nearest'): the cubic B-spline prefilter
@@ -123,6 +125,32 @@ __global__ void __launch_bounds__(256) k_zshift(uint16_t* __restrict__ im, long 
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
     im[t] = (uint16_t)(int)__fmul_rn(__fdiv_rn((float)im[t], med_z[t / XY]), med_all);
+}
+
+// correction_tools/filter.py:14-19 gaussian_high_pass_filter on a uint16 image: scipy.ndimage.gaussian_filter(im, sigma,
+// mode='nearest', truncate) -- three 1-D correlations, double accumulation in scipy's order (centre tap, then the tap pairs
+// from the outermost inwards, products and sums rounded separately), each pass stored as uint16 by truncation -- then
+// im - lowpass where that is positive, 0 elsewhere.  One thread per output, edge clamped ('nearest').
+__global__ void __launch_bounds__(256) k_gauss_nearest(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int L, long long inner, long long n,
+                                                       const double* __restrict__ w, int r) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long c = (t / inner) % L;
+  const uint16_t* line = in + (t - c * inner);
+  double acc = __dmul_rn((double)line[c * inner], w[0]);
+  for (int j = r; j >= 1; --j) {
+    const long long lo = c - j < 0 ? 0 : c - j, hi = c + j > L - 1 ? L - 1 : c + j;
+    acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)line[lo * inner], (double)line[hi * inner]), w[j]));
+  }
+  out[t] = (uint16_t)__double2int_rz(acc);
+}
+
+__global__ void __launch_bounds__(256) k_highpass(uint16_t* __restrict__ im, const uint16_t* __restrict__ low, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const unsigned a = im[t], b = low[t];
+    im[t] = (uint16_t)(a > b ? a - b : 0u);
+  }
 }
 
 constexpr int NPAD = 12;        // scipy.ndimage._interpolation._prepad_for_spline_filter
@@ -301,6 +329,20 @@ __global__ void __launch_bounds__(256) k_warp(const double* __restrict__ coef, i
   }
 }
 
+int launch_highpass(uint16_t* im, uint16_t* bufA, uint16_t* bufB, int Z, int X, int Y, const double* d_w, int r, cudaStream_t st) {
+  const long long n = (long long)Z * X * Y;
+  if (n == 0) return 0;
+  const unsigned g = (unsigned)((n + 255) / 256);
+  k_gauss_nearest<<<g, 256, 0, st>>>(im, bufA, Z, (long long)X * Y, n, d_w, r);
+  IA3_LAUNCH_CHECK();
+  k_gauss_nearest<<<g, 256, 0, st>>>(bufA, bufB, X, (long long)Y, n, d_w, r);
+  IA3_LAUNCH_CHECK();
+  k_gauss_nearest<<<g, 256, 0, st>>>(bufB, bufA, Y, 1, n, d_w, r);
+  IA3_LAUNCH_CHECK();
+  k_highpass<<<148 * 8, 256, 0, st>>>(im, bufA, n);
+  IA3_LAUNCH_CHECK();
+  return 0;
+}
 int launch_zshift(uint16_t* im, long long XY, long long n, const float* d_med_z, float med_all, cudaStream_t st) {
   if (n == 0) return 0;
   k_zshift<<<148 * 8, 256, 0, st>>>(im, XY, n, d_med_z, med_all);

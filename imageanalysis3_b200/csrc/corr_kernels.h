@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 namespace ia3 {
+int launch_highpass(uint16_t* im, uint16_t* bufA, uint16_t* bufB, int Z, int X, int Y, const double* d_w, int r, cudaStream_t st);
 int launch_zshift(uint16_t* im, long long XY, long long n, const float* d_med_z, float med_all, cudaStream_t st);
 int launch_hot_count(const uint16_t* im, int Z, int X, int Y, float hot_th, int* cnt, cudaStream_t st);
 int launch_hot_select(const int* cnt, long long n, double thr, int* out, int* count, int cap, cudaStream_t st);

@@ -9,7 +9,7 @@ to spot_tools.fitting.fit_fov_image without leaving the device (``return_stacks=
 Same signature, argument meaning and error behaviour as the reference.  Branches of the reference that leave this
 path raise NotImplementedError instead of computing something else: calculate_drift with use_autocorr=True (the phase
 correlation of correction_tools/alignment.py align_image needs skimage; its bead-fitting mode, use_autocorr=False, is built),
-gaussian_highpass, normalization and a non-uint16 output_dtype.  ``warp_image=False`` returns, like the
+normalization and a non-uint16 output_dtype.  ``warp_image=False`` returns, like the
 reference, the unwarped images plus one spot-coordinate function per channel (correction_tools/chromatic.py).
 
 One reference behaviour is kept on purpose because results must be the same: the warp code in the reference sits
@@ -174,7 +174,8 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
                          illumination_corr=True, illumination_profile=None,
                          bleed_corr=True, bleed_profile=None,
                          chromatic_ref_channel='647', chromatic_corr=True, chromatic_profile=None,
-                         warp=True, return_stacks=False, drift_from=None):
+                         warp=True, return_stacks=False, drift_from=None,
+                         gaussian_highpass=False, gauss_sigma=3, gauss_truncate=2):
     """The compute core of correct_fov_image on in-memory channel stacks (reference io_tools/load.py:318-459).
 
     ims: one (Z, X, Y) uint16 array (or resident _lib.Stack) per channel of load_channels -> the corrected stacks of
@@ -230,6 +231,9 @@ def correct_image_stacks(ims, load_channels, sel_channels, corr_channels, drift=
                 k = load_channels.index(ch)
                 stacks[k] = stacks[k].warp(drift=drift if drift.any() else None, chroma=pf)
     out = [stacks[load_channels.index(ch)] for ch in sel_channels]
+    if gaussian_highpass:
+        for s in {id(s): s for s in out}.values():          # (the reference filters every loaded channel; only the selected ones are returned)
+            s.gaussian_highpass(gauss_sigma, gauss_truncate)
     return out if return_stacks else [s.fetch() for s in out]
 
 
@@ -276,8 +280,8 @@ def correct_fov_image(dax_filename, sel_channels,
                                   "alignment.align_image), not built; use_autocorr=False (bead fitting on the device) or pass drift=")
     if calculate_drift and str(drift_channel) not in load_channels:
         load_channels.append(str(drift_channel))
-    if gaussian_highpass or normalization:
-        raise NotImplementedError("gaussian_highpass / normalization are not built on the device path")
+    if normalization:
+        raise NotImplementedError("normalization=True (a float32 pipeline end to end) is not built on the device path")
     if np.dtype(output_dtype) != np.dtype(np.uint16):
         raise NotImplementedError("the device corrections produce uint16 stacks (the reference's default output_dtype)")
     if illumination_corr:
@@ -342,7 +346,8 @@ def correct_fov_image(dax_filename, sel_channels,
                                illumination_corr=illumination_corr, illumination_profile=illumination_profile,
                                bleed_corr=bleed_corr, bleed_profile=bleed_profile,
                                chromatic_ref_channel=chromatic_ref_channel, chromatic_corr=chromatic_corr,
-                               chromatic_profile=chromatic_profile, warp=bool(warp_image and (verbose or force_warp)), return_stacks=return_stacks)
+                               chromatic_profile=chromatic_profile, warp=bool(warp_image and (verbose or force_warp)), return_stacks=return_stacks,
+                               gaussian_highpass=gaussian_highpass, gauss_sigma=gauss_sigma, gauss_truncate=gauss_truncate)
     warp_functions = None
     if not warp_image:
         # io_tools/load.py:461-485: the images stay where they are, the spots are moved instead

@@ -79,6 +79,9 @@ int ia3_corr_hot_pixels(ia3_stack* s, double hot_th, double hot_pix_th, int64_t*
 /* corrections.py:479-487 Z_Shift_Correction(im.astype(float32), dtype=uint16), in place: every plane divided by its median and multiplied
  * by the stack's median (float32, numpy's order), truncated to uint16.  io_tools/load.py:336-345. */
 int ia3_corr_zshift(ia3_stack* s);
+/* correction_tools/filter.py:14-19 gaussian_high_pass_filter, in place: im - gaussian_filter(im, sigma, mode='nearest', truncate) where
+ * positive, else 0 (io_tools/load.py:487-497).  w_half: r + 1 taps, centre to edge, of scipy's normalised kernel (radius r = int(truncate * sigma + 0.5)). */
+int ia3_corr_highpass(ia3_stack* s, const double* w_half, int r);
 /* out = illumination(bleed-through(ins)) (io_tools/load.py:347-381): with ``bleed`` (host, n_in x X x Y: row i of the
  * (n, n, X, Y) profile) out = clip(sum_j ins[j] * bleed[j]) truncated to uint16, else out = ins[0]; with ``illum``
  * (host, X x Y) that result is divided by it and truncated again.  profile_f64: the profiles are float64 (numpy then

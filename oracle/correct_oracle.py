@@ -6,6 +6,7 @@ Not part of the product.  Restates, on in-memory channel stacks (file reading st
   bleed-through mixing     io_tools/load.py:347-367
   illumination division    io_tools/load.py:369-381
   drift + chromatic warp   io_tools/load.py:424-459 (scipy.ndimage.map_coordinates, cubic, mode='nearest')
+  Gaussian high pass       correction_tools/filter.py:14-19 (io_tools/load.py:487-497)
 with numpy / scipy.ndimage, the reference's own third-party layer.  Pinned: oracle/make_golden.py runs the unmodified
 reference function (lifted by oracle/ref_loader.load_corrections) on a synthetic .dax and asserts equality.
 """
@@ -34,7 +35,17 @@ def z_shift_correction(im, dtype=np.uint16):
     return (im / np.median(im, axis=(1, 2))[:, np.newaxis, np.newaxis] * np.median(im)).astype(dtype)
 
 
+def gaussian_high_pass(image, sigma=5, truncate=2):
+    """image - gaussian_filter(image, sigma, mode='nearest', truncate) where positive, else 0 (correction_tools/filter.py:14-19)"""
+    from scipy.ndimage import gaussian_filter
+    low = gaussian_filter(image, sigma, mode='nearest', truncate=truncate)
+    high = image - low
+    high[low > image] = 0
+    return high
+
+
 def correct_stacks(ims, load_channels, sel_channels, corr_channels, drift=None, hot_pixel_corr=True, hot_pixel_th=4, z_shift_corr=False,
+                   gaussian_highpass=False, gauss_sigma=3, gauss_truncate=2,
                    illumination_corr=True, illumination_profile=None, bleed_corr=True, bleed_profile=None,
                    chromatic_ref_channel='647', chromatic_corr=True, chromatic_profile=None, warp_image=True,
                    output_dtype=np.uint16, verbose=True):
@@ -69,4 +80,6 @@ def correct_stacks(ims, load_channels, sel_channels, corr_channels, drift=None, 
                 if drift.any():
                     coords = coords - drift[:, np.newaxis, np.newaxis, np.newaxis]
                 ims[load_channels.index(ch)] = map_coordinates(im, coords.reshape(3, -1), mode='nearest').astype(output_dtype).reshape(im.shape)
+    if gaussian_highpass:
+        ims = [gaussian_high_pass(im, gauss_sigma, gauss_truncate) for im in ims]
     return [ims[load_channels.index(ch)].astype(output_dtype).copy() for ch in sel_channels]

@@ -285,6 +285,8 @@ def main_corr():
         "drift_big": (['647'], [11.0, -30.5, 60.25], off, True),    # far beyond the padding: mode='nearest' clamps
         "zshift_only": (['750', '561'], None, {**off, 'z_shift_corr': True}, True),
         "zshift_all": (['750', '647'], drift, {'z_shift_corr': True}, True),
+        "highpass_only": (['750', '561'], None, {**off, 'gaussian_highpass': True}, True),
+        "highpass_all": (['750', '647'], drift, {'gaussian_highpass': True, 'gauss_sigma': 2.2, 'gauss_truncate': 3}, True),
     }
     out = dict(frames=frames, bleed=bleed, meta=np.array(repr(dict(numpy=np.__version__, scipy=scipy.__version__))))
     for ch in chs:

@@ -276,7 +276,8 @@ def _correction_tools_pkg():
 
 def load_chromatic():
     """correction_tools/chromatic.py generate_chromatic_function (:41-114) and generate_polynomial_data (:415-438), lifted:
-    what the reference's correct_fov_image(warp_image=False) imports.  -> namespace with both functions"""
+    what the reference's correct_fov_image(warp_image=False) imports, and correction_tools/filter.py gaussian_high_pass_filter
+    (gaussian_highpass=True).  -> namespace with the three functions"""
     if "chrom" in _cache:
         return _cache["chrom"]
     load()
@@ -287,6 +288,14 @@ def load_chromatic():
     _lift_nodes("correction_tools/chromatic.py", {"generate_chromatic_function", "generate_polynomial_data"}, ch.__dict__)
     ct.chromatic = ch
     sys.modules[_PKG + ".correction_tools.chromatic"] = ch
-    ns = types.SimpleNamespace(generate_chromatic_function=ch.generate_chromatic_function, generate_polynomial_data=ch.generate_polynomial_data)
+    # correction_tools/filter.py:14-19 gaussian_high_pass_filter (its module imports the removed scipy.ndimage.filters namespace)
+    from scipy.ndimage import gaussian_filter
+    fl = types.ModuleType(_PKG + ".correction_tools.filter")
+    fl.__dict__.update(np=np, gaussian_filter=gaussian_filter)
+    _lift_nodes("correction_tools/filter.py", {"gaussian_high_pass_filter"}, fl.__dict__)
+    ct.filter = fl
+    sys.modules[_PKG + ".correction_tools.filter"] = fl
+    ns = types.SimpleNamespace(generate_chromatic_function=ch.generate_chromatic_function, generate_polynomial_data=ch.generate_polynomial_data,
+                               gaussian_high_pass_filter=fl.gaussian_high_pass_filter)
     _cache["chrom"] = ns
     return ns

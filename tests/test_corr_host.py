@@ -104,7 +104,7 @@ def test_argument_errors_follow_the_reference(corr, tmp_path):
         load.correct_fov_image(fn, ['750'], **{**kw, 'bleed_profile': bleed[:2, :2]})
     with pytest.raises(KeyError):
         load.correct_fov_image(fn, ['750'], **{**kw, 'chromatic_profile': {'647': None}})
-    for flag in ('calculate_drift', 'gaussian_highpass', 'normalization'):      # calculate_drift: with the default use_autocorr=True
+    for flag in ('calculate_drift', 'normalization'):      # calculate_drift: with the default use_autocorr=True
         with pytest.raises(NotImplementedError):
             load.correct_fov_image(fn, ['750'], **{**kw, flag: True})
 

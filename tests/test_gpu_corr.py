@@ -92,6 +92,16 @@ def test_each_step_matches_oracle_on_fresh_inputs(lib, shape, seed):
                                     bleed_profile=bleed, chromatic_profile=chrom)
     for ch, a, b in zip(['750', '561'], got, want):
         same_warp(a, b, f"z-shift + everything else, {ch}")
+    # Gaussian high pass: exact uint16 Gaussian with mode='nearest' (several sigmas / truncations, radius up to the plane count and beyond)
+    for sigma, trunc in ((3, 2), (5, 2), (1.3, 4), (4.5, 3)):
+        st = lib.Stack(ims[1])
+        st.gaussian_highpass(sigma, trunc)
+        assert np.array_equal(st.fetch(), correct_oracle.gaussian_high_pass(ims[1], sigma, trunc)), (sigma, trunc)
+    want = correct_oracle.correct_stacks(ims, chs, ['647'], chs, drift=[0.5, 0.5, -0.5], gaussian_highpass=True, illumination_profile=illum,
+                                         bleed_profile=bleed, chromatic_profile=chrom)
+    got = load.correct_image_stacks(ims, chs, ['647'], chs, drift=[0.5, 0.5, -0.5], gaussian_highpass=True, illumination_profile=illum,
+                                    bleed_profile=bleed, chromatic_profile=chrom)
+    same_warp(got[0], want[0], "high pass after the warp")
     # a per-plane chromatic profile (3, Z, X, Y)
     chrom_z = {ch: (rng.standard_normal((3, Z, X, Y)) * 0.5).astype(np.float32) if ch != '647' else None for ch in chs}
     off = dict(hot_pixel_corr=False, bleed_corr=False, illumination_corr=False)
