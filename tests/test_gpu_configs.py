@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_spots_close
-from oracle import fit_oracle, seed_oracle
+from oracle import fit_oracle
 
 pytestmark = pytest.mark.gpu
 PROCS = min(32, os.cpu_count() or 1)

@@ -24,7 +24,6 @@ def main():
         print(f"rep {rep}: align_image on the device path {1e3 * (time.perf_counter() - t0):.1f} ms -> drift {np.round(d, 4)} flag {flag} (planted {drift})", flush=True)
     if "--cpu" in sys.argv:
         from oracle import fit_oracle
-        from imageanalysis3_b200 import spot_tools
         import imageanalysis3_b200.spot_tools.fitting as fitting
         crops = alignment.generate_drift_crops(list(shape))
         t0 = time.perf_counter()

@@ -19,7 +19,7 @@ shape, n, seed, hr = (60, 2048, 2048), 50000, 4, (400.0, 3000.0)
 if len(sys.argv) > 3 and sys.argv[3] == "small":
     shape, n = (60, 1024, 1024), 12500
 if mode == "oracle":
-    from oracle import fit_oracle, seed_oracle
+    from oracle import seed_oracle
     im = synth(shape, n, seed, h_range=hr)
     seeds = seed_oracle.get_seeds_oracle(im, th_seed=300.0, backend="c")
     t0 = time.perf_counter()
